@@ -1,0 +1,183 @@
+/* trajgen.h -- C ABI of libtrajgen.so: batched closed-loop MPC trajectory generation on B200 (sm_100a).
+ *
+ * Drop-in boundary for ONE hot path of DorianaG01/trajectory_generation (paths below are relative to
+ * the reference root).  The reference has no FFI of its own: the path is plain Python,
+ *   MPC/mpc_6stati.py:120-275  mpc_step(x0, u_prev, path_ref, Ts, N, params, q_c, q_phi, q_vx, R, Rd,
+ *                                       vref, u_bounds, du_bounds, x_lo, x_hi, solver, verbose)
+ *                               -> (u_cmd[2], status:str, info:dict)
+ *   MPC/main.py:85-101          the closed loop that calls it and integrates the plant
+ *   generation_traj/generation_type{1,2}.py  the dataset shell (x0, clipping, noise, CSV rows)
+ * so the entry points here are what a ctypes binding of that path needs (INTEGRATION.md shows the stub).
+ *
+ * Conventions: plain pointers and sizes, no framework types.  Functions without a suffix take DEVICE
+ * pointers and enqueue on the handle's stream (asynchronous); *_host functions take HOST pointers and
+ * return after the results are in the caller's buffers.  All arrays are C-contiguous fp64 unless noted,
+ * one contiguous block per problem ("[B][6]" = B rows of 6).  Return value: 0 = ok, <0 = error
+ * (tg_last_error() gives the message).  A handle is bound to one device and one stream and is not
+ * thread-safe; use one handle per thread/stream.
+ */
+#ifndef TRAJGEN_H
+#define TRAJGEN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_VERSION 100
+
+/* error codes */
+#define TG_OK 0
+#define TG_ERR_INVALID (-1)      /* bad argument / config */
+#define TG_ERR_UNSUPPORTED (-2)  /* horizon / state-bound rows do not fit the kernel's shared memory */
+#define TG_ERR_CUDA (-3)         /* CUDA runtime error */
+#define TG_ERR_NOMEM (-4)
+
+/* per-problem solver status (mpc_step's status strings, MPC/mpc_6stati.py:257-262) */
+#define TG_STATUS_OPTIMAL 0            /* "optimal" */
+#define TG_STATUS_OPTIMAL_INACCURATE 1 /* "optimal_inaccurate" (accepted, :261) */
+#define TG_STATUS_INFEASIBLE 2         /* "infeasible"  -> u_cmd = u_prev */
+#define TG_STATUS_UNBOUNDED 3          /* "unbounded"   (cannot occur: R > 0; kept for the mapping) */
+#define TG_STATUS_USER_LIMIT 4         /* "user_limit"  (max_iter reached) -> u_cmd = u_prev */
+#define TG_STATUS_NAN 5                /* "Solver Error: ..." (non-finite data) -> u_cmd = u_prev */
+#define TG_NUM_STATUS 6
+
+/* dynamics variants */
+#define TG_MODEL_MPC 0   /* MPC/mpc_6stati.py:25-71 */
+#define TG_MODEL_GEN1 1  /* generation_traj/generation_type1.py:38-68 */
+#define TG_MODEL_GEN2 2  /* generation_traj/generation_type2.py:52-86 */
+/* plant post-step clipping: MPC/main.py:97 has none; generation_type1.py:81-82 / type2:186-187 clip */
+#define TG_PLANT_MPC 0   /* MPC model, no clipping */
+#define TG_PLANT_GEN1 1  /* gen1 model + vx>=0, |omega|<=6 */
+#define TG_PLANT_GEN2 2  /* gen2 model + vx>=0, |omega|<=6 */
+
+#define TG_JAC_ANALYTIC 0 /* closed-form Jacobians of f_cont */
+#define TG_JAC_FD 1       /* central differences eps=1e-5, MPC/mpc_6stati.py:73-97 verbatim */
+
+/* reference path kinds (MPC/main.py:64-66, MPC/README.md:68-76) */
+#define TG_PATH_PARABOLA 0 /* y = p0 x^2 + p1 x + p2 */
+#define TG_PATH_SINE 1     /* y = p0 sin(p1 x + p2) + p3 */
+#define TG_PATH_SPLINE 2   /* piecewise cubic y(x): breaks/coef table, scipy PPoly layout */
+/* velocity-reference kinds (MPC/mpc_6stati.py:158-163, MPC/main.py:28-47) */
+#define TG_VREF_HOLD 0      /* vref=None -> x0[3] */
+#define TG_VREF_CONST 1     /* v[0] */
+#define TG_VREF_RAMP 2      /* v0=v[0], v_cruise=v[1], tramp=v[2] */
+#define TG_VREF_TRAPEZOID 3 /* v0, vmax, t_acc, t_flat, t_dec */
+#define TG_VREF_SINE 4      /* v_mean, v_amp, period_s */
+
+#define TG_INF 1e20
+
+/* Order of params[]: Cm1 Cm2 Cr0 Cr2 Br Cr Dr Bf Cf Df m Iz lf lr g maxAlpha vx_zero (MPC/mpc_6stati.py:9-19) */
+#define TG_NPARAMS 17
+
+typedef struct tg_config {
+    int32_t N;               /* horizon (mpc_step N=20; MPC/main.py uses 40) */
+    int32_t model;           /* TG_MODEL_* used by the controller's linearisation */
+    int32_t plant;           /* TG_PLANT_* used by tg_closed_loop */
+    int32_t jacobian;        /* TG_JAC_* */
+    double Ts;
+    double params[TG_NPARAMS];
+    double q_c, q_phi, q_vx; /* MPC/mpc_6stati.py:128-130 */
+    double R[4], Rd[4];      /* row-major 2x2, :131-132 (symmetric part is used, like cp.quad_form) */
+    double u_lo[2], u_hi[2];   /* :135-136 */
+    double du_lo[2], du_hi[2]; /* :137-138 */
+    double x_lo[6], x_hi[6];   /* :139-140; <= -TG_INF / >= TG_INF = absent */
+    /* ADMM (OSQP-style) settings */
+    double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, adaptive_rho_tol;
+    int32_t max_iter, check_every, adaptive_rho, adaptive_rho_min_iter;
+    int32_t warm_start;      /* closed loop: shift-warm-start across steps; step API: keep per-problem state */
+    int32_t vref_advance;    /* 0 = the reference's behaviour (window never advances, MPC/main.py:87) */
+    /* sensor noise (generation_type1.py:25-32,255) */
+    double noise_std[6];
+    uint64_t noise_seed_base;
+    int32_t threads_per_problem; /* 0 = choose from N */
+    int32_t reserved;
+} tg_config;
+
+/* one reference scenario per trajectory (closed loop) */
+typedef struct tg_ref_spec {
+    int32_t path_kind;
+    int32_t vref_kind;
+    int32_t spline_first;  /* first piece of this trajectory in the spline tables */
+    int32_t spline_count;  /* number of pieces K: spl_breaks[first+i] = start of piece i, spl_coef[first+i][4] =
+                              (c0,c1,c2,c3) of y = ((c0 dx + c1) dx + c2) dx + c3, dx = x - start; either end extrapolates
+                              its end piece (scipy PPoly behaviour) */
+    double path[4];
+    double vref[6];
+} tg_ref_spec;
+
+typedef struct tg_handle tg_handle;
+
+const char *tg_last_error(void);
+int tg_version(void);
+void tg_default_config(tg_config *cfg); /* mpc_step's defaults (N=20, Ts=0.02, weights, bounds) + OSQP-like solver settings */
+
+int tg_create(const tg_config *cfg, int device, tg_handle **out);
+int tg_destroy(tg_handle *h);
+int tg_set_stream(tg_handle *h, void *cuda_stream);
+int tg_synchronize(tg_handle *h);
+int tg_kernel_launches(tg_handle *h, int64_t *count); /* kernels launched through this handle so far */
+
+/* K1 tap -- replaces MPC/mpc_6stati.py:165-178 (rollout + N x linearize_discretize).
+ * x0[B][6], u_prev[B][2] -> A[B][N][6][6], Bm[B][N][6][2], g[B][N][6], xbar[B][N+1][6] (any output may be NULL) */
+int tg_linearize(tg_handle *h, int B, const double *x0, const double *u_prev,
+                 double *A, double *Bm, double *g, double *xbar);
+
+/* K2 tap -- condensed form of the QP of MPC/mpc_6stati.py:180-252 in dU = U - u_prev:
+ * min 1/2 dU'H dU + q'dU + c0,  l <= [I; D; Gs] dU <= u.   H[B][n][n], q[B][n], c0[B], l/u[B][m], Gs[B][ms][n]
+ * with n = 2N, m = 4N + ms, ms = (#bounded states) * N.  Outputs may be NULL. */
+int tg_assemble(tg_handle *h, int B, const double *x0, const double *u_prev, const double *path_ref,
+                const double *vref, double *H, double *q, double *c0, double *l, double *u, double *Gs);
+
+/* K1+K2+K3 -- replaces mpc_step (MPC/mpc_6stati.py:120-275), batched.
+ * x0[B][6], u_prev[B][2], path_ref[B][N+1][3], vref[B][N+1] (NULL = hold x0[3], :158-159)
+ * -> u_cmd[B][2], status[B], iters[B], objective[B], U_opt[B][N][2], X_opt[B][N+1][6], y_opt[B][m] (optional outputs may be NULL) */
+int tg_mpc_step(tg_handle *h, int B, const double *x0, const double *u_prev, const double *path_ref,
+                const double *vref, double *u_cmd, int32_t *status, int32_t *iters, double *objective,
+                double *U_opt, double *X_opt, double *y_opt);
+int tg_mpc_step_host(tg_handle *h, int B, const double *x0, const double *u_prev, const double *path_ref,
+                     const double *vref, double *u_cmd, int32_t *status, int32_t *iters, double *objective,
+                     double *U_opt, double *X_opt, double *y_opt);
+
+/* a10 tap -- MPC/main.py:28-47,51-68: reference window for the current state.
+ * x0[B][6], spec[B], step index t -> path_ref[B][N+1][3], vref[B][N+1] */
+int tg_ref_window(tg_handle *h, int B, const double *x0, const tg_ref_spec *spec, const double *spl_breaks,
+                  const double *spl_coef, int t_index, double *path_ref, double *vref);
+
+/* fused K1..K4 -- replaces the loop MPC/main.py:85-101 plus the dataset shell
+ * (generation_type2.py:180-200): T closed-loop steps for B trajectories.
+ * x0[B][6], u0[B][2], spec[B], spline tables (may be NULL), traj_id0 = global id of trajectory 0 of this batch
+ * -> clean[B][T+1][6] (row 0 = x0), noisy[B][T+1][6], U[B][T][2], status_counts[B][TG_NUM_STATUS], iters_total[B] */
+int tg_closed_loop(tg_handle *h, int B, int T, const double *x0, const double *u0, const tg_ref_spec *spec,
+                   const double *spl_breaks, const double *spl_coef, int64_t traj_id0, double *clean,
+                   double *noisy, double *U, int32_t *status_counts, int64_t *iters_total);
+int tg_closed_loop_host(tg_handle *h, int B, int T, const double *x0, const double *u0, const tg_ref_spec *spec,
+                        const double *spl_breaks, int64_t n_breaks, const double *spl_coef, int64_t n_coef,
+                        int64_t traj_id0, double *clean, double *noisy, double *U, int32_t *status_counts,
+                        int64_t *iters_total);
+
+/* K4 taps -- plant + noise.  tg_plant_rollout: open-loop Euler integration with the configured plant
+ * (generation_type1.py:70-84): x0[B][6], U[B][T][2] -> X[B][T+1][6].
+ * tg_sensor_noise: standard normals [n_traj][n_rows][6] for seeds seed_base + traj_id0 + i (Philox4x32-10).
+ * tg_philox_u32: raw stream, out[n][4] = philox(ctr=(first+i, block, 0, 0), key=seed). */
+int tg_plant_rollout(tg_handle *h, int B, int T, const double *x0, const double *U, double *X);
+int tg_sensor_noise(tg_handle *h, int64_t traj_id0, int n_traj, int n_rows, double *out);
+int tg_philox_u32(tg_handle *h, uint64_t seed, uint32_t first, uint32_t block, int n, uint32_t *out);
+
+/* measured FMA peak of this GPU (roofline denominator): TFLOP/s for dtype 0 = fp64, 1 = fp32 */
+int tg_fma_peak(tg_handle *h, int dtype, double *tflops);
+
+/* host<->device helpers so a ctypes caller needs no other CUDA binding */
+int tg_device_count(int *n);
+int tg_malloc(void **dptr, int64_t bytes);
+int tg_free(void *dptr);
+int tg_memcpy_h2d(tg_handle *h, void *dst, const void *src, int64_t bytes);
+int tg_memcpy_d2h(tg_handle *h, void *dst, const void *src, int64_t bytes);
+int tg_malloc_host(void **hptr, int64_t bytes); /* pinned */
+int tg_free_host(void *hptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAJGEN_H */

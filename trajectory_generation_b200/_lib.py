@@ -1,0 +1,152 @@
+"""ctypes binding of libtrajgen.so (include/trajgen.h).  No CPU fallback: if the library is missing
+or no B200 is visible, the first use raises."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtrajgen.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "--shared", "-Xcompiler", "-fPIC"]
+
+TG_INF = 1e20
+TG_NPARAMS = 17
+TG_NUM_STATUS = 6
+PARAM_ORDER = ("Cm1", "Cm2", "Cr0", "Cr2", "Br", "Cr", "Dr", "Bf", "Cf", "Df", "m", "Iz", "lf", "lr", "g",
+               "maxAlpha", "vx_zero")
+# mpc_step's status strings (MPC/mpc_6stati.py:257-262)
+STATUS_STRINGS = ("optimal", "optimal_inaccurate", "infeasible", "unbounded", "user_limit", "Solver Error: NonFinite")
+ACCEPTED = (0, 1)
+
+d, i32, i64, u64, vp = ctypes.c_double, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_void_p
+
+
+class TgConfig(ctypes.Structure):
+    _fields_ = [
+        ("N", i32), ("model", i32), ("plant", i32), ("jacobian", i32),
+        ("Ts", d), ("params", d * TG_NPARAMS),
+        ("q_c", d), ("q_phi", d), ("q_vx", d), ("R", d * 4), ("Rd", d * 4),
+        ("u_lo", d * 2), ("u_hi", d * 2), ("du_lo", d * 2), ("du_hi", d * 2),
+        ("x_lo", d * 6), ("x_hi", d * 6),
+        ("rho", d), ("sigma", d), ("alpha", d), ("eps_abs", d), ("eps_rel", d), ("eps_prim_inf", d),
+        ("adaptive_rho_tol", d),
+        ("max_iter", i32), ("check_every", i32), ("adaptive_rho", i32), ("adaptive_rho_min_iter", i32),
+        ("warm_start", i32), ("vref_advance", i32),
+        ("noise_std", d * 6), ("noise_seed_base", u64),
+        ("threads_per_problem", i32), ("reserved", i32),
+    ]
+
+
+REF_SPEC_DTYPE = np.dtype([("path_kind", np.int32), ("vref_kind", np.int32), ("spline_first", np.int32),
+                           ("spline_count", np.int32), ("path", np.float64, 4), ("vref", np.float64, 6)], align=True)
+assert REF_SPEC_DTYPE.itemsize == 96
+
+# every symbol include/trajgen.h declares
+EXPORTS = (
+    "tg_last_error", "tg_version", "tg_default_config", "tg_create", "tg_destroy", "tg_set_stream", "tg_synchronize",
+    "tg_kernel_launches", "tg_linearize", "tg_assemble", "tg_mpc_step", "tg_mpc_step_host", "tg_ref_window",
+    "tg_closed_loop", "tg_closed_loop_host", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
+    "tg_device_count", "tg_malloc", "tg_free", "tg_memcpy_h2d", "tg_memcpy_d2h", "tg_malloc_host", "tg_free_host",
+)
+
+_lib = None
+
+
+class TrajgenError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> libtrajgen.so (in-tree)."""
+    src = os.path.join(CSRC, "trajgen.cu")
+    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    deps.append(os.path.join(_HERE, "..", "include", "trajgen.h"))
+    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(p) for p in deps):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, src]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TrajgenError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    L.tg_last_error.restype = ctypes.c_char_p
+    L.tg_default_config.argtypes = [ctypes.POINTER(TgConfig)]
+    L.tg_default_config.restype = None
+    L.tg_create.argtypes = [ctypes.POINTER(TgConfig), ctypes.c_int, ctypes.POINTER(vp)]
+    L.tg_destroy.argtypes = [vp]
+    L.tg_set_stream.argtypes = [vp, vp]
+    L.tg_synchronize.argtypes = [vp]
+    L.tg_kernel_launches.argtypes = [vp, ctypes.POINTER(i64)]
+    L.tg_linearize.argtypes = [vp, ctypes.c_int] + [vp] * 6
+    L.tg_assemble.argtypes = [vp, ctypes.c_int] + [vp] * 10
+    L.tg_mpc_step.argtypes = [vp, ctypes.c_int] + [vp] * 11
+    L.tg_mpc_step_host.argtypes = [vp, ctypes.c_int] + [vp] * 11
+    L.tg_ref_window.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp, vp]
+    L.tg_closed_loop.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+    L.tg_closed_loop_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, vp]
+    L.tg_plant_rollout.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
+    L.tg_sensor_noise.argtypes = [vp, i64, ctypes.c_int, ctypes.c_int, vp]
+    L.tg_philox_u32.argtypes = [vp, u64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, vp]
+    L.tg_fma_peak.argtypes = [vp, ctypes.c_int, ctypes.POINTER(d)]
+    L.tg_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
+    L.tg_malloc.argtypes = [ctypes.POINTER(vp), i64]
+    L.tg_free.argtypes = [vp]
+    L.tg_memcpy_h2d.argtypes = [vp, vp, vp, i64]
+    L.tg_memcpy_d2h.argtypes = [vp, vp, vp, i64]
+    L.tg_malloc_host.argtypes = [ctypes.POINTER(vp), i64]
+    L.tg_free_host.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise TrajgenError(f"libtrajgen error {rc}: {load().tg_last_error().decode()}")
+
+
+def default_config():
+    cfg = TgConfig()
+    load().tg_default_config(ctypes.byref(cfg))
+    return cfg
+
+
+def ptr(a):
+    """host pointer of a C-contiguous numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+class DeviceBuffer:
+    """A cudaMalloc'ed block owned by Python (used by tests / bench to keep data resident in HBM)."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        p = vp()
+        check(load().tg_malloc(ctypes.byref(p), self.nbytes))
+        self.ptr = p.value
+
+    def free(self):
+        if self.ptr:
+            load().tg_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

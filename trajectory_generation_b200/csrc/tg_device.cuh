@@ -1,0 +1,385 @@
+// tg_device.cuh -- device-side building blocks: vehicle model, analytic/FD linearisation,
+// reference windows, Philox4x32-10 sensor noise.  sm_100a, fp64.
+//
+// Reference (paths relative to the reference root):
+//   tire_forces / f_cont        MPC/mpc_6stati.py:25-71, generation_type1.py:38-68, generation_type2.py:52-86
+//   numerical_jacobian          MPC/mpc_6stati.py:73-97
+//   linearize_discretize        MPC/mpc_6stati.py:99-109
+//   vref profiles / ref window  MPC/main.py:28-47, 51-68 ; MPC/README.md:68-76
+//   plant clipping              generation_type1.py:81-82, generation_type2.py:186-187
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/trajgen.h"
+
+#define TG_LIN 28  // compact per-stage linearisation record (see lin_store)
+
+struct DevCfg {
+    int N, n;         // horizon, 2N
+    int model, plant, jacobian;
+    int ns;           // number of state components with a finite bound
+    int sidx[6];      // their indices
+    int ms, m;        // ns*N state rows, 4N + ms rows in total
+    int NP;           // padded matrix width S*SEG
+    int max_iter, check_every, adaptive_rho, adaptive_rho_min_iter, warm_start, vref_advance;
+    double Ts;
+    double p[TG_NPARAMS];
+    double q_c, q_phi, q_vx;
+    double Rs[4], Rds[4];  // symmetric parts
+    double u_lo[2], u_hi[2], du_lo[2], du_hi[2], x_lo[6], x_hi[6];
+    double rho, sigma, alpha, eps_abs, eps_rel, eps_pinf, adapt_tol;
+    double noise_std[6];
+    unsigned long long seed_base;
+};
+
+enum { P_Cm1 = 0, P_Cm2, P_Cr0, P_Cr2, P_Br, P_Cr, P_Dr, P_Bf, P_Cf, P_Df, P_m, P_Iz, P_lf, P_lr, P_g, P_maxAlpha, P_vx_zero };
+
+__device__ __forceinline__ double tg_clamp(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+// ------------------------------------------------------------------------------------------------
+// f_cont: continuous-time dynamics, all three variants.  sd/cd = sin/cos(delta) are passed in because
+// the controller evaluates the whole horizon at the same delta (ubar_k = u_prev, mpc_6stati.py:170).
+__device__ __forceinline__ void tg_f_cont(const double *__restrict__ p, int variant, const double x[6], double d,
+                                          double delta, double sd, double cd, double f[6])
+{
+    const double phi = x[2], vx = x[3], vy = x[4], om = x[5];
+    const double vmag = fmax(fabs(vx), p[P_vx_zero]);
+    double vx_eff;
+    if (variant == TG_MODEL_MPC) {
+        const double sgn = (double)((vx > 0.0) - (vx < 0.0));  // np.sign: sign(0) = 0  (:33)
+        vx_eff = sgn * vmag;
+    } else {
+        vx_eff = vmag;  // generation_type1.py:41
+    }
+    double af = -atan2(om * p[P_lf] + vy, vx_eff) + delta;
+    double ar = atan2(om * p[P_lr] - vy, vx_eff);
+    af = tg_clamp(af, -p[P_maxAlpha], p[P_maxAlpha]);
+    if (variant != TG_MODEL_GEN1) ar = tg_clamp(ar, -p[P_maxAlpha], p[P_maxAlpha]);  // gen1 leaves alpha_r free (:46)
+    const double Fyf = p[P_Df] * sin(p[P_Cf] * atan(p[P_Bf] * af));
+    const double Fyr = p[P_Dr] * sin(p[P_Cr] * atan(p[P_Br] * ar));
+    const double vl = (variant == TG_MODEL_MPC) ? vx : vx_eff;  // :51 vs generation_type1.py:53
+    const double Frx = (p[P_Cm1] - p[P_Cm2] * vl) * d - p[P_Cr0] - p[P_Cr2] * (vl * vl);
+    double sp, cp;
+    sincos(phi, &sp, &cp);
+    const double m = p[P_m], Iz = p[P_Iz];
+    f[0] = vx * cp - vy * sp;
+    f[1] = vx * sp + vy * cp;
+    f[2] = om;
+    if (variant == TG_MODEL_MPC) {
+        f[3] = (1.0 / m) * (Frx - Fyf * sd + m * vy * om);
+        f[4] = (1.0 / m) * (Fyr + Fyf * cd - m * vx * om);
+        f[5] = (1.0 / Iz) * (Fyf * p[P_lf] * cd - Fyr * p[P_lr]);
+    } else {
+        f[3] = (Frx - Fyf * sd + m * vy * om) / m;
+        f[4] = (Fyr + Fyf * cd - m * vx * om) / m;
+        f[5] = (Fyf * p[P_lf] * cd - Fyr * p[P_lr]) / Iz;
+    }
+}
+
+// plant step: x <- x + Ts f(x,u) (+ clipping for the generator plants)
+__device__ __forceinline__ void tg_plant_step(const DevCfg &c, double x[6], double d, double delta)
+{
+    double sd, cd, f[6];
+    sincos(delta, &sd, &cd);
+    tg_f_cont(c.p, c.plant, x, d, delta, sd, cd, f);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = x[i] + c.Ts * f[i];
+    if (c.plant != TG_PLANT_MPC) {
+        x[3] = fmax(x[3], 0.0);
+        x[5] = tg_clamp(x[5], -6.0, 6.0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compact linearisation record of one stage.  For every variant and both Jacobian modes the full
+// 6x6 / 6x2 matrices have this sparsity exactly (f does not depend on X,Y; phi enters rows 0,1 only;
+// rows 0-2 do not depend on u), so nothing is lost:
+//   [0..2]  A[0][2],A[0][3],A[0][4]   [3..5] A[1][2],A[1][3],A[1][4]   [6] A[2][5]
+//   [7..15] A[3..5][3..5] row-major   [16..21] B[3..5][0..1] row-major [22..27] g[0..5]
+//   A[i][i] = 1 for i<3, everything else 0.
+__device__ __forceinline__ void tg_lin_expand(const double *__restrict__ r, double *A, double *Bm, double *g)
+{
+    if (A) {
+        for (int i = 0; i < 36; ++i) A[i] = 0.0;
+        A[0] = 1.0; A[7] = 1.0; A[14] = 1.0;
+        A[2] = r[0]; A[3] = r[1]; A[4] = r[2];
+        A[8] = r[3]; A[9] = r[4]; A[10] = r[5];
+        A[17] = r[6];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) A[(3 + i) * 6 + 3 + j] = r[7 + 3 * i + j];
+    }
+    if (Bm) {
+        for (int i = 0; i < 6; ++i) Bm[i] = 0.0;
+        for (int i = 0; i < 6; ++i) Bm[6 + i] = r[16 + i];
+    }
+    if (g)
+        for (int i = 0; i < 6; ++i) g[i] = r[22 + i];
+}
+
+// Analytic linearisation at (x, u): Ad = I + Ts df/dx, Bd = Ts df/du, g = Ts (f - Jx x - Ju u).
+__device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double d, double delta, double sd,
+                                      double cd, double *__restrict__ rec)
+{
+    const double *p = c.p;
+    const int variant = c.model;
+    const double phi = x[2], vx = x[3], vy = x[4], om = x[5];
+    const double lf = p[P_lf], lr = p[P_lr], m = p[P_m], Iz = p[P_Iz], ma = p[P_maxAlpha];
+    const double avx = fabs(vx);
+    const double vmag = fmax(avx, p[P_vx_zero]);
+    const double sgn = (double)((vx > 0.0) - (vx < 0.0));
+    const bool free_v = avx > p[P_vx_zero];
+    double vx_eff, dveff;  // d vx_eff / d vx
+    if (variant == TG_MODEL_MPC) { vx_eff = sgn * vmag; dveff = free_v ? 1.0 : 0.0; }
+    else                         { vx_eff = vmag;       dveff = free_v ? sgn : 0.0; }
+    const double nf = om * lf + vy, nr = om * lr - vy;
+    const double denf = nf * nf + vx_eff * vx_eff, denr = nr * nr + vx_eff * vx_eff;
+    double af = -atan2(nf, vx_eff) + delta;
+    double ar = atan2(nr, vx_eff);
+    // partials of the slip angles (zero where the clamp is active)
+    double af_vx = (nf / denf) * dveff, af_vy = -vx_eff / denf, af_om = -lf * vx_eff / denf, af_de = 1.0;
+    double ar_vx = -(nr / denr) * dveff, ar_vy = -vx_eff / denr, ar_om = lr * vx_eff / denr;
+    if (af > ma || af < -ma) { af = tg_clamp(af, -ma, ma); af_vx = af_vy = af_om = af_de = 0.0; }
+    if (variant != TG_MODEL_GEN1 && (ar > ma || ar < -ma)) { ar = tg_clamp(ar, -ma, ma); ar_vx = ar_vy = ar_om = 0.0; }
+    double s1, c1, s2, c2;
+    const double Bf = p[P_Bf], Br = p[P_Br];
+    sincos(p[P_Cf] * atan(Bf * af), &s1, &c1);
+    sincos(p[P_Cr] * atan(Br * ar), &s2, &c2);
+    const double Fyf = p[P_Df] * s1, Fyr = p[P_Dr] * s2;
+    const double dFf = p[P_Df] * c1 * p[P_Cf] * Bf / (1.0 + (Bf * af) * (Bf * af));  // dFyf / d alpha_f
+    const double dFr = p[P_Dr] * c2 * p[P_Cr] * Br / (1.0 + (Br * ar) * (Br * ar));
+    const double Ff_vx = dFf * af_vx, Ff_vy = dFf * af_vy, Ff_om = dFf * af_om, Ff_de = dFf * af_de;
+    const double Fr_vx = dFr * ar_vx, Fr_vy = dFr * ar_vy, Fr_om = dFr * ar_om;
+    double vl, dvl;
+    if (variant == TG_MODEL_MPC) { vl = vx; dvl = 1.0; } else { vl = vx_eff; dvl = dveff; }
+    const double Frx = (p[P_Cm1] - p[P_Cm2] * vl) * d - p[P_Cr0] - p[P_Cr2] * (vl * vl);
+    const double Frx_vx = (-p[P_Cm2] * d - 2.0 * p[P_Cr2] * vl) * dvl;
+    const double Frx_d = p[P_Cm1] - p[P_Cm2] * vl;
+    double sp, cp;
+    sincos(phi, &sp, &cp);
+    double f[6];
+    f[0] = vx * cp - vy * sp;
+    f[1] = vx * sp + vy * cp;
+    f[2] = om;
+    f[3] = (Frx - Fyf * sd + m * vy * om) / m;
+    f[4] = (Fyr + Fyf * cd - m * vx * om) / m;
+    f[5] = (Fyf * lf * cd - Fyr * lr) / Iz;
+    // continuous Jacobian entries (rows 3..5)
+    const double j33 = (Frx_vx - Ff_vx * sd) / m, j34 = (-Ff_vy * sd + m * om) / m, j35 = (-Ff_om * sd + m * vy) / m;
+    const double j43 = (Fr_vx + Ff_vx * cd - m * om) / m, j44 = (Fr_vy + Ff_vy * cd) / m, j45 = (Fr_om + Ff_om * cd - m * vx) / m;
+    const double j53 = (Ff_vx * lf * cd - Fr_vx * lr) / Iz, j54 = (Ff_vy * lf * cd - Fr_vy * lr) / Iz,
+                 j55 = (Ff_om * lf * cd - Fr_om * lr) / Iz;
+    const double b30 = Frx_d / m, b31 = (-Ff_de * sd - Fyf * cd) / m;
+    const double b41 = (Ff_de * cd - Fyf * sd) / m;
+    const double b51 = (Ff_de * lf * cd - Fyf * lf * sd) / Iz;
+    const double Ts = c.Ts;
+    rec[0] = -Ts * f[1]; rec[1] = Ts * cp; rec[2] = -Ts * sp;
+    rec[3] = Ts * f[0];  rec[4] = Ts * sp; rec[5] = Ts * cp;
+    rec[6] = Ts;
+    rec[7] = 1.0 + Ts * j33; rec[8] = Ts * j34;        rec[9] = Ts * j35;
+    rec[10] = Ts * j43;      rec[11] = 1.0 + Ts * j44; rec[12] = Ts * j45;
+    rec[13] = Ts * j53;      rec[14] = Ts * j54;       rec[15] = 1.0 + Ts * j55;
+    rec[16] = Ts * b30; rec[17] = Ts * b31;
+    rec[18] = 0.0;      rec[19] = Ts * b41;
+    rec[20] = 0.0;      rec[21] = Ts * b51;
+    // g = x + Ts f - Ad x - Bd u = Ts f - (Ad - I) x - Bd u
+    rec[22] = Ts * f[0] - (rec[0] * phi + rec[1] * vx + rec[2] * vy);
+    rec[23] = Ts * f[1] - (rec[3] * phi + rec[4] * vx + rec[5] * vy);
+    rec[24] = Ts * f[2] - rec[6] * om;
+    rec[25] = Ts * f[3] - (Ts * j33 * vx + Ts * j34 * vy + Ts * j35 * om) - (rec[16] * d + rec[17] * delta);
+    rec[26] = Ts * f[4] - (Ts * j43 * vx + Ts * j44 * vy + Ts * j45 * om) - (rec[19] * delta);
+    rec[27] = Ts * f[5] - (Ts * j53 * vx + Ts * j54 * vy + Ts * j55 * om) - (rec[21] * delta);
+}
+
+// Central-difference linearisation, the reference's arithmetic verbatim (mpc_6stati.py:73-109):
+// 12 + 4 + 1 evaluations of f_cont, eps = 1e-5, g = xbar + Ts f - Ad xbar - Bd ubar.
+__device__ void tg_linearize_fd(const DevCfg &c, const double x[6], double d, double delta, double *__restrict__ rec)
+{
+    const double eps = 1e-5;
+    double Jx[6][6], Ju[6][2], f0[6], fp[6], fm[6], xx[6];
+    double sd, cd;
+    sincos(delta, &sd, &cd);
+    for (int i = 0; i < 6; ++i) {
+        for (int j = 0; j < 6; ++j) xx[j] = x[j];
+        xx[i] = x[i] + eps;
+        tg_f_cont(c.p, c.model, xx, d, delta, sd, cd, fp);
+        xx[i] = x[i] - eps;
+        tg_f_cont(c.p, c.model, xx, d, delta, sd, cd, fm);
+        for (int r = 0; r < 6; ++r) Jx[r][i] = (fp[r] - fm[r]) / (2.0 * eps);
+    }
+    tg_f_cont(c.p, c.model, x, d + eps, delta, sd, cd, fp);
+    tg_f_cont(c.p, c.model, x, d - eps, delta, sd, cd, fm);
+    for (int r = 0; r < 6; ++r) Ju[r][0] = (fp[r] - fm[r]) / (2.0 * eps);
+    {
+        double s2, c2;
+        sincos(delta + eps, &s2, &c2);
+        tg_f_cont(c.p, c.model, x, d, delta + eps, s2, c2, fp);
+        sincos(delta - eps, &s2, &c2);
+        tg_f_cont(c.p, c.model, x, d, delta - eps, s2, c2, fm);
+        for (int r = 0; r < 6; ++r) Ju[r][1] = (fp[r] - fm[r]) / (2.0 * eps);
+    }
+    tg_f_cont(c.p, c.model, x, d, delta, sd, cd, f0);
+    const double Ts = c.Ts;
+    double Ad[6][6], Bd[6][2], g[6];
+    for (int r = 0; r < 6; ++r) {
+        for (int j = 0; j < 6; ++j) Ad[r][j] = ((r == j) ? 1.0 : 0.0) + Ts * Jx[r][j];
+        Bd[r][0] = Ts * Ju[r][0];
+        Bd[r][1] = Ts * Ju[r][1];
+    }
+    for (int r = 0; r < 6; ++r) {
+        double ax = 0.0;
+        for (int j = 0; j < 6; ++j) ax += Ad[r][j] * x[j];
+        g[r] = x[r] + Ts * f0[r] - ax - (Bd[r][0] * d + Bd[r][1] * delta);
+    }
+    rec[0] = Ad[0][2]; rec[1] = Ad[0][3]; rec[2] = Ad[0][4];
+    rec[3] = Ad[1][2]; rec[4] = Ad[1][3]; rec[5] = Ad[1][4];
+    rec[6] = Ad[2][5];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) rec[7 + 3 * i + j] = Ad[3 + i][3 + j];
+    for (int i = 0; i < 3; ++i) { rec[16 + 2 * i] = Bd[3 + i][0]; rec[17 + 2 * i] = Bd[3 + i][1]; }
+    for (int i = 0; i < 6; ++i) rec[22 + i] = g[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reference generators (MPC/main.py:28-47, 51-68)
+__device__ __forceinline__ double tg_vref_at(int kind, const double *__restrict__ v, double t, double vx0)
+{
+    switch (kind) {
+        case TG_VREF_HOLD: return vx0;
+        case TG_VREF_CONST: return v[0];
+        case TG_VREF_RAMP: return v[0] + (v[1] - v[0]) * tg_clamp(t / v[2], 0.0, 1.0);
+        case TG_VREF_TRAPEZOID: {
+            const double v0 = v[0], vmax = v[1], t_acc = v[2], t_flat = v[3], t_dec = v[4];
+            double r = (t <= t_acc) ? v0 + (vmax - v0) * (t / t_acc) : vmax;
+            if (t > t_acc + t_flat) r = vmax - (vmax - v0) * ((t - (t_acc + t_flat)) / t_dec);
+            return tg_clamp(r, v0, vmax);
+        }
+        default: return v[0] + v[1] * sin(2.0 * 3.141592653589793 * t / v[2]);
+    }
+}
+
+__device__ __forceinline__ void tg_path_at(const tg_ref_spec &s, const double *__restrict__ brk,
+                                           const double *__restrict__ coef, double xs, double &y, double &dy)
+{
+    if (s.path_kind == TG_PATH_PARABOLA) {
+        y = s.path[0] * (xs * xs) + s.path[1] * xs + s.path[2];
+        dy = 2.0 * s.path[0] * xs + s.path[1];
+    } else if (s.path_kind == TG_PATH_SINE) {
+        double sn, cs;
+        sincos(s.path[1] * xs + s.path[2], &sn, &cs);
+        y = s.path[0] * sn + s.path[3];
+        dy = s.path[0] * s.path[1] * cs;
+    } else {
+        int lo = 0;
+        const int K = s.spline_count;
+        const double *b = brk + s.spline_first;
+        while (lo + 1 < K && xs >= b[lo + 1]) ++lo;
+        const double *cc = coef + 4 * (size_t)(s.spline_first + lo);
+        const double dx = xs - b[lo];
+        y = ((cc[0] * dx + cc[1]) * dx + cc[2]) * dx + cc[3];
+        dy = (3.0 * cc[0] * dx + 2.0 * cc[1]) * dx + cc[2];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller with fixed polynomial kernels: bit-identical to oracle/philox_ref.c
+// (same operations in the same order; __d*_rn / __fma_rn keep nvcc from contracting differently).
+__device__ __forceinline__ void tg_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                 uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double tg_log_u(uint32_t r)
+{
+    const unsigned long long mm = 2ull * r + 1ull;
+    int e = 63 - __clzll((long long)mm);
+    double f = __dmul_rn((double)mm, __longlong_as_double((long long)(1023 - e) << 52));  // exact scaling by 2^-e
+    if (f > 1.4142135623730951) { f = __dmul_rn(f, 0.5); e += 1; }
+    const double s = __ddiv_rn(__dadd_rn(f, -1.0), __dadd_rn(f, 1.0));
+    const double s2 = __dmul_rn(s, s);
+    double pl = 1.0 / 27.0;
+    pl = __fma_rn(pl, s2, 1.0 / 25.0);
+    pl = __fma_rn(pl, s2, 1.0 / 23.0);
+    pl = __fma_rn(pl, s2, 1.0 / 21.0);
+    pl = __fma_rn(pl, s2, 1.0 / 19.0);
+    pl = __fma_rn(pl, s2, 1.0 / 17.0);
+    pl = __fma_rn(pl, s2, 1.0 / 15.0);
+    pl = __fma_rn(pl, s2, 1.0 / 13.0);
+    pl = __fma_rn(pl, s2, 1.0 / 11.0);
+    pl = __fma_rn(pl, s2, 1.0 / 9.0);
+    pl = __fma_rn(pl, s2, 1.0 / 7.0);
+    pl = __fma_rn(pl, s2, 1.0 / 5.0);
+    pl = __fma_rn(pl, s2, 1.0 / 3.0);
+    pl = __fma_rn(pl, s2, 1.0);
+    const double lf = __dmul_rn(__dmul_rn(2.0, s), pl);
+    return __fma_rn((double)(e - 33), 0.6931471805599453, lf);
+}
+
+__device__ __forceinline__ void tg_sincos_2pi_u(uint32_t r, double &sn, double &cs)
+{
+    const unsigned long long mm = 2ull * r + 1ull;
+    const uint32_t oct = (uint32_t)(mm >> 30);
+    const unsigned long long frac = mm & ((1ull << 30) - 1);
+    double t = __dmul_rn((double)frac, 9.313225746154785e-10);  // 2^-30
+    if (oct & 1u) t = __dadd_rn(1.0, -t);
+    const double a = __dmul_rn(t, 0.7853981633974483);
+    const double a2 = __dmul_rn(a, a);
+    double ps = -1.0 / 1307674368000.0;
+    ps = __fma_rn(ps, a2, 1.0 / 6227020800.0);
+    ps = __fma_rn(ps, a2, -1.0 / 39916800.0);
+    ps = __fma_rn(ps, a2, 1.0 / 362880.0);
+    ps = __fma_rn(ps, a2, -1.0 / 5040.0);
+    ps = __fma_rn(ps, a2, 1.0 / 120.0);
+    ps = __fma_rn(ps, a2, -1.0 / 6.0);
+    ps = __fma_rn(ps, a2, 1.0);
+    const double sk = __dmul_rn(a, ps);
+    double pc = 1.0 / 20922789888000.0;
+    pc = __fma_rn(pc, a2, -1.0 / 87178291200.0);
+    pc = __fma_rn(pc, a2, 1.0 / 479001600.0);
+    pc = __fma_rn(pc, a2, -1.0 / 3628800.0);
+    pc = __fma_rn(pc, a2, 1.0 / 40320.0);
+    pc = __fma_rn(pc, a2, -1.0 / 720.0);
+    pc = __fma_rn(pc, a2, 1.0 / 24.0);
+    pc = __fma_rn(pc, a2, -0.5);
+    const double ck = __fma_rn(pc, a2, 1.0);
+    switch (oct) {
+        case 0: sn = sk; cs = ck; break;
+        case 1: sn = ck; cs = sk; break;
+        case 2: sn = ck; cs = -sk; break;
+        case 3: sn = sk; cs = -ck; break;
+        case 4: sn = -sk; cs = -ck; break;
+        case 5: sn = -ck; cs = -sk; break;
+        case 6: sn = -ck; cs = sk; break;
+        default: sn = -sk; cs = ck; break;
+    }
+}
+
+__device__ __forceinline__ void tg_box_muller(uint32_t r0, uint32_t r1, double &n0, double &n1)
+{
+    const double rad = __dsqrt_rn(__dmul_rn(-2.0, tg_log_u(r0)));
+    double sn, cs;
+    tg_sincos_2pi_u(r1, sn, cs);
+    n0 = __dmul_rn(rad, cs);
+    n1 = __dmul_rn(rad, sn);
+}
+
+// six standard normals of (seed,row): X, Y, phi, vx, vy, omega
+__device__ __forceinline__ void tg_noise_row(unsigned long long seed, uint32_t row, double out[6])
+{
+    uint32_t a[4], b[4];
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    tg_philox4x32_10(row, 0u, 0u, 0u, k0, k1, a);
+    tg_philox4x32_10(row, 1u, 0u, 0u, k0, k1, b);
+    tg_box_muller(a[0], a[1], out[0], out[1]);
+    tg_box_muller(a[2], a[3], out[2], out[3]);
+    tg_box_muller(b[0], b[1], out[4], out[5]);
+}

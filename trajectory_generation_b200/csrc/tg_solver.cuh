@@ -1,0 +1,522 @@
+// tg_solver.cuh -- one MPC step for one problem, executed by one CTA (sm_100a, fp64).
+//
+// Replaces MPC/mpc_6stati.py:165-275 (nominal rollout, N x linearize_discretize, CVXPY problem
+// construction, OSQP solve, receding-horizon output) with:
+//   K1  rollout + per-stage linearisation (compact 28-word records in shared memory)
+//   K2  condensing in dU = U - u_prev: the columns of G_k live in registers (one column per thread)
+//       and stream through the horizon; H = 2 (sum_k W_k' L W_k + Rbar + D' Rdbar D) accumulates in a
+//       register-resident n x n matrix distributed as (row, column segment) over the CTA
+//   K3  ADMM (OSQP iteration) with per-row rho scaled by diag(H); K = H + sigma I + A' diag(rho) A is
+//       inverted in registers by n symmetric sweep steps; every iteration is one register mat-vec plus
+//       O(n) vector work; warp-shuffle reductions for the residual norms; adaptive rho refactors from a
+//       copy of H kept in an L2-resident per-CTA workspace.
+// Thread layout: thread t -> matrix row t / S, column segment t % S of width SEG (n <= S*SEG = NP).
+#pragma once
+#include "tg_device.cuh"
+
+// shared-memory layout (offsets in doubles), identical on host and device
+struct SmemLayout {
+    int x0, uprev, misc, xbar, lin, Xr, Yr, Pr, sn, cs, vref, rr, w, v, q, x, xt, dH, z, y, l, u, rho, zt, dy, Gs, red;
+    int total;
+};
+
+__host__ __device__ inline SmemLayout tg_make_layout(int N, int ms, int NP)
+{
+    SmemLayout L;
+    int o = 0;
+    const int n = 2 * N, m = 4 * N + ms;
+    auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };  // keep 16-byte alignment
+    L.x0 = take(6); L.uprev = take(2); L.misc = take(16);
+    L.xbar = take(6 * (N + 1)); L.lin = take(TG_LIN * N);
+    L.Xr = take(N + 1); L.Yr = take(N + 1); L.Pr = take(N + 1); L.sn = take(N + 1); L.cs = take(N + 1); L.vref = take(N + 1);
+    L.rr = take(3 * (N + 1));
+    L.w = take(2 * 3 * NP); L.v = take(2 * NP + 2);
+    L.q = take(n); L.x = take(n); L.xt = take(NP); L.dH = take(n);
+    L.z = take(m); L.y = take(m); L.l = take(m); L.u = take(m); L.rho = take(m); L.zt = take(m); L.dy = take(m);
+    L.Gs = take(ms * NP);
+    L.red = take(16 * 32);
+    L.total = o;
+    return L;
+}
+
+// misc slots
+enum { M_C0 = 0, M_FLAG = 1, M_RHOSCALE = 2, M_NORMQ = 3, M_PIV0 = 4, M_PIV1 = 5, M_OBJ = 6 };
+
+struct StepTaps {   // optional debug/parity outputs of this problem (global memory, may be null)
+    double *A, *Bm, *g, *xbar;          // tg_linearize
+    double *H, *q, *c0, *l, *u, *Gs;    // tg_assemble
+    int stop;                           // 0 = full step, 1 = stop after linearisation, 2 = stop after assembly
+};
+
+struct StepResult {
+    int status, iters;
+    double objective;
+};
+
+template <int NRED>
+__device__ __forceinline__ void tg_block_reduce_max(double (&vals)[NRED], double *red, int tid, int nthreads)
+{
+    const int lane = tid & 31, wid = tid >> 5, nw = (nthreads + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NRED; ++i) {
+        double v = vals[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        vals[i] = v;
+    }
+    if (nw > 1) {
+        if (lane == 0)
+#pragma unroll
+            for (int i = 0; i < NRED; ++i) red[wid * 16 + i] = vals[i];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NRED; ++i) {
+            double v = red[i];
+            for (int w = 1; w < nw; ++w) v = fmax(v, red[w * 16 + i]);
+            vals[i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ double tg_block_reduce_sum(double v, double *red, int tid, int nthreads)
+{
+    const int lane = tid & 31, wid = tid >> 5, nw = (nthreads + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (nw > 1) {
+        if (lane == 0) red[wid * 16] = v;
+        __syncthreads();
+        v = red[0];
+        for (int w = 1; w < nw; ++w) v += red[w * 16];
+        __syncthreads();
+    }
+    return v;
+}
+
+// K = H + sigma I + A' diag(rho) A on the register tile; rho vectors are in shared memory.
+template <int SEG>
+__device__ __forceinline__ void tg_build_K(const DevCfg &c, const SmemLayout &L, const double *sm, double (&a)[SEG],
+                                           int row, int col0)
+{
+    const int n = c.n;
+    if (row >= n) return;
+    const double *rho_b = sm + L.rho, *rho_r = sm + L.rho + n, *rho_s = sm + L.rho + 2 * n;
+    const double dg = c.sigma + rho_b[row] + rho_r[row] + ((row + 2 < n) ? rho_r[row + 2] : 0.0);
+    const double lo = -rho_r[row];
+    const double hi = (row + 2 < n) ? -rho_r[row + 2] : 0.0;
+#pragma unroll
+    for (int jj = 0; jj < SEG; ++jj) {
+        const int col = col0 + jj;
+        double add = 0.0;
+        if (col == row) add = dg;
+        else if (col == row - 2) add = lo;
+        else if (col == row + 2) add = hi;
+        a[jj] += add;
+    }
+    const double *Gs = sm + L.Gs;
+    for (int i = 0; i < c.ms; ++i) {
+        const double gi = Gs[i * c.NP + row] * rho_s[i];
+#pragma unroll
+        for (int jj = 0; jj < SEG; ++jj) a[jj] = fma(gi, Gs[i * c.NP + col0 + jj], a[jj]);
+    }
+}
+
+// In-register inversion of the SPD tile by n symmetric sweeps; on return a = -K^{-1}.
+template <int SEG, int S>
+__device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayout &L, double *sm, double (&a)[SEG],
+                                                int row, int col0)
+{
+    const int n = c.n, NP = c.NP;
+    double *vb = sm + L.v;
+    for (int k = 0; k < n; ++k) {
+        double *v = vb + (k & 1) * (NP + 1);
+        if (row == k) {  // publish row k (= column k by symmetry); entry k carries a_kk - 1, slot NP the pivot
+#pragma unroll
+            for (int jj = 0; jj < SEG; ++jj) {
+                double val = a[jj];
+                if (col0 + jj == k) { v[NP] = val; val -= 1.0; }
+                v[col0 + jj] = val;
+            }
+        }
+        __syncthreads();
+        if (row < n) {
+            const double piv = v[NP];
+            const double p = 1.0 / piv;
+            if (row != k) {
+                const double wi = v[row] * p;
+#pragma unroll
+                for (int jj = 0; jj < SEG; ++jj) a[jj] = fma(-wi, v[col0 + jj], a[jj]);
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < SEG; ++jj) a[jj] = (col0 + jj == k) ? -p : v[col0 + jj] * p;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// One MPC step.  On entry shared memory holds x0, uprev, the reference window (Xr, Yr, Pr, vref) and, if
+// `warm`, the warm-start dU in sm[L.x] and duals in sm[L.y].  On exit sm[L.xt] holds dU* (x-tilde of the
+// last check), sm[L.y] the duals, sm[L.zt] = A dU*, and the result is returned to every thread.
+template <int SEG, int S>
+__device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, double *sm, bool warm, double *Hws,
+                                       const StepTaps &tap)
+{
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int N = c.N, n = c.n, NP = c.NP, ms = c.ms, m = c.m, ns = c.ns;
+    const int row = tid / S, seg = tid % S, col0 = seg * SEG;
+    StepResult res;
+    res.status = TG_STATUS_NAN; res.iters = 0; res.objective = 0.0;
+
+    double *x0 = sm + L.x0, *up = sm + L.uprev, *misc = sm + L.misc, *xbar = sm + L.xbar, *lin = sm + L.lin;
+    double *Xr = sm + L.Xr, *Yr = sm + L.Yr, *Pr = sm + L.Pr, *sn = sm + L.sn, *cs = sm + L.cs, *vref = sm + L.vref;
+    double *rr = sm + L.rr, *wbuf = sm + L.w, *q = sm + L.q, *x = sm + L.x, *xt = sm + L.xt, *dH = sm + L.dH;
+    double *z = sm + L.z, *y = sm + L.y, *lb = sm + L.l, *ub = sm + L.u, *rho = sm + L.rho, *zt = sm + L.zt, *dy = sm + L.dy;
+    double *Gs = sm + L.Gs, *red = sm + L.red;
+
+    const double ud = up[0], udel = up[1];
+
+    // ---------------- K1a: nominal rollout (mpc_6stati.py:167-172), sequential in k
+    if (tid == 0) {
+        double sd, cd, xs[6], f[6];
+        sincos(udel, &sd, &cd);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { xs[i] = x0[i]; xbar[i] = xs[i]; }
+        for (int k = 0; k < N; ++k) {
+            tg_f_cont(c.p, c.model, xs, ud, udel, sd, cd, f);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { xs[i] = xs[i] + c.Ts * f[i]; xbar[6 * (k + 1) + i] = xs[i]; }
+        }
+    }
+    // zero the W staging buffers and the mat-vec input pad while thread 0 integrates
+    for (int i = tid; i < 2 * 3 * NP; i += NT) wbuf[i] = 0.0;
+    for (int i = tid; i < 2 * NP + 2; i += NT) sm[L.v + i] = 0.0;
+    for (int i = tid; i < NP; i += NT) xt[i] = 0.0;
+    for (int i = tid; i < ms * (NP - n); i += NT) Gs[(i / (NP - n)) * NP + n + i % (NP - n)] = 0.0;  // pad columns
+    for (int i = tid; i <= N; i += NT) { double s_, c_; sincos(Pr[i], &s_, &c_); sn[i] = s_; cs[i] = c_; }
+    __syncthreads();
+
+    // ---------------- K1b: linearise every stage (mpc_6stati.py:175-178) + tracking residuals at xbar
+    for (int k = tid; k < N; k += NT) {
+        double xs[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xs[i] = xbar[6 * k + i];
+        if (c.jacobian == TG_JAC_FD) {
+            tg_linearize_fd(c, xs, ud, udel, lin + TG_LIN * k);
+        } else {
+            double sd, cd;
+            sincos(udel, &sd, &cd);
+            tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k);
+        }
+    }
+    double c0_part = 0.0;
+    for (int k = tid; k <= N; k += NT) {
+        const double *xk = xbar + 6 * k;
+        const double rc = sn[k] * (xk[0] - Xr[k]) - cs[k] * (xk[1] - Yr[k]);  // lateral_error :111-117
+        const double rp = xk[2] - Pr[k], rv = xk[3] - vref[k];
+        rr[3 * k] = rc; rr[3 * k + 1] = rp; rr[3 * k + 2] = rv;
+        c0_part += c.q_c * rc * rc + c.q_phi * rp * rp + c.q_vx * rv * rv;
+    }
+    __syncthreads();
+    if (tap.A || tap.Bm || tap.g || tap.xbar) {
+        for (int k = tid; k < N; k += NT)
+            tg_lin_expand(lin + TG_LIN * k, tap.A ? tap.A + 36 * k : nullptr, tap.Bm ? tap.Bm + 12 * k : nullptr,
+                          tap.g ? tap.g + 6 * k : nullptr);
+        if (tap.xbar)
+            for (int i = tid; i < 6 * (N + 1); i += NT) tap.xbar[i] = xbar[i];
+    }
+    if (tap.stop == 1) return res;
+
+    // ---------------- K2: condensing.  Thread j < n owns column j of G_k (6 registers).
+    double a[SEG];
+#pragma unroll
+    for (int jj = 0; jj < SEG; ++jj) a[jj] = 0.0;
+    double G0 = 0, G1 = 0, G2 = 0, G3 = 0, G4 = 0, G5 = 0, qacc = 0.0;
+    const double tqc = 2.0 * c.q_c, tqp = 2.0 * c.q_phi, tqv = 2.0 * c.q_vx;
+    for (int k = 0; k < N; ++k) {
+        double *wb = wbuf + (k & 1) * 3 * NP;
+        if (tid < n) {
+            const double *r = lin + TG_LIN * k;
+            const int j = tid;
+            if (j < 2 * k) {  // G_{k+1} = A_k G_k
+                const double n0 = G0 + r[0] * G2 + r[1] * G3 + r[2] * G4;
+                const double n1 = G1 + r[3] * G2 + r[4] * G3 + r[5] * G4;
+                const double n2 = G2 + r[6] * G5;
+                const double n3 = r[7] * G3 + r[8] * G4 + r[9] * G5;
+                const double n4 = r[10] * G3 + r[11] * G4 + r[12] * G5;
+                const double n5 = r[13] * G3 + r[14] * G4 + r[15] * G5;
+                G0 = n0; G1 = n1; G2 = n2; G3 = n3; G4 = n4; G5 = n5;
+            } else if (j < 2 * k + 2) {  // new block column: B_k
+                const int cc = j - 2 * k;
+                G0 = 0.0; G1 = 0.0; G2 = 0.0;
+                G3 = r[16 + cc]; G4 = r[18 + cc]; G5 = r[20 + cc];
+            }
+            const int kk = k + 1;
+            const double wc = sn[kk] * G0 - cs[kk] * G1;
+            wb[j] = wc; wb[NP + j] = G2; wb[2 * NP + j] = G3;
+            qacc += tqc * rr[3 * kk] * wc + tqp * rr[3 * kk + 1] * G2 + tqv * rr[3 * kk + 2] * G3;
+            for (int si = 0; si < ns; ++si) {
+                const int s_ = c.sidx[si];
+                const double gv = (s_ == 0) ? G0 : (s_ == 1) ? G1 : (s_ == 2) ? G2 : (s_ == 3) ? G3 : (s_ == 4) ? G4 : G5;
+                Gs[(k * ns + si) * NP + j] = gv;
+            }
+        }
+        __syncthreads();
+        if (row < 2 * k + 2 && col0 < 2 * k + 2 && row < n) {
+            const double w0 = wb[row] * tqc, w1 = wb[NP + row] * tqp, w2 = wb[2 * NP + row] * tqv;
+#pragma unroll
+            for (int jj = 0; jj < SEG; ++jj) {
+                double t = a[jj];
+                t = fma(w0, wb[col0 + jj], t);
+                t = fma(w1, wb[NP + col0 + jj], t);
+                t = fma(w2, wb[2 * NP + col0 + jj], t);
+                a[jj] = t;
+            }
+        }
+    }
+    // input and input-rate penalties (mpc_6stati.py:238-245), expressed in dU
+    if (row < n) {
+        const int kr = row >> 1, cr = row & 1;
+#pragma unroll
+        for (int jj = 0; jj < SEG; ++jj) {
+            const int col = col0 + jj;
+            const int kc = col >> 1, cc = col & 1;
+            double add = 0.0;
+            if (col < n) {
+                if (kc == kr) add = 2.0 * c.Rs[cr * 2 + cc] + ((kr < N - 1) ? 4.0 : 2.0) * c.Rds[cr * 2 + cc];
+                else if (kc == kr + 1 || kc + 1 == kr) add = -2.0 * c.Rds[cr * 2 + cc];
+            }
+            a[jj] += add;
+            if (col == row) dH[row] = a[jj];
+        }
+    }
+    if (tid < n) {
+        const int cc = tid & 1;
+        q[tid] = qacc + 2.0 * (c.Rs[cc * 2] * ud + c.Rs[cc * 2 + 1] * udel);
+    }
+    // constant term: stage costs at xbar + N u_prev' R u_prev
+    {
+        double c0 = tg_block_reduce_sum(c0_part, red, tid, NT);
+        c0 += (double)N * (ud * (c.Rs[0] * ud + c.Rs[1] * udel) + udel * (c.Rs[2] * ud + c.Rs[3] * udel));
+        if (tid == 0) misc[M_C0] = c0;
+    }
+    __syncthreads();
+
+    // ---------------- bounds (mpc_6stati.py:198-221) and per-row rho = rho0 / max_j(a_ij^2 / H_jj)
+    bool x0_infeasible = false;
+    for (int si = 0; si < ns; ++si) {
+        const int s_ = c.sidx[si];
+        if (x0[s_] < c.x_lo[s_] - c.eps_abs || x0[s_] > c.x_hi[s_] + c.eps_abs) x0_infeasible = true;  // k = 0 rows (:217,:220)
+    }
+    if (tid < n) {
+        const int j = tid, cc = j & 1;
+        lb[j] = c.u_lo[cc] - up[cc]; ub[j] = c.u_hi[cc] - up[cc];
+        lb[n + j] = c.du_lo[cc];     ub[n + j] = c.du_hi[cc];
+        rho[j] = dH[j];
+        rho[n + j] = (j >= 2) ? fmin(dH[j], dH[j - 2]) : dH[j];
+    }
+    for (int i = tid; i < ms; i += NT) {
+        const int kk = i / ns + 1, s_ = c.sidx[i % ns];
+        const double xb = xbar[6 * kk + s_];
+        lb[2 * n + i] = (c.x_lo[s_] <= -TG_INF) ? -TG_INF : c.x_lo[s_] - xb;
+        ub[2 * n + i] = (c.x_hi[s_] >= TG_INF) ? TG_INF : c.x_hi[s_] - xb;
+        double mx = 0.0;
+        for (int j = 0; j < n; ++j) { const double gij = Gs[i * NP + j]; mx = fmax(mx, gij * gij / dH[j]); }
+        rho[2 * n + i] = (mx > 1e-30) ? 1.0 / mx : 1.0;
+    }
+    if (tap.H && row < n) {
+#pragma unroll
+        for (int jj = 0; jj < SEG; ++jj)
+            if (col0 + jj < n) tap.H[row * n + col0 + jj] = a[jj];
+    }
+    if (Hws && row < n) {
+#pragma unroll
+        for (int jj = 0; jj < SEG; ++jj) Hws[row * NP + col0 + jj] = a[jj];
+    }
+    __syncthreads();
+    if (tap.q) for (int i = tid; i < n; i += NT) tap.q[i] = q[i];
+    if (tap.c0 && tid == 0) tap.c0[0] = misc[M_C0];
+    if (tap.l) for (int i = tid; i < m; i += NT) { tap.l[i] = lb[i]; tap.u[i] = ub[i]; }
+    if (tap.Gs) for (int i = tid; i < ms * n; i += NT) tap.Gs[i] = Gs[(i / n) * NP + (i % n)];
+    if (tap.stop == 2) return res;
+
+    // scale the unit rho pattern by rho0 (kept separately so adaptive rho can rescale)
+    double rho_scale = c.rho;
+    for (int i = tid; i < m; i += NT) rho[i] *= rho_scale;
+    double nq = 0.0;
+    for (int i = tid; i < n; i += NT) nq = fmax(nq, fabs(q[i]));
+    {
+        double vals[1] = {nq};
+        tg_block_reduce_max<1>(vals, red, tid, NT);
+        nq = vals[0];
+    }
+    __syncthreads();
+
+    // ---------------- K3: factor
+    tg_build_K<SEG>(c, L, sm, a, row, col0);
+    tg_sweep_invert<SEG, S>(c, L, sm, a, row, col0);
+
+    // ---------------- ADMM
+    if (!warm) {
+        for (int i = tid; i < n; i += NT) x[i] = 0.0;
+        for (int i = tid; i < m; i += NT) { z[i] = 0.0; y[i] = 0.0; }
+    } else {
+        // z = clip(A x, l, u) for the warm-start point
+        for (int j = tid; j < n; j += NT) {
+            z[j] = tg_clamp(x[j], lb[j], ub[j]);
+            const double r_ = x[j] - ((j >= 2) ? x[j - 2] : 0.0);
+            z[n + j] = tg_clamp(r_, lb[n + j], ub[n + j]);
+        }
+        for (int i = tid; i < ms; i += NT) {
+            double acc = 0.0;
+            for (int j = 0; j < n; ++j) acc = fma(Gs[i * NP + j], x[j], acc);
+            z[2 * n + i] = tg_clamp(acc, lb[2 * n + i], ub[2 * n + i]);
+        }
+    }
+    __syncthreads();
+
+    const double alpha = c.alpha, sigma = c.sigma;
+    double *v = sm + L.v;  // mat-vec input (first NP entries)
+    int status = TG_STATUS_USER_LIMIT, it = 0;
+    double obj = 0.0;
+    if (x0_infeasible) status = TG_STATUS_INFEASIBLE;
+    else
+    for (it = 1; it <= c.max_iter; ++it) {
+        const bool check = (it % c.check_every == 0) || (it == c.max_iter);
+        // (a) rhs = sigma x - q + A'(rho z - y)
+        if (tid < n) {
+            const int j = tid;
+            double r_ = sigma * x[j] - q[j] + (rho[j] * z[j] - y[j]) + (rho[n + j] * z[n + j] - y[n + j]);
+            if (j + 2 < n) r_ -= (rho[n + j + 2] * z[n + j + 2] - y[n + j + 2]);
+            for (int i = 0; i < ms; ++i) r_ = fma(Gs[i * NP + j], rho[2 * n + i] * z[2 * n + i] - y[2 * n + i], r_);
+            v[j] = r_;
+        }
+        __syncthreads();
+        // (b) x~ = K^{-1} rhs   (a holds -K^{-1})
+        {
+            double part = 0.0;
+            if (row < n) {
+#pragma unroll
+                for (int jj = 0; jj < SEG; ++jj) part = fma(a[jj], v[col0 + jj], part);
+            }
+#pragma unroll
+            for (int o = 1; o < S; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (row < n && seg == 0) xt[row] = -part;
+        }
+        __syncthreads();
+        // (c) relaxation, projection, dual update
+        double rp = 0.0, nzt = 0.0, nz = 0.0;
+        if (tid < n) {
+            const int j = tid;
+            const double xtj = xt[j];
+            x[j] = alpha * xtj + (1.0 - alpha) * x[j];
+            {   // box row j
+                const double zr = alpha * xtj + (1.0 - alpha) * z[j];
+                const double zn = tg_clamp(zr + y[j] / rho[j], lb[j], ub[j]);
+                const double yn = y[j] + rho[j] * (zr - zn);
+                dy[j] = yn - y[j]; y[j] = yn; z[j] = zn; zt[j] = xtj;
+                rp = fmax(rp, fabs(xtj - zn)); nzt = fmax(nzt, fabs(xtj)); nz = fmax(nz, fabs(zn));
+            }
+            {   // rate row j
+                const int i = n + j;
+                const double ztl = xtj - ((j >= 2) ? xt[j - 2] : 0.0);
+                const double zr = alpha * ztl + (1.0 - alpha) * z[i];
+                const double zn = tg_clamp(zr + y[i] / rho[i], lb[i], ub[i]);
+                const double yn = y[i] + rho[i] * (zr - zn);
+                dy[i] = yn - y[i]; y[i] = yn; z[i] = zn; zt[i] = ztl;
+                rp = fmax(rp, fabs(ztl - zn)); nzt = fmax(nzt, fabs(ztl)); nz = fmax(nz, fabs(zn));
+            }
+        }
+        for (int r_ = tid; r_ < ms; r_ += NT) {
+            const int i = 2 * n + r_;
+            double ztl = 0.0;
+            for (int j = 0; j < n; ++j) ztl = fma(Gs[r_ * NP + j], xt[j], ztl);
+            const double zr = alpha * ztl + (1.0 - alpha) * z[i];
+            const double zn = tg_clamp(zr + y[i] / rho[i], lb[i], ub[i]);
+            const double yn = y[i] + rho[i] * (zr - zn);
+            dy[i] = yn - y[i]; y[i] = yn; z[i] = zn; zt[i] = ztl;
+            rp = fmax(rp, fabs(ztl - zn)); nzt = fmax(nzt, fabs(ztl)); nz = fmax(nz, fabs(zn));
+        }
+        __syncthreads();
+        if (!check) continue;
+
+        // (d) residuals at (x~, z, y):  H x~ = rhs - sigma x~ - A'(rho .* z~)
+        double rd = 0.0, nh = 0.0, na = 0.0, natdy = 0.0, ndy = 0.0, cert = 0.0, objp = 0.0;
+        bool cert_ok = true, bad = false;
+        if (tid < n) {
+            const int j = tid;
+            double aty = y[j] + y[n + j], atr = rho[j] * zt[j] + rho[n + j] * zt[n + j], atd = dy[j] + dy[n + j];
+            if (j + 2 < n) { aty -= y[n + j + 2]; atr -= rho[n + j + 2] * zt[n + j + 2]; atd -= dy[n + j + 2]; }
+            for (int i = 0; i < ms; ++i) {
+                const double gij = Gs[i * NP + j];
+                aty = fma(gij, y[2 * n + i], aty);
+                atr = fma(gij, rho[2 * n + i] * zt[2 * n + i], atr);
+                atd = fma(gij, dy[2 * n + i], atd);
+            }
+            const double hx = v[j] - sigma * xt[j] - atr;
+            rd = fabs(hx + q[j] + aty); nh = fabs(hx); na = fabs(aty); natdy = fabs(atd);
+            objp = xt[j] * (0.5 * hx + q[j]);
+            bad = !(isfinite(hx) && isfinite(aty));
+        }
+        for (int i = tid; i < m; i += NT) {
+            const double d_ = dy[i];
+            ndy = fmax(ndy, fabs(d_));
+            if (d_ > 0.0) { if (ub[i] >= TG_INF) cert_ok = cert_ok && (d_ <= 0.0); else cert += ub[i] * d_; }
+            else if (d_ < 0.0) { if (lb[i] <= -TG_INF) cert_ok = cert_ok && (d_ >= 0.0); else cert += lb[i] * d_; }
+        }
+        double vals[9] = {rp, nzt, nz, rd, nh, na, natdy, ndy, bad ? 1.0 : 0.0};
+        tg_block_reduce_max<9>(vals, red, tid, NT);
+        const double cert_sum = tg_block_reduce_sum(cert, red, tid, NT);
+        obj = tg_block_reduce_sum(objp, red, tid, NT);
+        const double eps_p = c.eps_abs + c.eps_rel * fmax(vals[1], vals[2]);
+        const double eps_d = c.eps_abs + c.eps_rel * fmax(fmax(vals[4], vals[5]), nq);
+        if (vals[8] > 0.0 || !(vals[0] == vals[0]) || !(vals[3] == vals[3])) { status = TG_STATUS_NAN; break; }
+        if (vals[0] <= eps_p && vals[3] <= eps_d) { status = TG_STATUS_OPTIMAL; break; }
+        if (it == c.max_iter) {
+            if (vals[0] <= 10.0 * eps_p && vals[3] <= 10.0 * eps_d) status = TG_STATUS_OPTIMAL_INACCURATE;
+            break;
+        }
+        // primal infeasibility certificate (OSQP section 3.4); rows with an infinite bound on the side dy
+        // points to cannot certify (handled conservatively through the thresholded test below)
+        if (vals[7] > c.eps_pinf) {
+            // re-evaluate the support term with OSQP's thresholding of dy on infinite sides
+            if (cert_sum < -c.eps_pinf * vals[7] && vals[6] <= c.eps_pinf * vals[7]) {
+                // make sure no infinite side carries a significant component
+                double infc = 0.0;
+                for (int i = tid; i < m; i += NT) {
+                    const double d_ = dy[i];
+                    if ((ub[i] >= TG_INF && d_ > c.eps_pinf * vals[7]) || (lb[i] <= -TG_INF && d_ < -c.eps_pinf * vals[7])) infc = 1.0;
+                }
+                double iv[1] = {infc};
+                tg_block_reduce_max<1>(iv, red, tid, NT);
+                if (iv[0] == 0.0) { status = TG_STATUS_INFEASIBLE; break; }
+            }
+        }
+        // adaptive rho (OSQP section 5.2), iteration-triggered so runs are reproducible
+        if (c.adaptive_rho && Hws && it >= c.adaptive_rho_min_iter) {
+            const double sp = fmax(vals[1], vals[2]), sd = fmax(fmax(vals[4], vals[5]), nq);
+            const double ratio = sqrt((vals[0] / (sp + 1e-10)) / (vals[3] / (sd + 1e-10) + 1e-10));
+            double ns_ = fmin(fmax(rho_scale * ratio, 1e-6), 1e6);
+            if (ns_ > rho_scale * c.adapt_tol || ns_ * c.adapt_tol < rho_scale) {
+                const double f_ = ns_ / rho_scale;
+                rho_scale = ns_;
+                for (int i = tid; i < m; i += NT) rho[i] *= f_;
+                if (row < n) {
+#pragma unroll
+                    for (int jj = 0; jj < SEG; ++jj) a[jj] = Hws[row * NP + col0 + jj];
+                }
+                __syncthreads();
+                tg_build_K<SEG>(c, L, sm, a, row, col0);
+                tg_sweep_invert<SEG, S>(c, L, sm, a, row, col0);
+            }
+        }
+    }
+    if (it > c.max_iter) it = c.max_iter;
+    res.status = status;
+    res.iters = it;
+    res.objective = obj + misc[M_C0];
+    if (tid == 0) misc[M_RHOSCALE] = rho_scale;
+    __syncthreads();
+    return res;
+}

@@ -1,0 +1,746 @@
+// trajgen.cu -- kernels + C ABI (include/trajgen.h) of libtrajgen.so.  sm_100a only.
+//
+// Kernels (one CTA per problem / trajectory, persistent grid-stride over the batch):
+//   tg_mpc_step_kernel     K1+K2+K3: replaces mpc_step, MPC/mpc_6stati.py:120-275
+//   tg_closed_loop_kernel  fused K1..K4: replaces the loop MPC/main.py:85-101 + the dataset shell
+//                          generation_type2.py:180-200 (plant clipping, sensor noise)
+//   tg_ref_window_kernel   MPC/main.py:28-47,51-68
+//   tg_plant_kernel        generation_type1.py:70-84 (open-loop integration with clipping)
+//   tg_noise_kernel / tg_philox_kernel   Philox4x32-10 sensor-noise stream
+//   tg_fma_peak_kernel     FMA micro-benchmark (roofline denominator)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "tg_solver.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(TG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ kernels
+struct StepArgs {
+    int B;
+    const double *x0, *u_prev, *path_ref, *vref;
+    double *u_cmd; int *status; int *iters; double *objective; double *U_opt, *X_opt, *y_opt;
+    // taps
+    double *A, *Bm, *g, *xbar, *H, *q, *c0, *l, *u, *Gs;
+    int stop;
+    double *ws_x, *ws_y; int *ws_valid;   // per-problem warm-start state (step API), may be null
+    double *Hws;                          // per-CTA H workspace, may be null
+};
+
+template <int SEG, int S>
+__global__ void __launch_bounds__(((SEG * S * S + 31) / 32) * 32 < 64 ? 64 : ((SEG * S * S + 31) / 32) * 32)
+tg_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, const __grid_constant__ StepArgs a)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int N = c.N, n = c.n, m = c.m;
+    double *Hws = a.Hws ? a.Hws + (size_t)blockIdx.x * n * c.NP : nullptr;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        __syncthreads();
+        if (tid < 6) sm[L.x0 + tid] = a.x0[6 * (size_t)b + tid];
+        if (tid < 2) sm[L.uprev + tid] = a.u_prev[2 * (size_t)b + tid];
+        const double vx0 = a.x0[6 * (size_t)b + 3];
+        for (int k = tid; k <= N; k += NT) {
+            if (a.path_ref) {
+                const double *pr = a.path_ref + 3 * ((size_t)b * (N + 1) + k);
+                sm[L.Xr + k] = pr[0]; sm[L.Yr + k] = pr[1]; sm[L.Pr + k] = pr[2];
+            } else { sm[L.Xr + k] = 0.0; sm[L.Yr + k] = 0.0; sm[L.Pr + k] = 0.0; }
+            sm[L.vref + k] = a.vref ? a.vref[(size_t)b * (N + 1) + k] : vx0;
+        }
+        bool warm = false;
+        if (a.ws_valid && c.warm_start && a.ws_valid[b]) {
+            warm = true;
+            for (int i = tid; i < n; i += NT) sm[L.x + i] = a.ws_x[(size_t)b * n + i];
+            for (int i = tid; i < m; i += NT) sm[L.y + i] = a.ws_y[(size_t)b * m + i];
+        }
+        __syncthreads();
+        StepTaps tap;
+        tap.A = a.A ? a.A + (size_t)b * N * 36 : nullptr;
+        tap.Bm = a.Bm ? a.Bm + (size_t)b * N * 12 : nullptr;
+        tap.g = a.g ? a.g + (size_t)b * N * 6 : nullptr;
+        tap.xbar = a.xbar ? a.xbar + (size_t)b * (N + 1) * 6 : nullptr;
+        tap.H = a.H ? a.H + (size_t)b * n * n : nullptr;
+        tap.q = a.q ? a.q + (size_t)b * n : nullptr;
+        tap.c0 = a.c0 ? a.c0 + b : nullptr;
+        tap.l = a.l ? a.l + (size_t)b * m : nullptr;
+        tap.u = a.u ? a.u + (size_t)b * m : nullptr;
+        tap.Gs = a.Gs ? a.Gs + (size_t)b * c.ms * n : nullptr;
+        tap.stop = a.stop;
+        const StepResult r = tg_mpc_step_body<SEG, S>(c, L, sm, warm, Hws, tap);
+        if (a.stop) continue;
+        const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);  // :261
+        const double ud = sm[L.uprev], udel = sm[L.uprev + 1];
+        if (tid == 0) {
+            a.u_cmd[2 * (size_t)b] = ok ? ud + sm[L.xt] : ud;          // :265 / fallback :262
+            a.u_cmd[2 * (size_t)b + 1] = ok ? udel + sm[L.xt + 1] : udel;
+            if (a.status) a.status[b] = r.status;
+            if (a.iters) a.iters[b] = r.iters;
+            if (a.objective) a.objective[b] = ok ? r.objective : nan("");
+        }
+        if (a.U_opt)
+            for (int i = tid; i < n; i += NT) a.U_opt[(size_t)b * n + i] = ok ? ((i & 1) ? udel : ud) + sm[L.xt + i] : nan("");
+        if (a.y_opt)
+            for (int i = tid; i < m; i += NT) a.y_opt[(size_t)b * m + i] = ok ? sm[L.y + i] : nan("");
+        if (a.X_opt && tid == 0) {   // X_k of the QP: x_{k+1} = A_k x_k + B_k u_k + g_k  (:189-192)
+            double *X = a.X_opt + (size_t)b * (N + 1) * 6;
+            double xs[6];
+            for (int i = 0; i < 6; ++i) { xs[i] = sm[L.x0 + i]; X[i] = ok ? xs[i] : nan(""); }
+            for (int k = 0; k < N; ++k) {
+                const double *r_ = sm + L.lin + TG_LIN * k;
+                const double u0 = ud + sm[L.xt + 2 * k], u1 = udel + sm[L.xt + 2 * k + 1];
+                double nx[6];
+                nx[0] = xs[0] + r_[0] * xs[2] + r_[1] * xs[3] + r_[2] * xs[4] + r_[22];
+                nx[1] = xs[1] + r_[3] * xs[2] + r_[4] * xs[3] + r_[5] * xs[4] + r_[23];
+                nx[2] = xs[2] + r_[6] * xs[5] + r_[24];
+                nx[3] = r_[7] * xs[3] + r_[8] * xs[4] + r_[9] * xs[5] + r_[16] * u0 + r_[17] * u1 + r_[25];
+                nx[4] = r_[10] * xs[3] + r_[11] * xs[4] + r_[12] * xs[5] + r_[18] * u0 + r_[19] * u1 + r_[26];
+                nx[5] = r_[13] * xs[3] + r_[14] * xs[4] + r_[15] * xs[5] + r_[20] * u0 + r_[21] * u1 + r_[27];
+                for (int i = 0; i < 6; ++i) { xs[i] = nx[i]; X[6 * (k + 1) + i] = ok ? xs[i] : nan(""); }
+            }
+        }
+        if (a.ws_valid && c.warm_start) {
+            for (int i = tid; i < n; i += NT) a.ws_x[(size_t)b * n + i] = sm[L.xt + i];
+            for (int i = tid; i < m; i += NT) a.ws_y[(size_t)b * m + i] = sm[L.y + i];
+            if (tid == 0) a.ws_valid[b] = ok ? 1 : 0;
+        }
+    }
+}
+
+// reference window into shared memory (MPC/main.py:87-90)
+__device__ __forceinline__ void tg_ref_window_dev(const DevCfg &c, const SmemLayout &L, double *sm, const tg_ref_spec &sp,
+                                                  const double *brk, const double *coef, int t_index)
+{
+    const int tid = threadIdx.x, NT = blockDim.x, N = c.N;
+    const double t0 = c.vref_advance ? (double)t_index * c.Ts : 0.0;
+    const double vx0 = sm[L.x0 + 3];
+    for (int k = tid; k <= N; k += NT) sm[L.vref + k] = tg_vref_at(sp.vref_kind, sp.vref, t0 + (double)k * c.Ts, vx0);
+    __syncthreads();
+    if (tid == 0) {
+        double xs = sm[L.x0];
+        sm[L.Xr] = xs;
+        for (int k = 0; k < N; ++k) { xs = xs + sm[L.vref + k] * c.Ts; sm[L.Xr + k + 1] = xs; }   // :59-61
+    }
+    __syncthreads();
+    for (int k = tid; k <= N; k += NT) {
+        double y, dy;
+        tg_path_at(sp, brk, coef, sm[L.Xr + k], y, dy);
+        sm[L.Yr + k] = y;
+        sm[L.Pr + k] = atan(dy);   // :66
+    }
+    __syncthreads();
+}
+
+struct LoopArgs {
+    int B, T;
+    const double *x0, *u0;
+    const tg_ref_spec *spec;
+    const double *brk, *coef;
+    long long traj_id0;
+    double *clean, *noisy, *U;
+    int *status_counts;
+    long long *iters_total;
+    double *Hws;
+};
+
+template <int SEG, int S>
+__global__ void __launch_bounds__(((SEG * S * S + 31) / 32) * 32 < 64 ? 64 : ((SEG * S * S + 31) / 32) * 32)
+tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, const __grid_constant__ LoopArgs a)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int N = c.N, n = c.n, m = c.m, ms = c.ms, ns = c.ns, T = a.T;
+    double *Hws = a.Hws ? a.Hws + (size_t)blockIdx.x * n * c.NP : nullptr;
+    StepTaps tap = {};
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        __syncthreads();
+        const tg_ref_spec sp = a.spec[b];
+        const unsigned long long seed = c.seed_base + (unsigned long long)(a.traj_id0 + b);
+        double *clean = a.clean + (size_t)b * (T + 1) * 6, *noisy = a.noisy + (size_t)b * (T + 1) * 6;
+        double *U = a.U + (size_t)b * T * 2;
+        if (tid < 6) { const double v_ = a.x0[6 * (size_t)b + tid]; sm[L.x0 + tid] = v_; clean[tid] = v_; }
+        if (tid < 2) sm[L.uprev + tid] = a.u0[2 * (size_t)b + tid];
+        if (tid >= 32 && tid < 35) {   // row 0 noise
+            const int pr = tid - 32;
+            uint32_t r[4];
+            tg_philox4x32_10(0u, (uint32_t)(pr >> 1), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+            double n0, n1;
+            tg_box_muller(r[(pr & 1) * 2], r[(pr & 1) * 2 + 1], n0, n1);
+            noisy[2 * pr] = a.x0[6 * (size_t)b + 2 * pr] + c.noise_std[2 * pr] * n0;
+            noisy[2 * pr + 1] = a.x0[6 * (size_t)b + 2 * pr + 1] + c.noise_std[2 * pr + 1] * n1;
+        }
+        int cnt[TG_NUM_STATUS];
+#pragma unroll
+        for (int i = 0; i < TG_NUM_STATUS; ++i) cnt[i] = 0;
+        long long itsum = 0;
+        bool warm = false;
+        __syncthreads();
+        for (int t = 0; t < T; ++t) {
+            tg_ref_window_dev(c, L, sm, sp, a.brk, a.coef, t);
+            const StepResult r = tg_mpc_step_body<SEG, S>(c, L, sm, warm, Hws, tap);
+            const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);
+#pragma unroll
+            for (int i = 0; i < TG_NUM_STATUS; ++i) cnt[i] += (r.status == i) ? 1 : 0;
+            itsum += r.iters;
+            // shifted warm start for the next step, in the next step's dU coordinates
+            double nx = 0.0, nyb = 0.0, nyr = 0.0;
+            if (tid < n) {
+                const double d0 = sm[L.xt + (tid & 1)];
+                nx = ((tid + 2 < n) ? sm[L.xt + tid + 2] : sm[L.xt + tid]) - d0;
+                if (tid + 2 < n) { nyb = sm[L.y + tid + 2]; nyr = sm[L.y + n + tid + 2]; }
+            }
+            if (tid == 0) {   // plant (MPC/main.py:97) + outputs
+                const double ud = sm[L.uprev], udel = sm[L.uprev + 1];
+                const double u0 = ok ? ud + sm[L.xt] : ud, u1 = ok ? udel + sm[L.xt + 1] : udel;
+                double xs[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) xs[i] = sm[L.x0 + i];
+                tg_plant_step(c, xs, u0, u1);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { sm[L.misc + 8 + i] = xs[i]; clean[6 * (size_t)(t + 1) + i] = xs[i]; }
+                U[2 * (size_t)t] = u0; U[2 * (size_t)t + 1] = u1;
+                sm[L.misc + 14] = u0; sm[L.misc + 15] = u1;
+            }
+            __syncthreads();
+            // commit the new state / warm start
+            if (tid < 6) sm[L.x0 + tid] = sm[L.misc + 8 + tid];
+            if (tid < 2) sm[L.uprev + tid] = sm[L.misc + 14 + tid];
+            if (tid < n) { sm[L.x + tid] = nx; sm[L.y + tid] = nyb; sm[L.y + n + tid] = nyr; }
+            if (ms > 0) {
+                double tmp[4];   // ms <= 6 N <= 4 NT for every supported shape
+#pragma unroll
+                for (int r_ = 0; r_ < 4; ++r_) { const int i = tid + r_ * NT; tmp[r_] = (i + ns < ms) ? sm[L.y + 2 * n + i + ns] : 0.0; }
+                __syncthreads();
+#pragma unroll
+                for (int r_ = 0; r_ < 4; ++r_) { const int i = tid + r_ * NT; if (i < ms) sm[L.y + 2 * n + i] = tmp[r_]; }
+            }
+            if (tid >= 32 && tid < 35) {   // sensor noise of row t+1 (generation_type2.py:190-200), never fed back
+                const int pr = tid - 32;
+                uint32_t r4[4];
+                tg_philox4x32_10((uint32_t)(t + 1), (uint32_t)(pr >> 1), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r4);
+                double n0, n1;
+                tg_box_muller(r4[(pr & 1) * 2], r4[(pr & 1) * 2 + 1], n0, n1);
+                noisy[6 * (size_t)(t + 1) + 2 * pr] = sm[L.misc + 8 + 2 * pr] + c.noise_std[2 * pr] * n0;
+                noisy[6 * (size_t)(t + 1) + 2 * pr + 1] = sm[L.misc + 8 + 2 * pr + 1] + c.noise_std[2 * pr + 1] * n1;
+            }
+            warm = ok && c.warm_start;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            if (a.status_counts)
+                for (int i = 0; i < TG_NUM_STATUS; ++i) a.status_counts[(size_t)b * TG_NUM_STATUS + i] = cnt[i];
+            if (a.iters_total) a.iters_total[b] = itsum;
+        }
+    }
+}
+
+__global__ void tg_ref_window_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, int B,
+                                     const double *x0, const tg_ref_spec *spec, const double *brk, const double *coef,
+                                     int t_index, double *path_ref, double *vref)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, NT = blockDim.x, N = c.N;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        if (tid < 6) sm[L.x0 + tid] = x0[6 * (size_t)b + tid];
+        __syncthreads();
+        const tg_ref_spec sp = spec[b];
+        tg_ref_window_dev(c, L, sm, sp, brk, coef, t_index);
+        for (int k = tid; k <= N; k += NT) {
+            double *pr = path_ref + 3 * ((size_t)b * (N + 1) + k);
+            pr[0] = sm[L.Xr + k]; pr[1] = sm[L.Yr + k]; pr[2] = sm[L.Pr + k];
+            vref[(size_t)b * (N + 1) + k] = sm[L.vref + k];
+        }
+    }
+}
+
+__global__ void tg_plant_kernel(const __grid_constant__ DevCfg c, int B, int T, const double *x0, const double *U, double *X)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double xs[6];
+    double *Xo = X + (size_t)b * (T + 1) * 6;
+    for (int i = 0; i < 6; ++i) { xs[i] = x0[6 * (size_t)b + i]; Xo[i] = xs[i]; }
+    for (int t = 0; t < T; ++t) {
+        tg_plant_step(c, xs, U[((size_t)b * T + t) * 2], U[((size_t)b * T + t) * 2 + 1]);
+        for (int i = 0; i < 6; ++i) Xo[6 * (size_t)(t + 1) + i] = xs[i];
+    }
+}
+
+__global__ void tg_noise_kernel(unsigned long long seed0, int n_traj, int n_rows, double *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_traj * n_rows) return;
+    const int tr = (int)(i / n_rows), row = (int)(i % n_rows);
+    double nz[6];
+    tg_noise_row(seed0 + (unsigned long long)tr, (uint32_t)row, nz);
+    for (int k = 0; k < 6; ++k) out[6 * i + k] = nz[k];
+}
+
+__global__ void tg_philox_kernel(unsigned long long seed, uint32_t first, uint32_t block, int n, uint32_t *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r[4];
+    tg_philox4x32_10(first + (uint32_t)i, block, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    for (int k = 0; k < 4; ++k) out[4 * (size_t)i + k] = r[k];
+}
+
+template <typename T>
+__global__ void tg_fma_peak_kernel(T *out, int iters)
+{
+    T a0 = (T)threadIdx.x * (T)1e-3, a1 = a0 + (T)1, a2 = a0 + (T)2, a3 = a0 + (T)3, a4 = a0 + (T)4, a5 = a0 + (T)5,
+      a6 = a0 + (T)6, a7 = a0 + (T)7;
+    const T b = (T)0.999, cc = (T)1e-4;
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * b + cc; a1 = a1 * b + cc; a2 = a2 * b + cc; a3 = a3 * b + cc;
+        a4 = a4 * b + cc; a5 = a5 * b + cc; a6 = a6 * b + cc; a7 = a7 * b + cc;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct Shape { int SEG, S, NP, NT; };
+
+static bool pick_shape(int N, Shape &s)
+{
+    const int n = 2 * N;
+    if (n <= 24) { s.SEG = 12; s.S = 2; }
+    else if (n <= 40) { s.SEG = 20; s.S = 2; }
+    else if (n <= 64) { s.SEG = 16; s.S = 4; }
+    else if (n <= 80) { s.SEG = 20; s.S = 4; }
+    else if (n <= 112) { s.SEG = 28; s.S = 4; }
+    else return false;
+    s.NP = s.SEG * s.S;
+    s.NT = ((n * s.S + 31) / 32) * 32;
+    if (s.NT < 64) s.NT = 64;
+    return true;
+}
+
+struct tg_handle {
+    tg_config cfg;
+    DevCfg dc;
+    SmemLayout L;
+    Shape shape;
+    int device, num_sms, grid_cap;
+    size_t smem_bytes;
+    cudaStream_t stream;
+    long long launches;
+    double *Hws; size_t Hws_elems;
+    // warm-start state for the step API
+    double *ws_x, *ws_y; int *ws_valid; int ws_B;
+    // staging for *_host entry points
+    void *dstage; size_t dstage_bytes;
+    void *hstage; size_t hstage_bytes;
+};
+
+template <typename F>
+static int dispatch_shape(const Shape &s, F &&f)
+{
+    if (s.SEG == 12 && s.S == 2) return f(std::integral_constant<int, 12>(), std::integral_constant<int, 2>());
+    if (s.SEG == 20 && s.S == 2) return f(std::integral_constant<int, 20>(), std::integral_constant<int, 2>());
+    if (s.SEG == 16 && s.S == 4) return f(std::integral_constant<int, 16>(), std::integral_constant<int, 4>());
+    if (s.SEG == 20 && s.S == 4) return f(std::integral_constant<int, 20>(), std::integral_constant<int, 4>());
+    if (s.SEG == 28 && s.S == 4) return f(std::integral_constant<int, 28>(), std::integral_constant<int, 4>());
+    return fail(TG_ERR_UNSUPPORTED, "no kernel shape for this horizon");
+}
+
+extern "C" {
+
+const char *tg_last_error(void) { return g_err.c_str(); }
+int tg_version(void) { return TG_VERSION; }
+
+void tg_default_config(tg_config *c)
+{
+    memset(c, 0, sizeof(*c));
+    c->N = 20; c->model = TG_MODEL_MPC; c->plant = TG_PLANT_MPC; c->jacobian = TG_JAC_ANALYTIC;
+    c->Ts = 0.02;
+    const double p[TG_NPARAMS] = {0.287, 0.0545, 0.0518, 0.00035, 3.3852, 1.2691, 0.1737, 2.579, 1.2, 0.192,
+                                  0.041, 27.8e-6, 0.029, 0.033, 9.81, 0.6, 0.3};
+    memcpy(c->params, p, sizeof(p));
+    c->q_c = 6.0; c->q_phi = 0.5; c->q_vx = 0.5;
+    c->R[0] = 0.02; c->R[3] = 2.0; c->Rd[0] = 0.01; c->Rd[3] = 5.0;
+    c->u_lo[0] = -1.0; c->u_hi[0] = 1.0; c->u_lo[1] = -0.6; c->u_hi[1] = 0.6;
+    c->du_lo[0] = -0.5; c->du_hi[0] = 0.5; c->du_lo[1] = -0.3; c->du_hi[1] = 0.3;
+    for (int i = 0; i < 6; ++i) { c->x_lo[i] = -TG_INF; c->x_hi[i] = TG_INF; }
+    c->rho = 0.1; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-5; c->eps_rel = 1e-5; c->eps_prim_inf = 1e-4;
+    c->adaptive_rho_tol = 5.0; c->max_iter = 4000; c->check_every = 10; c->adaptive_rho = 1; c->adaptive_rho_min_iter = 20;
+    c->warm_start = 0; c->vref_advance = 0;
+    const double sd[6] = {0.05, 0.05, 0.003, 0.010, 0.003, 0.030};
+    memcpy(c->noise_std, sd, sizeof(sd));
+    c->noise_seed_base = 12345ull;
+}
+
+int tg_device_count(int *n) { CK(cudaGetDeviceCount(n)); return TG_OK; }
+
+int tg_create(const tg_config *cfg, int device, tg_handle **out)
+{
+    if (!cfg || !out) return fail(TG_ERR_INVALID, "null argument");
+    if (cfg->N < 1) return fail(TG_ERR_INVALID, "N must be >= 1");
+    if (!(cfg->Ts > 0)) return fail(TG_ERR_INVALID, "Ts must be > 0");
+    if (cfg->max_iter < 1 || cfg->check_every < 1) return fail(TG_ERR_INVALID, "max_iter and check_every must be >= 1");
+    if (!(cfg->rho > 0) || !(cfg->sigma > 0) || !(cfg->alpha > 0 && cfg->alpha < 2)) return fail(TG_ERR_INVALID, "rho, sigma > 0 and 0 < alpha < 2 required");
+    Shape sh;
+    if (!pick_shape(cfg->N, sh)) return fail(TG_ERR_UNSUPPORTED, "horizon N > 56 is not supported");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) return fail(TG_ERR_CUDA, "no CUDA device: libtrajgen has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(TG_ERR_INVALID, "bad device index");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(TG_ERR_UNSUPPORTED, "libtrajgen is built for sm_100a (B200) only");
+
+    tg_handle *h = new (std::nothrow) tg_handle();
+    if (!h) return fail(TG_ERR_NOMEM, "out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg; h->shape = sh; h->device = device; h->num_sms = prop.multiProcessorCount;
+    DevCfg &d = h->dc;
+    d.N = cfg->N; d.n = 2 * cfg->N; d.model = cfg->model; d.plant = cfg->plant; d.jacobian = cfg->jacobian;
+    d.ns = 0;
+    for (int i = 0; i < 6; ++i)
+        if (cfg->x_lo[i] > -TG_INF || cfg->x_hi[i] < TG_INF) d.sidx[d.ns++] = i;
+    d.ms = d.ns * d.N; d.m = 4 * d.N + d.ms; d.NP = sh.NP;
+    d.max_iter = cfg->max_iter; d.check_every = cfg->check_every; d.adaptive_rho = cfg->adaptive_rho;
+    d.adaptive_rho_min_iter = cfg->adaptive_rho_min_iter; d.warm_start = cfg->warm_start; d.vref_advance = cfg->vref_advance;
+    d.Ts = cfg->Ts;
+    memcpy(d.p, cfg->params, sizeof(d.p));
+    d.q_c = cfg->q_c; d.q_phi = cfg->q_phi; d.q_vx = cfg->q_vx;
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+            d.Rs[i * 2 + j] = 0.5 * (cfg->R[i * 2 + j] + cfg->R[j * 2 + i]);
+            d.Rds[i * 2 + j] = 0.5 * (cfg->Rd[i * 2 + j] + cfg->Rd[j * 2 + i]);
+        }
+    memcpy(d.u_lo, cfg->u_lo, 16); memcpy(d.u_hi, cfg->u_hi, 16); memcpy(d.du_lo, cfg->du_lo, 16); memcpy(d.du_hi, cfg->du_hi, 16);
+    memcpy(d.x_lo, cfg->x_lo, 48); memcpy(d.x_hi, cfg->x_hi, 48);
+    d.rho = cfg->rho; d.sigma = cfg->sigma; d.alpha = cfg->alpha; d.eps_abs = cfg->eps_abs; d.eps_rel = cfg->eps_rel;
+    d.eps_pinf = cfg->eps_prim_inf; d.adapt_tol = cfg->adaptive_rho_tol > 1.0 ? cfg->adaptive_rho_tol : 5.0;
+    memcpy(d.noise_std, cfg->noise_std, 48);
+    d.seed_base = cfg->noise_seed_base;
+
+    h->L = tg_make_layout(d.N, d.ms, d.NP);
+    h->smem_bytes = (size_t)h->L.total * sizeof(double);
+    if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+        delete h;
+        return fail(TG_ERR_UNSUPPORTED, "state-bound rows x horizon exceed the 227 KB shared memory of one CTA");
+    }
+    int occ = 0;
+    int rc = dispatch_shape(sh, [&](auto SEG, auto S) -> int {
+        auto k1 = tg_mpc_step_kernel<decltype(SEG)::value, decltype(S)::value>;
+        auto k2 = tg_closed_loop_kernel<decltype(SEG)::value, decltype(S)::value>;
+        CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        int o1 = 0, o2 = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k1, sh.NT, h->smem_bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k2, sh.NT, h->smem_bytes));
+        occ = o1 < o2 ? o1 : o2;
+        return TG_OK;
+    });
+    if (rc != TG_OK) { delete h; return rc; }
+    if (occ < 1) { delete h; return fail(TG_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration"); }
+    h->grid_cap = occ * h->num_sms;
+    CK(cudaFuncSetAttribute(tg_ref_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    if (d.adaptive_rho) {
+        h->Hws_elems = (size_t)h->grid_cap * d.n * d.NP;
+        CK(cudaMalloc(&h->Hws, h->Hws_elems * sizeof(double)));
+    }
+    h->stream = 0;
+    *out = h;
+    return TG_OK;
+}
+
+int tg_destroy(tg_handle *h)
+{
+    if (!h) return TG_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->Hws); cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_valid); cudaFree(h->dstage);
+    if (h->hstage) cudaFreeHost(h->hstage);
+    delete h;
+    return TG_OK;
+}
+
+int tg_set_stream(tg_handle *h, void *s) { if (!h) return fail(TG_ERR_INVALID, "null handle"); h->stream = (cudaStream_t)s; return TG_OK; }
+int tg_synchronize(tg_handle *h) { if (!h) return fail(TG_ERR_INVALID, "null handle"); CK(cudaStreamSynchronize(h->stream)); return TG_OK; }
+int tg_kernel_launches(tg_handle *h, int64_t *count) { if (!h || !count) return fail(TG_ERR_INVALID, "null argument"); *count = h->launches; return TG_OK; }
+
+static int launch_step(tg_handle *h, StepArgs &a)
+{
+    if (a.B <= 0) return TG_OK;   // empty batch: nothing to do
+    CK(cudaSetDevice(h->device));
+    a.Hws = h->Hws;
+    const int grid = a.B < h->grid_cap ? a.B : h->grid_cap;
+    int rc = dispatch_shape(h->shape, [&](auto SEG, auto S) -> int {
+        tg_mpc_step_kernel<decltype(SEG)::value, decltype(S)::value><<<grid, h->shape.NT, h->smem_bytes, h->stream>>>(h->dc, h->L, a);
+        return TG_OK;
+    });
+    if (rc != TG_OK) return rc;
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_linearize(tg_handle *h, int B, const double *x0, const double *u_prev, double *A, double *Bm, double *g, double *xbar)
+{
+    if (!h || B < 0 || (B > 0 && (!x0 || !u_prev))) return fail(TG_ERR_INVALID, "bad argument");
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.x0 = x0; a.u_prev = u_prev; a.path_ref = nullptr; a.vref = nullptr;
+    a.A = A; a.Bm = Bm; a.g = g; a.xbar = xbar; a.stop = 1;
+    // the tap does not read the reference window; point it at x0 so loads stay in bounds
+    a.path_ref = nullptr;
+    return launch_step(h, a);
+}
+
+int tg_assemble(tg_handle *h, int B, const double *x0, const double *u_prev, const double *path_ref, const double *vref,
+                double *H, double *q, double *c0, double *l, double *u, double *Gs)
+{
+    if (!h || B < 0 || (B > 0 && (!x0 || !u_prev || !path_ref))) return fail(TG_ERR_INVALID, "bad argument");
+    if ((l == nullptr) != (u == nullptr)) return fail(TG_ERR_INVALID, "l and u must be given together");
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.x0 = x0; a.u_prev = u_prev; a.path_ref = path_ref; a.vref = vref;
+    a.H = H; a.q = q; a.c0 = c0; a.l = l; a.u = u; a.Gs = Gs; a.stop = 2;
+    return launch_step(h, a);
+}
+
+static int ensure_ws(tg_handle *h, int B)
+{
+    if (!h->cfg.warm_start || B <= h->ws_B) return TG_OK;
+    cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_valid);
+    h->ws_x = h->ws_y = nullptr; h->ws_valid = nullptr; h->ws_B = 0;
+    CK(cudaMalloc(&h->ws_x, (size_t)B * h->dc.n * sizeof(double)));
+    CK(cudaMalloc(&h->ws_y, (size_t)B * h->dc.m * sizeof(double)));
+    CK(cudaMalloc(&h->ws_valid, (size_t)B * sizeof(int)));
+    CK(cudaMemsetAsync(h->ws_valid, 0, (size_t)B * sizeof(int), h->stream));
+    h->ws_B = B;
+    return TG_OK;
+}
+
+int tg_mpc_step(tg_handle *h, int B, const double *x0, const double *u_prev, const double *path_ref, const double *vref,
+                double *u_cmd, int32_t *status, int32_t *iters, double *objective, double *U_opt, double *X_opt, double *y_opt)
+{
+    if (!h || B < 0 || (B > 0 && (!x0 || !u_prev || !path_ref || !u_cmd))) return fail(TG_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_ws(h, B);
+    if (rc != TG_OK) return rc;
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.x0 = x0; a.u_prev = u_prev; a.path_ref = path_ref; a.vref = vref;
+    a.u_cmd = u_cmd; a.status = status; a.iters = iters; a.objective = objective; a.U_opt = U_opt; a.X_opt = X_opt; a.y_opt = y_opt;
+    a.ws_x = h->ws_x; a.ws_y = h->ws_y; a.ws_valid = h->ws_valid;
+    return launch_step(h, a);
+}
+
+int tg_ref_window(tg_handle *h, int B, const double *x0, const tg_ref_spec *spec, const double *brk, const double *coef,
+                  int t_index, double *path_ref, double *vref)
+{
+    if (!h || B < 0 || (B > 0 && (!x0 || !spec || !path_ref || !vref))) return fail(TG_ERR_INVALID, "bad argument");
+    if (B == 0) return TG_OK;
+    CK(cudaSetDevice(h->device));
+    const int grid = B < 8 * h->num_sms ? B : 8 * h->num_sms;
+    tg_ref_window_kernel<<<grid, 64, h->smem_bytes, h->stream>>>(h->dc, h->L, B, x0, spec, brk, coef, t_index, path_ref, vref);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_closed_loop(tg_handle *h, int B, int T, const double *x0, const double *u0, const tg_ref_spec *spec,
+                   const double *brk, const double *coef, int64_t traj_id0, double *clean, double *noisy, double *U,
+                   int32_t *status_counts, int64_t *iters_total)
+{
+    if (!h || B < 0 || T < 0 || (B > 0 && (!x0 || !u0 || !spec || !clean || !noisy || (T > 0 && !U)))) return fail(TG_ERR_INVALID, "bad argument");
+    if (B == 0) return TG_OK;
+    CK(cudaSetDevice(h->device));
+    LoopArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.T = T; a.x0 = x0; a.u0 = u0; a.spec = spec; a.brk = brk; a.coef = coef; a.traj_id0 = traj_id0;
+    a.clean = clean; a.noisy = noisy; a.U = U; a.status_counts = status_counts; a.iters_total = (long long *)iters_total;
+    a.Hws = h->Hws;
+    const int grid = B < h->grid_cap ? B : h->grid_cap;
+    int rc = dispatch_shape(h->shape, [&](auto SEG, auto S) -> int {
+        tg_closed_loop_kernel<decltype(SEG)::value, decltype(S)::value><<<grid, h->shape.NT, h->smem_bytes, h->stream>>>(h->dc, h->L, a);
+        return TG_OK;
+    });
+    if (rc != TG_OK) return rc;
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_plant_rollout(tg_handle *h, int B, int T, const double *x0, const double *U, double *X)
+{
+    if (!h || B < 0 || T < 0 || (B > 0 && (!x0 || !X || (T > 0 && !U)))) return fail(TG_ERR_INVALID, "bad argument");
+    if (B == 0) return TG_OK;
+    CK(cudaSetDevice(h->device));
+    tg_plant_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->dc, B, T, x0, U, X);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_sensor_noise(tg_handle *h, int64_t traj_id0, int n_traj, int n_rows, double *out)
+{
+    if (!h || n_traj < 0 || n_rows < 0 || ((long long)n_traj * n_rows > 0 && !out)) return fail(TG_ERR_INVALID, "bad argument");
+    const long long tot = (long long)n_traj * n_rows;
+    if (tot == 0) return TG_OK;
+    CK(cudaSetDevice(h->device));
+    tg_noise_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->dc.seed_base + (unsigned long long)traj_id0, n_traj, n_rows, out);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_philox_u32(tg_handle *h, uint64_t seed, uint32_t first, uint32_t block, int n, uint32_t *out)
+{
+    if (!h || n < 0 || (n > 0 && !out)) return fail(TG_ERR_INVALID, "bad argument");
+    if (n == 0) return TG_OK;
+    CK(cudaSetDevice(h->device));
+    tg_philox_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(seed, first, block, n, out);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_fma_peak(tg_handle *h, int dtype, double *tflops)
+{
+    if (!h || !tflops) return fail(TG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    const int blocks = h->num_sms * 8, threads = 256, iters = 1 << 15;
+    void *buf = nullptr;
+    CK(cudaMalloc(&buf, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, h->stream));
+        if (dtype == 0) tg_fma_peak_kernel<double><<<blocks, threads, 0, h->stream>>>((double *)buf, iters);
+        else tg_fma_peak_kernel<float><<<blocks, threads, 0, h->stream>>>((float *)buf, iters);
+        CK(cudaEventRecord(e1, h->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+        h->launches += 1;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+    return TG_OK;
+}
+
+int tg_malloc(void **p, int64_t bytes) { if (!p || bytes < 0) return fail(TG_ERR_INVALID, "bad argument"); *p = nullptr; if (bytes == 0) return TG_OK; CK(cudaMalloc(p, (size_t)bytes)); return TG_OK; }
+int tg_free(void *p) { if (p) CK(cudaFree(p)); return TG_OK; }
+int tg_malloc_host(void **p, int64_t bytes) { if (!p || bytes < 0) return fail(TG_ERR_INVALID, "bad argument"); *p = nullptr; if (bytes == 0) return TG_OK; CK(cudaMallocHost(p, (size_t)bytes)); return TG_OK; }
+int tg_free_host(void *p) { if (p) CK(cudaFreeHost(p)); return TG_OK; }
+int tg_memcpy_h2d(tg_handle *h, void *dst, const void *src, int64_t bytes)
+{
+    if (!h || bytes < 0) return fail(TG_ERR_INVALID, "bad argument");
+    if (bytes == 0) return TG_OK;
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return TG_OK;
+}
+int tg_memcpy_d2h(tg_handle *h, void *dst, const void *src, int64_t bytes)
+{
+    if (!h || bytes < 0) return fail(TG_ERR_INVALID, "bad argument");
+    if (bytes == 0) return TG_OK;
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return TG_OK;
+}
+
+// ---- host-buffer entry points: stage through one device arena, copies on the handle's stream
+struct Arena {
+    char *base; size_t off, cap;
+    void *take(size_t bytes) { size_t o = (off + 255) & ~(size_t)255; off = o + bytes; return (off <= cap) ? base + o : nullptr; }
+};
+static int ensure_dstage(tg_handle *h, size_t bytes)
+{
+    if (bytes <= h->dstage_bytes) return TG_OK;
+    if (h->dstage) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->dstage)); h->dstage = nullptr; h->dstage_bytes = 0; }
+    CK(cudaMalloc(&h->dstage, bytes));
+    h->dstage_bytes = bytes;
+    return TG_OK;
+}
+#define PAD(x) (((size_t)(x) + 255) & ~(size_t)255)
+#define H2D(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream))
+#define D2H(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream))
+
+int tg_mpc_step_host(tg_handle *h, int B, const double *x0, const double *u_prev, const double *path_ref, const double *vref,
+                     double *u_cmd, int32_t *status, int32_t *iters, double *objective, double *U_opt, double *X_opt, double *y_opt)
+{
+    if (!h || B < 0 || (B > 0 && (!x0 || !u_prev || !path_ref || !u_cmd))) return fail(TG_ERR_INVALID, "bad argument");
+    if (B == 0) return TG_OK;
+    CK(cudaSetDevice(h->device));
+    const int N = h->dc.N, n = h->dc.n, m = h->dc.m;
+    const size_t b8 = sizeof(double);
+    const size_t s_x0 = (size_t)B * 6 * b8, s_up = (size_t)B * 2 * b8, s_pr = (size_t)B * (N + 1) * 3 * b8, s_vr = (size_t)B * (N + 1) * b8;
+    const size_t s_uc = (size_t)B * 2 * b8, s_i = (size_t)B * 4, s_ob = (size_t)B * b8, s_U = (size_t)B * n * b8, s_X = (size_t)B * (N + 1) * 6 * b8, s_y = (size_t)B * m * b8;
+    const size_t total = PAD(s_x0) + PAD(s_up) + PAD(s_pr) + PAD(s_vr) + PAD(s_uc) + 2 * PAD(s_i) + PAD(s_ob) + PAD(s_U) + PAD(s_X) + PAD(s_y) + 4096;
+    int rc = ensure_dstage(h, total);
+    if (rc != TG_OK) return rc;
+    Arena ar{(char *)h->dstage, 0, h->dstage_bytes};
+    double *d_x0 = (double *)ar.take(s_x0), *d_up = (double *)ar.take(s_up), *d_pr = (double *)ar.take(s_pr);
+    double *d_vr = vref ? (double *)ar.take(s_vr) : nullptr;
+    double *d_uc = (double *)ar.take(s_uc);
+    int32_t *d_st = (int32_t *)ar.take(s_i), *d_it = (int32_t *)ar.take(s_i);
+    double *d_ob = (double *)ar.take(s_ob);
+    double *d_U = U_opt ? (double *)ar.take(s_U) : nullptr, *d_X = X_opt ? (double *)ar.take(s_X) : nullptr, *d_y = y_opt ? (double *)ar.take(s_y) : nullptr;
+    H2D(d_x0, x0, s_x0); H2D(d_up, u_prev, s_up); H2D(d_pr, path_ref, s_pr);
+    if (vref) H2D(d_vr, vref, s_vr);
+    rc = tg_mpc_step(h, B, d_x0, d_up, d_pr, d_vr, d_uc, d_st, d_it, d_ob, d_U, d_X, d_y);
+    if (rc != TG_OK) return rc;
+    D2H(u_cmd, d_uc, s_uc);
+    if (status) D2H(status, d_st, s_i);
+    if (iters) D2H(iters, d_it, s_i);
+    if (objective) D2H(objective, d_ob, s_ob);
+    if (U_opt) D2H(U_opt, d_U, s_U);
+    if (X_opt) D2H(X_opt, d_X, s_X);
+    if (y_opt) D2H(y_opt, d_y, s_y);
+    CK(cudaStreamSynchronize(h->stream));
+    return TG_OK;
+}
+
+int tg_closed_loop_host(tg_handle *h, int B, int T, const double *x0, const double *u0, const tg_ref_spec *spec,
+                        const double *brk, int64_t n_breaks, const double *coef, int64_t n_coef, int64_t traj_id0,
+                        double *clean, double *noisy, double *U, int32_t *status_counts, int64_t *iters_total)
+{
+    if (!h || B < 0 || T < 0 || (B > 0 && (!x0 || !u0 || !spec || !clean || !noisy || (T > 0 && !U)))) return fail(TG_ERR_INVALID, "bad argument");
+    if (B == 0) return TG_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t b8 = sizeof(double);
+    const size_t s_x0 = (size_t)B * 6 * b8, s_u0 = (size_t)B * 2 * b8, s_sp = (size_t)B * sizeof(tg_ref_spec);
+    const size_t s_bk = (size_t)(n_breaks > 0 ? n_breaks : 0) * b8, s_cf = (size_t)(n_coef > 0 ? n_coef : 0) * 4 * b8;
+    const size_t s_cl = (size_t)B * (T + 1) * 6 * b8, s_U = (size_t)B * T * 2 * b8, s_sc = (size_t)B * TG_NUM_STATUS * 4, s_it = (size_t)B * 8;
+    const size_t total = PAD(s_x0) + PAD(s_u0) + PAD(s_sp) + PAD(s_bk) + PAD(s_cf) + 2 * PAD(s_cl) + PAD(s_U) + PAD(s_sc) + PAD(s_it) + 4096;
+    int rc = ensure_dstage(h, total);
+    if (rc != TG_OK) return rc;
+    Arena ar{(char *)h->dstage, 0, h->dstage_bytes};
+    double *d_x0 = (double *)ar.take(s_x0), *d_u0 = (double *)ar.take(s_u0);
+    tg_ref_spec *d_sp = (tg_ref_spec *)ar.take(s_sp);
+    double *d_bk = s_bk ? (double *)ar.take(s_bk) : nullptr, *d_cf = s_cf ? (double *)ar.take(s_cf) : nullptr;
+    double *d_cl = (double *)ar.take(s_cl), *d_no = (double *)ar.take(s_cl), *d_U = (double *)ar.take(s_U ? s_U : 8);
+    int32_t *d_sc = (int32_t *)ar.take(s_sc);
+    long long *d_it = (long long *)ar.take(s_it);
+    H2D(d_x0, x0, s_x0); H2D(d_u0, u0, s_u0); H2D(d_sp, spec, s_sp);
+    if (s_bk) H2D(d_bk, brk, s_bk);
+    if (s_cf) H2D(d_cf, coef, s_cf);
+    rc = tg_closed_loop(h, B, T, d_x0, d_u0, d_sp, d_bk, d_cf, traj_id0, d_cl, d_no, d_U, d_sc, (int64_t *)d_it);
+    if (rc != TG_OK) return rc;
+    D2H(clean, d_cl, s_cl); D2H(noisy, d_no, s_cl);
+    if (s_U) D2H(U, d_U, s_U);
+    if (status_counts) D2H(status_counts, d_sc, s_sc);
+    if (iters_total) D2H(iters_total, d_it, s_it);
+    CK(cudaStreamSynchronize(h->stream));
+    return TG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+"""Closed-loop MPC dataset generation on B200: the drop-in for the generators' hot path.
+
+Mirrors the shell of generation_traj/generation_type2.py:162-220 (x0 sampling, per-trajectory seeds,
+plant clipping, Gaussian sensor noise, clean/noisy rows) and the closed loop of MPC/main.py:85-101,
+with the control sequence produced by the MPC instead of the open-loop synthesis.  All T steps of all
+B trajectories run inside ONE kernel launch (tg_closed_loop); this module builds the per-trajectory
+scenario table, calls the C ABI and lays the results out in the reference's dataset schema.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .mpc import BatchedMPC, Params  # noqa: F401
+
+PATH_PARABOLA, PATH_SINE, PATH_SPLINE = 0, 1, 2
+VREF_HOLD, VREF_CONST, VREF_RAMP, VREF_TRAPEZOID, VREF_SINE = 0, 1, 2, 3, 4
+
+CLEAN_COLS = ["t", "X", "Y", "phi", "vx", "vy", "omega", "d", "delta", "trajectory_id"]   # generation_type1.py:327
+NOISY_COLS = ["t", "X", "Y", "vx", "vy", "omega", "d", "delta", "trajectory_id"]
+# generation_type1.py:260-265 / generation_type2.py:171-174
+X0_RANGES_TYPE1 = ((-2.0, 2.0), (-2.0, 2.0), (-np.pi, np.pi), (0.4, 1.5), (-0.05, 0.05), (-1.0, 1.0))
+X0_RANGES_TYPE2 = ((-2.0, 2.0), (-2.0, 2.0), (-np.pi, np.pi), (0.2, 0.6), (-0.05, 0.05), (-1.0, 1.0))
+
+
+def d_steady_state(v, p=Params):
+    """MPC/main.py:9-18."""
+    return (p["Cr0"] + p["Cr2"] * v ** 2) / (p["Cm1"] - p["Cm2"] * v)
+
+
+class Scenarios:
+    """Per-trajectory reference scenarios (tg_ref_spec table + shared spline tables)."""
+
+    def __init__(self, n):
+        self.spec = np.zeros(n, dtype=_lib.REF_SPEC_DTYPE)
+        self.spec["path_kind"] = PATH_PARABOLA
+        self.spec["path"][:, 0] = 0.1                      # MPC/main.py:64
+        self.spec["vref_kind"] = VREF_RAMP
+        self.spec["vref"][:, :3] = (0.8, 2.0, 2.0)         # MPC/main.py:87
+        self._breaks, self._coef = [], []
+
+    def __len__(self):
+        return len(self.spec)
+
+    def set_parabola(self, i, c2=0.1, c1=0.0, c0=0.0):
+        self.spec["path_kind"][i] = PATH_PARABOLA
+        self.spec["path"][i] = np.stack(np.broadcast_arrays(c2, c1, c0, 0.0), -1)
+
+    def set_sine(self, i, A=0.5, k=0.5, psi=0.0, c0=0.0):
+        self.spec["path_kind"][i] = PATH_SINE
+        self.spec["path"][i] = np.stack(np.broadcast_arrays(A, k, psi, c0), -1)
+
+    def set_spline(self, i, knots_x, knots_y):
+        """natural cubic spline y(x) through the knots (scipy CubicSpline, as generation_type1.py:97 uses)."""
+        from scipy.interpolate import CubicSpline
+        cs = CubicSpline(np.asarray(knots_x, float), np.asarray(knots_y, float), bc_type="natural")
+        first = sum(len(b) for b in self._breaks)
+        K = cs.c.shape[1]
+        self._breaks.append(np.asarray(cs.x[:K], float))
+        self._coef.append(np.ascontiguousarray(cs.c.T, dtype=float))
+        self.spec["path_kind"][i] = PATH_SPLINE
+        self.spec["spline_first"][i] = first
+        self.spec["spline_count"][i] = K
+
+    def set_vref(self, i, kind, *prm):
+        self.spec["vref_kind"][i] = kind
+        cols = list(prm) + [0.0] * (6 - len(prm))
+        self.spec["vref"][i] = np.stack(np.broadcast_arrays(*cols), -1)
+
+    def tables(self):
+        if not self._breaks:
+            return np.zeros(0), np.zeros((0, 4))
+        return np.concatenate(self._breaks), np.concatenate(self._coef, axis=0)
+
+    def slice(self, lo, hi):
+        s = Scenarios(0)
+        s.spec = self.spec[lo:hi].copy()
+        s._breaks, s._coef = self._breaks, self._coef      # spline_first indexes the shared tables
+        return s
+
+
+class ClosedLoopGenerator(BatchedMPC):
+    """MPC-in-the-loop trajectory generator.  Keyword arguments are mpc_step's plus ``plant``
+    (PLANT_MPC = MPC/main.py:97; PLANT_GEN1/2 = the generators' clipped plants), ``warm_start``,
+    ``noise_std`` and ``noise_seed_base`` (generation_type2.py:31-43,191)."""
+
+    def __init__(self, device=0, warm_start=True, **kwargs):
+        super().__init__(device=device, warm_start=warm_start, **kwargs)
+
+    def generate(self, x0, u0, scenarios, T, traj_id0=0):
+        """x0[B,6], u0[B,2], scenarios (len B), T steps -> dict(clean[B,T+1,6], noisy[B,T+1,6], U[B,T,2],
+        status_counts[B,6], iters_total[B]).  Row 0 of clean is x0; noise seed = base + traj_id0 + i."""
+        x0 = np.ascontiguousarray(np.asarray(x0, float).reshape(-1, 6))
+        B = x0.shape[0]
+        u0 = self._arr(np.asarray(u0, float).reshape(-1, 2), (B, 2))
+        if len(scenarios) != B:
+            raise ValueError("one scenario per trajectory required")
+        spec = np.ascontiguousarray(scenarios.spec)
+        brk, coef = scenarios.tables()
+        out = {"clean": np.empty((B, T + 1, 6)), "noisy": np.empty((B, T + 1, 6)), "U": np.empty((B, T, 2)),
+               "status_counts": np.zeros((B, _lib.TG_NUM_STATUS), np.int32), "iters_total": np.zeros(B, np.int64)}
+        _lib.check(_lib.load().tg_closed_loop_host(
+            self._h, B, int(T), _lib.ptr(x0), _lib.ptr(u0), spec.ctypes.data, _lib.ptr(brk) if len(brk) else None,
+            len(brk), _lib.ptr(coef) if len(coef) else None, len(coef), int(traj_id0),
+            _lib.ptr(out["clean"]), _lib.ptr(out["noisy"]), _lib.ptr(out["U"]), _lib.ptr(out["status_counts"]),
+            _lib.ptr(out["iters_total"])))
+        return out
+
+    def ref_window(self, x0, scenarios, t_index=0):
+        """a10 tap: -> path_ref[B,N+1,3], vref[B,N+1] (MPC/main.py:87-90)."""
+        x0 = np.ascontiguousarray(np.asarray(x0, float).reshape(-1, 6))
+        B, N = x0.shape[0], self.N
+        spec = np.ascontiguousarray(scenarios.spec)
+        brk, coef = scenarios.tables()
+        bufs = self._on_device([x0, spec.view(np.uint8), brk if len(brk) else None, coef if len(coef) else None])
+        op, ov = _lib.DeviceBuffer(B * (N + 1) * 3 * 8), _lib.DeviceBuffer(B * (N + 1) * 8)
+        _lib.check(_lib.load().tg_ref_window(self._h, B, bufs[0].ptr, bufs[1].ptr, bufs[2].ptr if bufs[2] else None,
+                                             bufs[3].ptr if bufs[3] else None, int(t_index), op.ptr, ov.ptr))
+        return self._from_device(op, (B, N + 1, 3)), self._from_device(ov, (B, N + 1))
+
+    def plant_rollout(self, x0, U):
+        """K4 tap: open-loop Euler integration with the configured plant (generation_type1.py:70-84)."""
+        x0 = np.ascontiguousarray(np.asarray(x0, float).reshape(-1, 6))
+        B = x0.shape[0]
+        U = np.ascontiguousarray(np.asarray(U, float))
+        T = U.shape[1]
+        bx, bu = self._on_device([x0, U])
+        oX = _lib.DeviceBuffer(B * (T + 1) * 6 * 8)
+        _lib.check(_lib.load().tg_plant_rollout(self._h, B, T, bx.ptr, bu.ptr, oX.ptr))
+        return self._from_device(oX, (B, T + 1, 6))
+
+    def sensor_noise_normals(self, traj_id0, n_traj, n_rows):
+        """K4 tap: standard normals [n_traj, n_rows, 6] of seeds noise_seed_base + traj_id0 + i."""
+        o = _lib.DeviceBuffer(max(n_traj * n_rows * 6 * 8, 8))
+        _lib.check(_lib.load().tg_sensor_noise(self._h, int(traj_id0), int(n_traj), int(n_rows), o.ptr))
+        return self._from_device(o, (n_traj, n_rows, 6))
+
+    def philox_u32(self, seed, first, block, n):
+        o = _lib.DeviceBuffer(max(n * 16, 16))
+        _lib.check(_lib.load().tg_philox_u32(self._h, int(seed), int(first), int(block), int(n), o.ptr))
+        return self._from_device(o, (n, 4), np.uint32)
+
+    def fma_peak_tflops(self, dtype="f64"):
+        v = ctypes.c_double()
+        _lib.check(_lib.load().tg_fma_peak(self._h, 0 if dtype == "f64" else 1, ctypes.byref(v)))
+        return v.value
+
+
+# ----------------------------------------------------------------------------------- dataset schema
+def sample_x0(num_traj, seed=42, ranges=X0_RANGES_TYPE2):
+    """generation_type2.py:164,171-174: six successive rng.uniform draws per trajectory from default_rng(seed)."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((num_traj, 6))
+    for i in range(num_traj):
+        for j, (lo, hi) in enumerate(ranges):
+            out[i, j] = rng.uniform(lo, hi)
+    return out
+
+
+def to_frames(result, Ts, traj_id0=0):
+    """-> (clean DataFrame, noisy DataFrame) in the reference schema (generation_type2.py:202-216,309-317):
+    T+1 rows per trajectory, t = k Ts, last row's d, delta = NaN, noisy has no phi."""
+    import pandas as pd
+    clean, noisy, U = result["clean"], result["noisy"], result["U"]
+    B, T1, _ = clean.shape
+    t = np.tile(np.arange(T1) * Ts, B)
+    tid = np.repeat(np.arange(traj_id0, traj_id0 + B), T1)
+    Upad = np.concatenate([U, np.full((B, 1, 2), np.nan)], axis=1).reshape(B * T1, 2)
+    frames = []
+    for S in (clean, noisy):
+        S2 = S.reshape(B * T1, 6)
+        frames.append(pd.DataFrame({"t": t, "X": S2[:, 0], "Y": S2[:, 1], "phi": S2[:, 2], "vx": S2[:, 3],
+                                    "vy": S2[:, 4], "omega": S2[:, 5], "d": Upad[:, 0], "delta": Upad[:, 1],
+                                    "trajectory_id": tid}))
+    return frames[0][CLEAN_COLS], frames[1][NOISY_COLS]
+
+
+def write_csv(result, Ts, clean_path, noisy_path, traj_id0=0):
+    """clean/noisy CSV files exactly as generation_type2.py:319-322 writes them (pandas to_csv, index=False)."""
+    c, n = to_frames(result, Ts, traj_id0)
+    c.to_csv(clean_path, index=False)
+    n.to_csv(noisy_path, index=False)
+
+
+def to_loader_tensors(result, T_steps):
+    """The arrays KalmanNet/data_loader.py:33-53 would build from the CSVs, without the CSV round trip:
+    y[B,5,T] noisy (X,Y,vx,vy,omega), u[B,2,T], x[B,6,T] clean; float32."""
+    clean, noisy, U = result["clean"], result["noisy"], result["U"]
+    y = noisy[:, :T_steps][:, :, [0, 1, 3, 4, 5]].transpose(0, 2, 1).astype(np.float32)
+    u = U[:, :T_steps].transpose(0, 2, 1).astype(np.float32)
+    x = clean[:, :T_steps].transpose(0, 2, 1).astype(np.float32)
+    return y, u, x
