@@ -1,0 +1,158 @@
+"""Generates the committed fixtures under tests/golden/ (run in the BUILD container only: it imports
+the reference from /root/reference through oracle/refload.py, which the GPU box does not have).
+
+  python tests/golden/make_golden.py            # reference-pinned fixtures + oracle-made QP fixtures
+
+reference_*.npz / reference_*.csv  = outputs of the reference's OWN code (pinned parity):
+    f_cont (three variants), linearize_discretize, vref profiles + reference window, gen1/gen2 plant
+    integration with clipping, gen2 dataset rows and CSV text, PCG64 noise facts.
+oracle_*.npz = outputs of oracle/ (the QP cannot be run through CVXPY/OSQP here -> PARITY UNPINNED):
+    per-step QP optima (interior point, 1e-10) and closed-loop trajectories.
+"""
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+from oracle import dynamics as dyn, mpc as ompc, refgen as R, refload  # noqa: E402
+
+
+def reference_fixtures():
+    m = refload.load_mpc()
+    g1 = refload.load_gen1()
+    g2 = refload.load_gen2()
+    rng = np.random.default_rng(20251018)
+    n = 64
+    X = np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n), rng.uniform(-np.pi, np.pi, n), rng.uniform(-0.5, 2.5, n),
+                  rng.uniform(-0.5, 0.5, n), rng.uniform(-6, 6, n)], axis=1)
+    U = np.stack([rng.uniform(-1, 1, n), rng.uniform(-0.6, 0.6, n)], axis=1)
+    # SURVEY appendix A points first
+    X[0] = [0.3, -0.2, 0.4, 1.2, 0.08, -0.7]; U[0] = [0.35, -0.12]
+    X[1] = [0.0, 0.0, -1.0, 0.2, 0.25, 3.0]; U[1] = [0.8, 0.5]
+    X[2] = [0.0, 0.5, 0.0, 1.0, 0.0, 0.0]; U[2] = [(0.0518 + 0.00035) / (0.287 - 0.0545), 0.0]
+    X[3] = [0.0, 0.0, 0.0, 0.0, 0.1, 0.5]; U[3] = [0.5, 0.1]     # vx = 0: sign(0) = 0 branch
+    F = np.zeros((3, n, 6))
+    for i in range(n):
+        F[0, i] = m.f_cont(X[i], U[i], m.Params)
+        F[1, i] = g1.f_cont(X[i], U[i], g1.Params)
+        F[2, i] = g2.f_cont(X[i], U[i], g2.Params)
+    # linearisation away from the kinks (|vx| = 0.3, |alpha| = 0.6) so analytic and FD Jacobians agree
+    nl = 48
+    XL = np.stack([rng.uniform(-2, 2, nl), rng.uniform(-2, 2, nl), rng.uniform(-np.pi, np.pi, nl), rng.uniform(0.4, 2.5, nl),
+                   rng.uniform(-0.08, 0.08, nl), rng.uniform(-1.5, 1.5, nl)], axis=1)
+    UL = np.stack([rng.uniform(-1, 1, nl), rng.uniform(-0.25, 0.25, nl)], axis=1)
+    XL[0], UL[0] = X[0], U[0]
+    XL[1], UL[1] = X[2], U[2]
+    TsL = np.where(np.arange(nl) % 2 == 0, 0.02, 0.01)
+    AL = np.zeros((nl, 6, 6)); BL = np.zeros((nl, 6, 2)); GL = np.zeros((nl, 6))
+    for i in range(nl):
+        AL[i], BL[i], GL[i] = m.linearize_discretize(XL[i], UL[i], float(TsL[i]), m.Params)
+    # horizon linearisation exactly as mpc_step does it (:165-178) for 4 start states
+    N = 20
+    AH = np.zeros((4, N, 6, 6)); BH = np.zeros((4, N, 6, 2)); GH = np.zeros((4, N, 6)); XB = np.zeros((4, N + 1, 6))
+    for i in range(4):
+        xbar = np.zeros((6, N + 1)); xbar[:, 0] = XL[i]
+        for k in range(N):
+            xbar[:, k + 1] = xbar[:, k] + 0.02 * m.f_cont(xbar[:, k], UL[i], m.Params)
+            AH[i, k], BH[i, k], GH[i, k] = m.linearize_discretize(xbar[:, k], UL[i], 0.02, m.Params)
+        XB[i] = xbar.T
+    # MPC/main.py function definitions (the module body runs the CVXPY loop, so only the head is executed)
+    src = open(os.path.join(refload.REFERENCE_ROOT, "MPC", "main.py")).read().split("# --- MPC SIMULATION SETUP ---")[0]
+    refload._stub_matplotlib()
+    ns = {}
+    old = sys.stdout; sys.stdout = io.StringIO()
+    try:
+        exec(compile(src, "main_head", "exec"), ns)
+    finally:
+        sys.stdout = old
+    vr40 = ns["vref_profile_ramp_cruise"](40, 0.02, v0=0.8, v_cruise=2.0, tramp=2.0)
+    vtr = ns["vref_profile_trapezoid"](40, 0.1, v0=0.8, vmax=2.0, t_acc=1.0, t_flat=1.5, t_dec=1.0)
+    vsn = ns["vref_profile_sine"](40, 0.1)
+    win = ns["ref_window_from_x_with_vref"](0.37, 40, 0.02, vr40)
+    dss = np.array([ns["d_steady_state"](v) for v in (0.5, 1.0, 2.0)])
+    # generator plants (clipping) on aggressive controls so that the clips engage
+    T = 300
+    Usim = np.stack([np.clip(0.3 + 0.7 * np.sin(np.arange(T) * 0.05), -1, 1), 0.5 * np.sin(np.arange(T) * 0.11)], axis=1)
+    x0p = np.array([0.0, 0.0, 0.3, 0.45, 0.0, 0.2])
+    Xg1 = g1.simulate_trajectory(x0p, Usim, 0.01, g1.Params)
+    Xg2 = np.empty((T + 1, 6)); Xg2[0] = x0p
+    for k in range(T):     # generation_type2.py:180-187
+        Xg2[k + 1] = Xg2[k] + 0.01 * g2.f_cont(Xg2[k], Usim[k], g2.Params)
+        Xg2[k + 1, 3] = max(Xg2[k + 1, 3], 0.0)
+        Xg2[k + 1, 5] = float(np.clip(Xg2[k + 1, 5], -6, 6))
+    Xm = np.empty((T + 1, 6)); Xm[0] = x0p
+    for k in range(T):     # MPC/main.py:97
+        Xm[k + 1] = Xm[k] + 0.01 * m.f_cont(Xm[k], Usim[k], m.Params)
+    np.savez_compressed(os.path.join(HERE, "reference_physics.npz"), X=X, U=U, F=F, XL=XL, UL=UL, TsL=TsL, AL=AL, BL=BL,
+                        GL=GL, AH=AH, BH=BH, GH=GH, XB=XB, vr40=vr40, vtr=vtr, vsn=vsn, win=win, dss=dss,
+                        Usim=Usim, x0p=x0p, Xg1=Xg1, Xg2=Xg2, Xm=Xm)
+    # gen2 dataset: 3 trajectories x 0.5 s, the reference's own DataFrame -> CSV text
+    old = sys.stdout; sys.stdout = io.StringIO()
+    try:
+        df = g2.generate_dataset(num_traj=3, T=0.5, Ts=0.01, seed=42)
+    finally:
+        sys.stdout = old
+    clean = df[df["noise_type"] == "clean"].drop(columns=["noise_type", "mode"])       # generation_type2.py:309-317
+    noisy = df[df["noise_type"] == "noisy"].drop(columns=["noise_type", "mode", "phi"])
+    clean.to_csv(os.path.join(HERE, "reference_gen2_clean.csv"), index=False)
+    noisy.to_csv(os.path.join(HERE, "reference_gen2_noisy.csv"), index=False)
+    print("reference fixtures written")
+
+
+def oracle_qp_fixtures():
+    rng = np.random.default_rng(7)
+    cases = []
+    hard = dict(du_bounds=((-0.1, 0.1), (-0.04, 0.04)), x_lo=[-1e20] * 4 + [-0.15, -2.0], x_hi=[1e20] * 4 + [0.15, 2.0])
+    for N, Ts, is_hard, cnt in ((20, 0.02, False, 6), (20, 0.02, True, 6), (10, 0.02, True, 3), (40, 0.02, False, 2),
+                                (50, 0.02, True, 2), (20, 0.01, False, 3)):
+        for _ in range(cnt):
+            vx = rng.uniform(0.5, 1.5)
+            x = np.array([rng.uniform(-1, 1), 0.0, rng.uniform(-0.3, 0.3), vx, rng.uniform(-0.05, 0.05), rng.uniform(-1, 1)])
+            prm = (rng.uniform(0.2, 1.0), rng.uniform(0.3, 1.0), rng.uniform(0, 2 * np.pi), 0.0)
+            y0, _ = R.path_eval(R.PATH_SINE, prm, x[0:1])
+            x[1] = y0[0] + (rng.uniform(-1.5, 1.5) if is_hard else rng.uniform(-0.2, 0.2))
+            up = np.array([R.d_steady_state(vx), rng.uniform(-0.1, 0.1)])
+            v = R.vref_profile(R.VREF_RAMP, (0.8, rng.uniform(0.8, 2.0), 2.0), N, Ts)
+            pr = R.ref_window(x[0], N, Ts, v, R.PATH_SINE, prm)
+            kw = hard if is_hard else {}
+            u_cmd, status, info = ompc.mpc_step(x, up, pr, Ts=Ts, N=N, vref=v, solver="ipm", **kw)
+            if status != "optimal":
+                continue
+            cases.append(dict(N=N, Ts=Ts, hard=is_hard, x0=x, u_prev=up, path_ref=pr, vref=v, u_cmd=u_cmd,
+                              U_opt=info["U_opt"], X_opt=info["X_opt"], objective=info["objective"], y=info["y_ineq"]))
+    out = {"n": len(cases)}
+    for i, c in enumerate(cases):
+        for k, v in c.items():
+            out[f"{k}_{i}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, "oracle_qp.npz"), **out)
+    print("oracle QP fixtures:", len(cases))
+
+
+def oracle_closed_loop_fixtures():
+    # BASELINE config 1: MPC/main.py verbatim (N=40, Ts=0.02, x0=[0,.5,0,1,0,0], parabola, ramp vref), 600 steps
+    x0 = np.array([0.0, 0.5, 0.0, 1.0, 0.0, 0.0]); u0 = np.array([R.d_steady_state(1.0), 0.0])
+    X40, U40, st40, _ = ompc.closed_loop(x0, u0, 600, 0.02, 40)
+    assert all(s == "optimal" for s in st40)
+    X20, U20, st20, _ = ompc.closed_loop(x0, u0, 300, 0.02, 20, path_kind=R.PATH_SINE, path_prm=(0.5, 0.5, 0.0, 0.0))
+    assert all(s == "optimal" for s in st20)
+    # generator-style: Ts=0.01, gen2 plant with clipping, hard rate bounds
+    x1 = np.array([0.0, 0.8, 0.1, 0.6, 0.0, 0.0]); u1 = np.array([R.d_steady_state(0.6), 0.0])
+    Xg, Ug, stg, _ = ompc.closed_loop(x1, u1, 200, 0.01, 20, plant=dyn.PLANT_GEN2,
+                                      du_bounds=((-0.1, 0.1), (-0.04, 0.04)))
+    np.savez_compressed(os.path.join(HERE, "oracle_closed_loop.npz"), x0=x0, u0=u0, X40=X40, U40=U40, X20=X20, U20=U20,
+                        x1=x1, u1=u1, Xg=Xg, Ug=Ug, stg=np.array([s == "optimal" for s in stg]))
+    d, de = U40[:, 0], U40[:, 1]
+    print("config-1 control statistics (cf. generation_type1.py:250: d 0.2161/0.1314, delta 0.0035/0.0338):",
+          d.mean(), d.std(), de.mean(), de.std())
+
+
+if __name__ == "__main__":
+    if not refload.available():
+        raise SystemExit("the reference tree is not mounted; fixtures can only be regenerated in the build container")
+    reference_fixtures()
+    oracle_qp_fixtures()
+    oracle_closed_loop_fixtures()

@@ -1,0 +1,320 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star): linearisation A/B/g within 1e-6 (fp64); per-step QP inputs within
+1e-3 of the converged optimum with identical active sets (margin 1e-4); closed-loop trajectories within
+1e-3 over the horizon of the run (state units: m, rad, m/s, rad/s); Philox stream and the Gaussian
+noise bit-exact."""
+import numpy as np
+import pytest
+
+import trajectory_generation_b200 as tg
+from oracle import dynamics as dyn, mpc as ompc, philox as oph, qp as oqp, refgen as R
+from conftest import HARD
+
+pytestmark = pytest.mark.gpu
+
+TOL_LIN = 1e-6
+TOL_U = 1e-3
+TOL_LOOP = 1e-3
+TIGHT = {"eps_abs": 1e-6, "eps_rel": 1e-6}
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("jac", [tg.JAC_ANALYTIC, tg.JAC_FD])
+def test_linearize_horizon_vs_reference_golden(golden_physics, jac):
+    g = golden_physics
+    ctl = tg.BatchedMPC(N=20, Ts=0.02, jacobian=jac)
+    A, B, c, xbar = ctl.linearize(g["XL"][:4], g["UL"][:4])
+    tol = TOL_LIN if jac == tg.JAC_ANALYTIC else 1e-9
+    np.testing.assert_allclose(A, g["AH"], atol=tol)
+    np.testing.assert_allclose(B, g["BH"], atol=tol)
+    np.testing.assert_allclose(c, g["GH"], atol=tol)
+    np.testing.assert_allclose(xbar, g["XB"], atol=1e-12)
+
+
+def test_linearize_single_stage_points_vs_reference_golden(golden_physics):
+    """stage 0 of the horizon is linearize_discretize(x0, u_prev): all 48 golden points, both Ts."""
+    g = golden_physics
+    for Ts in (0.02, 0.01):
+        sel = np.where(g["TsL"] == Ts)[0]
+        ctl = tg.BatchedMPC(N=10, Ts=Ts)
+        A, B, c, _ = ctl.linearize(g["XL"][sel], g["UL"][sel])
+        np.testing.assert_allclose(A[:, 0], g["AL"][sel], atol=TOL_LIN)
+        np.testing.assert_allclose(B[:, 0], g["BL"][sel], atol=TOL_LIN)
+        np.testing.assert_allclose(c[:, 0], g["GL"][sel], atol=TOL_LIN)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_linearize_variants_vs_oracle(variant):
+    rng = np.random.default_rng(variant)
+    B = 64
+    x0 = np.stack([rng.uniform(-2, 2, B), rng.uniform(-2, 2, B), rng.uniform(-np.pi, np.pi, B), rng.uniform(0.4, 1.5, B),
+                   rng.uniform(-0.05, 0.05, B), rng.uniform(-1, 1, B)], 1)
+    up = np.stack([rng.uniform(0, 0.5, B), rng.uniform(-0.1, 0.1, B)], 1)
+    ctl = tg.BatchedMPC(N=12, Ts=0.01, model=variant, jacobian=tg.JAC_FD)
+    A, Bm, g, xb = ctl.linearize(x0, up)
+    for i in range(0, B, 7):
+        Ao, Bo, go, xbo = dyn.linearize_horizon(x0[i], up[i], 0.01, 12, variant=variant)
+        assert max(np.abs(A[i] - Ao).max(), np.abs(Bm[i] - Bo).max(), np.abs(g[i] - go).max()) < 1e-9
+
+
+def test_empty_batch_is_a_no_op():
+    ctl = tg.BatchedMPC(N=20)
+    A, B, g, xb = ctl.linearize(np.zeros((0, 6)), np.zeros((0, 2)))
+    assert A.shape == (0, 20, 6, 6)
+    out = ctl.step(np.zeros((0, 6)), np.zeros((0, 2)), np.zeros((0, 21, 3)))
+    assert out["u_cmd"].shape == (0, 2)
+
+
+# ------------------------------------------------------------------ K2
+def _sparse_objective(c, kw, U):
+    """objective of the reference's sparse QP at the dynamics-consistent point implied by U."""
+    N, Ts = int(c["N"]), float(c["Ts"])
+    A, B, g, _ = dyn.linearize_horizon(c["x0"], c["u_prev"], Ts, N)
+    prob = oqp.build_sparse_qp(c["x0"], c["u_prev"], A, B, g, c["path_ref"], c["vref"], **kw)
+    X = np.zeros((N + 1, 6)); X[0] = c["x0"]
+    for k in range(N):
+        X[k + 1] = A[k] @ X[k] + B[k] @ U[k] + g[k]
+    z = np.concatenate([X.reshape(-1), U.reshape(-1)])
+    return prob.objective(z), prob, z
+
+
+def test_condensed_qp_equals_sparse_statement(golden_qp):
+    """1/2 dU'H dU + q'dU + c0 equals the sparse objective for arbitrary U; constraint rows agree."""
+    rng = np.random.default_rng(0)
+    for c in golden_qp[::3]:
+        kw = HARD if bool(c["hard"]) else {}
+        N, Ts = int(c["N"]), float(c["Ts"])
+        ctl = tg.BatchedMPC(N=N, Ts=Ts, jacobian=tg.JAC_FD, **kw)
+        asm = ctl.assemble(c["x0"][None], c["u_prev"][None], c["path_ref"][None], c["vref"][None])
+        H, q, c0 = asm["H"][0], asm["q"][0], asm["c0"][0]
+        assert np.abs(H - H.T).max() < 1e-9 * np.abs(H).max() and np.linalg.eigvalsh(H).min() > 0
+        for _ in range(3):
+            U = c["u_prev"][None, :] + rng.normal(0, 0.1, (N, 2))
+            dU = (U - c["u_prev"][None, :]).reshape(-1)
+            obj, prob, z = _sparse_objective(c, kw, U)
+            assert abs(0.5 * dU @ H @ dU + q @ dU + c0 - obj) < 1e-8 * (1 + abs(obj))
+            # inequality rows: [I; D; Gs] dU within [l,u]  <=>  sparse rows within their bounds
+            n = 2 * N
+            Ac = np.vstack([np.eye(n), np.eye(n) - np.eye(n, k=-2), asm["Gs"][0]])
+            lhs = Ac @ dU
+            sp = (prob.A @ z)[prob.n_eq:]
+            m_in = 4 * N
+            # sparse ordering per stage: u box (2), rate (2); condensed: all boxes then all rates
+            box = np.stack([sp[4 * k:4 * k + 2] for k in range(N)]).reshape(-1)
+            rate = np.stack([sp[4 * k + 2:4 * k + 4] for k in range(N)]).reshape(-1)
+            np.testing.assert_allclose(lhs[:n] + np.tile(c["u_prev"], N), box, atol=1e-12)
+            r0 = rate.copy(); r0[:2] -= c["u_prev"]
+            np.testing.assert_allclose(lhs[n:2 * n], r0, atol=1e-12)
+            if asm["Gs"].shape[1]:
+                ns = asm["Gs"].shape[1] // N
+                st = sp[m_in + ns:]                      # sparse has k = 0 rows first
+                xbar = dyn.nominal_rollout(c["x0"], c["u_prev"], Ts, N)[0].T
+                sidx = [4, 5]
+                xb = np.stack([xbar[k + 1, sidx] for k in range(N)]).reshape(-1)
+                np.testing.assert_allclose(lhs[2 * n:] + xb, st, atol=1e-9)
+
+
+# ------------------------------------------------------------------ K3
+def _active(v, lo, hi, margin=1e-4):
+    return (v <= lo + margin).astype(int) - (v >= hi - margin).astype(int)
+
+
+def test_mpc_step_vs_golden_optima(golden_qp):
+    """u_cmd / U_opt within 1e-3 of the converged optimum, identical active sets, objective to 1e-5 rel."""
+    worst = 0.0
+    for c in golden_qp:
+        kw = HARD if bool(c["hard"]) else {}
+        N, Ts = int(c["N"]), float(c["Ts"])
+        u_cmd, status, info = tg.mpc_step(c["x0"], c["u_prev"], c["path_ref"], Ts=Ts, N=N, vref=c["vref"], solver_opts=TIGHT, **kw)
+        assert status == "optimal"
+        err = np.abs(info["U_opt"] - c["U_opt"]).max()
+        worst = max(worst, err)
+        assert err < TOL_U and np.abs(u_cmd - c["u_cmd"]).max() < TOL_U
+        assert np.abs(info["X_opt"] - c["X_opt"]).max() < 5e-3
+        assert abs(info["objective"] - c["objective"]) < 1e-5 * (1 + abs(c["objective"]))
+        ub, dub = kw.get("u_bounds", ((-1, 1), (-0.6, 0.6))), kw.get("du_bounds", ((-0.5, 0.5), (-0.3, 0.3)))
+        for j in range(2):
+            assert np.array_equal(_active(info["U_opt"][j], *ub[j]), _active(c["U_opt"][j], *ub[j]))
+            du_g = np.diff(np.concatenate([[c["u_prev"][j]], info["U_opt"][j]]))
+            du_o = np.diff(np.concatenate([[c["u_prev"][j]], c["U_opt"][j]]))
+            assert np.array_equal(_active(du_g, *dub[j]), _active(du_o, *dub[j]))
+    print("worst |U - U*| over golden QPs:", worst)
+
+
+def test_mpc_step_default_eps_matches_reference_settings(golden_qp):
+    """at the reference's eps (CVXPY passes eps_abs = eps_rel = 1e-5 to OSQP) the answer is still within 1e-3."""
+    for c in golden_qp[:9]:
+        kw = HARD if bool(c["hard"]) else {}
+        u_cmd, status, info = tg.mpc_step(c["x0"], c["u_prev"], c["path_ref"], Ts=float(c["Ts"]), N=int(c["N"]), vref=c["vref"], **kw)
+        assert status == "optimal" and np.abs(u_cmd - c["u_cmd"]).max() < TOL_U
+
+
+def test_batched_step_equals_single_calls(golden_qp):
+    cs = [c for c in golden_qp if int(c["N"]) == 20 and not bool(c["hard"]) and float(c["Ts"]) == 0.02]
+    ctl = tg.BatchedMPC(N=20, Ts=0.02, solver_opts=TIGHT)
+    out = ctl.step(np.stack([c["x0"] for c in cs]), np.stack([c["u_prev"] for c in cs]),
+                   np.stack([c["path_ref"] for c in cs]), np.stack([c["vref"] for c in cs]))
+    for i, c in enumerate(cs):
+        assert out["status"][i] == 0 and np.abs(out["U_opt"][i].T - c["U_opt"]).max() < TOL_U
+        one = ctl.step(c["x0"][None], c["u_prev"][None], c["path_ref"][None], c["vref"][None])
+        assert np.array_equal(one["U_opt"][0], out["U_opt"][i])        # batch composition does not change a result
+
+
+def test_shim_signature_fallback_and_status_strings(golden_qp):
+    """the reference's conventions (MPC/mpc_6stati.py:148-163, 255-275)."""
+    c = golden_qp[0]
+    x, up, pr, v = c["x0"], c["u_prev"], c["path_ref"], c["vref"]
+    u, st, info = tg.mpc_step(x, up, pr, vref=v)
+    assert st == "optimal" and u.shape == (2,)
+    assert set(info) >= {"status", "objective", "X_opt", "U_opt", "path_ref", "vref"}
+    assert info["X_opt"].shape == (6, 21) and info["U_opt"].shape == (2, 20) and np.array_equal(info["X_opt"][:, 0], x)
+    u2, st2, info2 = tg.mpc_step(list(x), tuple(up), pr.tolist(), vref=None)       # coercion + vref=None -> x0[3]
+    assert st2 == "optimal" and np.array_equal(info2["vref"], np.full(21, x[3]))
+    u3, st3, _ = tg.mpc_step(x, up, pr, vref=1.3)                                  # scalar vref
+    o3 = ompc.mpc_step(x, up, pr, vref=1.3)
+    assert np.abs(u3 - o3[0]).max() < TOL_U
+    ub, stb, infob = tg.mpc_step(x, [2.0, 0.0], pr, vref=v)                        # rate + box cannot both hold
+    assert stb == "infeasible" and infob == {} and np.array_equal(ub, [2.0, 0.0])
+    ux, stx, infox = tg.mpc_step(x, up, pr, vref=v, x_lo=[-1e20, -1e20, -1e20, 2.0, -1e20, -1e20])   # x0 violates the k=0 row
+    assert stx == "infeasible" and infox == {}
+    ul, stl, infol = tg.mpc_step(x, up, pr, vref=v, solver_opts={"max_iter": 3, "check_every": 3, "eps_abs": 1e-12, "eps_rel": 1e-12})
+    assert stl == "user_limit" and infol == {} and np.array_equal(ul, up)
+    un, stn, infon = tg.mpc_step(np.array([0, 0, 0, np.nan, 0, 0]), up, pr, vref=v)
+    assert stn.startswith("Solver Error") and infon == {}
+    with pytest.raises(AssertionError):
+        tg.mpc_step(x, up, pr[:-1], vref=v)                                        # :151
+
+
+def test_solution_is_kkt_point_at_full_batch_size():
+    """size-independent property at BASELINE config-2 size (B = 1024): feasibility and stationarity of
+    every returned solution, computed from the assembled condensed QP."""
+    rng = np.random.default_rng(3)
+    B, N, Ts = 1024, 20, 0.02
+    x0 = np.stack([rng.uniform(-1, 1, B), rng.uniform(-0.6, 0.6, B), rng.uniform(-0.3, 0.3, B), rng.uniform(0.5, 1.5, B),
+                   rng.uniform(-0.05, 0.05, B), rng.uniform(-1, 1, B)], 1)
+    up = np.stack([tg.d_steady_state(x0[:, 3]), rng.uniform(-0.1, 0.1, B)], 1)
+    gen = tg.ClosedLoopGenerator(N=N, Ts=Ts, du_bounds=((-0.1, 0.1), (-0.04, 0.04)), solver_opts=TIGHT)
+    sc = tg.Scenarios(B)
+    sc.set_sine(slice(0, B, 2), A=rng.uniform(0.2, 1.0, B // 2), k=rng.uniform(0.3, 1.0, B // 2), psi=rng.uniform(0, 6.28, B // 2))
+    pr, vr = gen.ref_window(x0, sc)
+    out = gen.step(x0, up, pr, vr)
+    asm = gen.assemble(x0, up, pr, vr)
+    ok = out["status"] == 0
+    assert ok.mean() > 0.99
+    n = 2 * N
+    D = np.eye(n) - np.eye(n, k=-2)
+    dU = (out["U_opt"] - up[:, None, :]).reshape(B, n)
+    y = out["y_opt"]
+    act = 0
+    for i in np.where(ok)[0]:
+        lhs = np.concatenate([dU[i], D @ dU[i]])
+        assert (lhs >= asm["l"][i] - 1e-4).all() and (lhs <= asm["u"][i] + 1e-4).all()
+        r = asm["H"][i] @ dU[i] + asm["q"][i] + y[i, :n] + D.T @ y[i, n:]
+        assert np.abs(r).max() < 1e-4 * max(1.0, np.abs(asm["q"][i]).max())
+        act += int((np.abs(y[i]) > 1e-6).sum())
+    assert act > 0     # the tight rate bounds are really active somewhere
+
+
+# ------------------------------------------------------------------ K4
+def test_plant_rollout_vs_reference_golden(golden_physics):
+    g = golden_physics
+    for plant, key in ((tg.PLANT_MPC, "Xm"), (tg.PLANT_GEN1, "Xg1"), (tg.PLANT_GEN2, "Xg2")):
+        gen = tg.ClosedLoopGenerator(N=10, Ts=0.01, plant=plant)
+        X = gen.plant_rollout(g["x0p"][None], g["Usim"][None])
+        np.testing.assert_allclose(X[0], g[key], rtol=1e-9, atol=1e-9)
+
+
+def test_philox_stream_and_noise_bit_exact():
+    gen = tg.ClosedLoopGenerator(N=10)
+    for seed, first, block in ((12345, 0, 0), (12345 + 77, 1000, 1), ((9 << 32) | 5, 4294967290, 0)):
+        assert np.array_equal(gen.philox_u32(seed, first, block, 64), oph.philox_stream(seed, first, block, 64))
+    assert [f"{v:08x}" for v in tg.ClosedLoopGenerator(N=10).philox_u32(0, 0, 0, 1)[0]] == ["6627e8d5", "e169c58d", "bc57ac4c", "9b00dbd8"]
+    nz = gen.sensor_noise_normals(5, 4, 1201)
+    ref = np.stack([oph.standard_normals(12345 + 5 + i, 1201) for i in range(4)])
+    assert np.array_equal(nz, ref)                                    # Gaussians too, not only the integers
+
+
+def test_reference_window_tap_vs_golden(golden_physics):
+    g = golden_physics
+    gen = tg.ClosedLoopGenerator(N=40, Ts=0.02)
+    x0 = np.zeros((1, 6)); x0[0, 0] = 0.37
+    pr, vr = gen.ref_window(x0, tg.Scenarios(1))
+    np.testing.assert_allclose(vr[0], g["vr40"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(pr[0], g["win"], rtol=0, atol=1e-14)
+    # spline + trapezoid + sine vref against the oracle
+    sc = tg.Scenarios(2)
+    kx, ky = np.array([-1.0, 0.5, 2.0, 3.5, 5.0]), np.array([0.0, 0.4, -0.3, 0.2, 0.0])
+    sc.set_spline(0, kx, ky); sc.set_vref(0, tg.VREF_TRAPEZOID, 0.8, 2.0, 0.2, 0.3, 0.2)
+    sc.set_sine(1, 0.5, 0.5, 0.3, 0.1); sc.set_vref(1, tg.VREF_SINE, 1.5, 0.5, 6.0)
+    x0 = np.zeros((2, 6)); x0[:, 0] = (0.1, -0.4)
+    pr, vr = gen.ref_window(x0, sc)
+    v0 = R.vref_profile(R.VREF_TRAPEZOID, (0.8, 2.0, 0.2, 0.3, 0.2), 40, 0.02)
+    w0 = R.ref_window(0.1, 40, 0.02, v0, R.PATH_SPLINE, None, R.natural_spline_ppoly(kx, ky))
+    v1 = R.vref_profile(R.VREF_SINE, (1.5, 0.5, 6.0), 40, 0.02)
+    w1 = R.ref_window(-0.4, 40, 0.02, v1, R.PATH_SINE, (0.5, 0.5, 0.3, 0.1))
+    np.testing.assert_allclose(vr, [v0, v1], atol=1e-14)
+    np.testing.assert_allclose(pr, [w0, w1], atol=1e-12)
+
+
+# ------------------------------------------------------------------ fused closed loop
+def test_closed_loop_config1_vs_golden(golden_loop):
+    """BASELINE config 1: MPC/main.py verbatim (N=40, Ts=0.02, 600 steps, parabola, ramp vref)."""
+    g = golden_loop
+    gen = tg.ClosedLoopGenerator(N=40, Ts=0.02, solver_opts=TIGHT)
+    res = gen.generate(g["x0"][None], g["u0"][None], tg.Scenarios(1), 600)
+    assert res["status_counts"][0, 0] == 600
+    assert np.abs(res["clean"][0] - g["X40"]).max() < TOL_LOOP
+    assert np.abs(res["U"][0] - g["U40"]).max() < TOL_LOOP
+    d = res["U"][0, :, 0]
+    assert abs(d.mean() - 0.2161) < 5e-3            # generation_type1.py:250 (soft anchor)
+
+
+def test_closed_loop_sine_and_generator_plant_vs_golden(golden_loop):
+    g = golden_loop
+    gen = tg.ClosedLoopGenerator(N=20, Ts=0.02, solver_opts=TIGHT)
+    sc = tg.Scenarios(1); sc.set_sine(0, 0.5, 0.5, 0.0, 0.0)
+    res = gen.generate(g["x0"][None], g["u0"][None], sc, 300)
+    assert np.abs(res["clean"][0] - g["X20"]).max() < TOL_LOOP and np.abs(res["U"][0] - g["U20"]).max() < TOL_LOOP
+    gen2 = tg.ClosedLoopGenerator(N=20, Ts=0.01, plant=tg.PLANT_GEN2, du_bounds=((-0.1, 0.1), (-0.04, 0.04)), solver_opts=TIGHT)
+    res2 = gen2.generate(g["x1"][None], g["u1"][None], tg.Scenarios(1), 200)
+    assert np.abs(res2["clean"][0] - g["Xg"]).max() < TOL_LOOP and np.abs(res2["U"][0] - g["Ug"]).max() < TOL_LOOP
+
+
+def test_closed_loop_noise_contract_and_shard_invariance():
+    """noise = sigma_c * n(seed_base + global id, row, c) on all T+1 rows, never fed back; a trajectory is
+    bit-identical whether it runs in a batch of 64 from id 0 or in a shard starting at its own id."""
+    rng = np.random.default_rng(1)
+    B, T = 64, 40
+    x0 = np.tile([0, 0.5, 0, 1.0, 0, 0], (B, 1)).astype(float); x0[:, 1] += rng.uniform(-0.3, 0.3, B)
+    u0 = np.tile([tg.d_steady_state(1.0), 0.0], (B, 1))
+    sc = tg.Scenarios(B); sc.set_sine(slice(0, B, 3), 0.5, 0.5, 0.0, 0.0)
+    gen = tg.ClosedLoopGenerator(N=20, Ts=0.02)
+    full = gen.generate(x0, u0, sc, T)
+    for i in (0, 17, 63):
+        nz = (full["noisy"][i] - full["clean"][i])
+        ref = oph.sensor_noise(i, T + 1)
+        np.testing.assert_allclose(nz, ref, atol=1e-15)
+    part = gen.generate(x0[32:], u0[32:], sc.slice(32, 64), T, traj_id0=32)
+    for k in ("clean", "noisy", "U"):
+        assert np.array_equal(part[k], full[k][32:])
+    # warm start changes iteration counts, not results beyond the solver tolerance
+    cold = tg.ClosedLoopGenerator(N=20, Ts=0.02, warm_start=False).generate(x0[:8], u0[:8], sc.slice(0, 8), T)
+    assert np.abs(cold["clean"] - full["clean"][:8]).max() < TOL_LOOP
+    assert cold["iters_total"].sum() >= full["iters_total"][:8].sum()
+
+
+def test_generated_csv_loads_through_the_reference_schema(tmp_path):
+    import pandas as pd
+    gen = tg.ClosedLoopGenerator(N=20, Ts=0.01, plant=tg.PLANT_GEN2)
+    B, T = 6, 120
+    x0 = tg.sample_x0(B, 42); x0[:, 2] = 0.0; x0[:, 1] = 0.1 * x0[:, 0] ** 2; x0[:, 3] += 0.3
+    u0 = np.stack([tg.d_steady_state(x0[:, 3]), np.zeros(B)], 1)
+    res = gen.generate(x0, u0, tg.Scenarios(B), T)
+    tg.write_csv(res, 0.01, tmp_path / "c.csv", tmp_path / "n.csv")
+    c, n = pd.read_csv(tmp_path / "c.csv"), pd.read_csv(tmp_path / "n.csv")
+    assert list(c.columns) == tg.CLEAN_COLS and list(n.columns) == tg.NOISY_COLS
+    assert len(c) == B * (T + 1) and sorted(c["trajectory_id"].unique()) == list(range(B))
+    assert c["d"].isna().sum() == B and not c[["X", "Y", "phi", "vx", "vy", "omega"]].isna().any().any()
+    y, u, x = tg.to_loader_tensors(res, T)
+    assert y.shape == (B, 5, T) and not np.isnan(u).any()

@@ -1,0 +1,82 @@
+"""CPU: host-side logic of the package -- scenario tables, dataset schema / CSV text, loader hand-off,
+sharding.  No compute calls."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import trajectory_generation_b200 as tg
+from trajectory_generation_b200 import distributed as tgd
+from conftest import GOLDEN
+
+
+def _reference_rows():
+    c = pd.read_csv(os.path.join(GOLDEN, "reference_gen2_clean.csv"), float_precision="round_trip")
+    n = pd.read_csv(os.path.join(GOLDEN, "reference_gen2_noisy.csv"), float_precision="round_trip")
+    B = c["trajectory_id"].nunique()
+    T1 = len(c) // B
+    clean = c[["X", "Y", "phi", "vx", "vy", "omega"]].values.reshape(B, T1, 6)
+    noisy = np.zeros_like(clean)
+    noisy[:, :, [0, 1, 3, 4, 5]] = n[["X", "Y", "vx", "vy", "omega"]].values.reshape(B, T1, 5)
+    U = c[["d", "delta"]].values.reshape(B, T1, 2)[:, :-1]
+    return {"clean": clean, "noisy": noisy, "U": U}
+
+
+def test_csv_writer_is_byte_identical_to_the_reference(tmp_path):
+    """feeding the reference's own rows through the package's writer reproduces the reference's files."""
+    res = _reference_rows()
+    tg.write_csv(res, 0.01, tmp_path / "c.csv", tmp_path / "n.csv")
+    assert open(tmp_path / "c.csv").read() == open(os.path.join(GOLDEN, "reference_gen2_clean.csv")).read()
+    assert open(tmp_path / "n.csv").read() == open(os.path.join(GOLDEN, "reference_gen2_noisy.csv")).read()
+    c, n = tg.to_frames(res, 0.01)
+    assert list(c.columns) == tg.CLEAN_COLS and list(n.columns) == tg.NOISY_COLS
+    last = c[c["trajectory_id"] == 2].iloc[-1]
+    assert np.isnan(last["d"]) and np.isnan(last["delta"])          # generation_type2.py:211-212
+
+
+def test_loader_tensors_match_reference_loader(tmp_path):
+    res = _reference_rows()
+    tg.write_csv(res, 0.01, tmp_path / "c.csv", tmp_path / "n.csv")
+    y, u, x = tg.to_loader_tensors(res, 50)
+    assert y.shape == (3, 5, 50) and u.shape == (3, 2, 50) and x.shape == (3, 6, 50) and y.dtype == np.float32
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference tree not mounted")
+    dl = refload.load_data_loader()
+    tr, va, te = dl.load_vehicle_dataset(str(tmp_path / "n.csv"), str(tmp_path / "c.csv"), T_steps=50)
+    allx = np.concatenate([tr[2].numpy(), va[2].numpy(), te[2].numpy()])
+    ally = np.concatenate([tr[0].numpy(), va[0].numpy(), te[0].numpy()])
+    perm = np.arange(3); np.random.default_rng(42).shuffle(perm)      # KalmanNet/data_loader.py:60-62
+    np.testing.assert_array_equal(allx, x[perm])
+    np.testing.assert_array_equal(ally, y[perm])
+    assert not np.isnan(allx).any()
+
+
+def test_sample_x0_is_the_reference_draw():
+    x0 = tg.sample_x0(3, 42)
+    np.testing.assert_allclose(x0[0], [1.0958241942238534, -0.24448624099179073, 2.2531371815723604,
+                                       0.47894721162374554, -0.04058226521123505, 0.9512447032735118], rtol=0, atol=0)
+
+
+def test_scenarios_table():
+    sc = tg.Scenarios(5)
+    assert (sc.spec["path_kind"] == tg.PATH_PARABOLA).all() and sc.spec["path"][0, 0] == 0.1
+    sc.set_sine(slice(1, 3), A=np.array([0.3, 0.4]), k=0.5, psi=0.1)
+    sc.set_spline(3, [0, 1, 2, 3], [0, 0.5, -0.2, 0.1])
+    sc.set_spline(4, [0, 2, 4], [0, 1.0, 0.0])
+    sc.set_vref(slice(0, 5), tg.VREF_CONST, 1.2)
+    brk, coef = sc.tables()
+    assert list(sc.spec["path"][2]) == [0.4, 0.5, 0.1, 0.0]
+    assert len(brk) == 5 and coef.shape == (5, 4) and sc.spec["spline_first"][4] == 3 and sc.spec["spline_count"][4] == 2
+    sub = sc.slice(3, 5)
+    assert len(sub) == 2 and sub.spec["spline_first"][1] == 3 and np.array_equal(sub.tables()[0], brk)
+    assert tg.d_steady_state(1.0) == pytest.approx(0.2243010752688172)
+
+
+def test_shard_ranges_partition_the_ids():
+    for B, W in ((10, 1), (10, 3), (1048576, 8), (5, 8), (0, 2)):
+        r = [tgd.shard_range(B, k, W) for k in range(W)]
+        assert r[0][0] == 0 and r[-1][1] == B
+        assert all(r[k][1] == r[k + 1][0] for k in range(W - 1))
+        assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
