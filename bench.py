@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- closed-loop MPC steps/s on B200 (BASELINE.json metric), roofline and CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--horizon-steps T]
+
+One "step" = one pass of the hot path over one batch: BASELINE config 2 -- B = 1024 trajectories per GPU,
+spline / sinusoidal references, N = 20, Ts = 0.01, T = 1200 closed-loop MPC steps each (1.23 M MPC steps),
+run by ONE launch of the fused closed-loop kernel.  `value` is timed with CUDA events on the kernel's
+stream with inputs resident in HBM; `e2e` goes through the public host-buffer API (pinned host memory,
+H2D + D2H inside the timed region).  For N > 1 the driver launches this file under torchrun: each rank
+owns its own block of trajectory ids (weak scaling, no collective on the solve path), time = max over
+ranks.  `--impl reference` times the reference's algorithm on the host cores (oracle/ port of
+MPC/main.py's loop with the restated OSQP; cvxpy/osqp are not installable offline).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_HORIZON, TS = 20, 0.01
+METRIC = "closed-loop MPC steps/sec (batched QP solves/sec)"
+
+
+def make_workload(B, traj_id0=0, seed=2025):
+    """BASELINE config 2: per trajectory id i (seed 2025 + i): even ids a natural cubic
+    spline y(x) through knots every U(1,3) m with N(0, 0.3^2) m ordinates, odd ids y = A sin(kx + psi) with
+    A~U(0.2,1), k~U(0.3,1), psi~U(0,2pi); vref ramp-cruise 0.8 -> U(0.8,2.0) m/s over 2 s, advancing in time;
+    x0 from generation_type1.py:260-265's ranges with heading / lateral offset relative to the path."""
+    import trajectory_generation_b200 as tg
+    sc = tg.Scenarios(B)
+    x0 = np.zeros((B, 6))
+    for b in range(B):
+        i = traj_id0 + b
+        rng = np.random.default_rng(seed + i)
+        X = rng.uniform(-2.0, 2.0)
+        if i % 2 == 0:
+            kx = [-6.0]
+            while kx[-1] < 45.0:
+                kx.append(kx[-1] + rng.uniform(1.0, 3.0))
+            ky = rng.normal(0.0, 0.3, len(kx))
+            sc.set_spline(b, kx, ky)
+            from scipy.interpolate import CubicSpline
+            cs = CubicSpline(kx, ky, bc_type="natural")
+            y, dy = float(cs(X)), float(cs(X, 1))
+        else:
+            A, k, psi = rng.uniform(0.2, 1.0), rng.uniform(0.3, 1.0), rng.uniform(0.0, 2 * np.pi)
+            sc.set_sine(b, A, k, psi, 0.0)
+            y, dy = A * np.sin(k * X + psi), A * k * np.cos(k * X + psi)
+        sc.set_vref(b, tg.VREF_RAMP, 0.8, rng.uniform(0.8, 2.0), 2.0)
+        x0[b] = [X, y + rng.uniform(-0.2, 0.2), np.arctan(dy) + rng.uniform(-0.2, 0.2), rng.uniform(0.4, 1.5),
+                 rng.uniform(-0.05, 0.05), rng.uniform(-1.0, 1.0)]
+    u0 = np.stack([tg.d_steady_state(x0[:, 3]), np.zeros(B)], axis=1)
+    return x0, u0, sc
+
+
+GEN_KW = dict(N=N_HORIZON, Ts=TS, plant=1, vref_advance=True)   # plant 1 = generation_type1's clipped plant
+
+
+def algorithmic_flops_per_step(N, iters, check_every):
+    """SURVEY.md section 8(d) convention (add/mul = 1, FMA = 2, transcendental/div/sqrt = 1), analytic Jacobians."""
+    F_lin = 420 * N
+    F_cond = 72 * N * (N - 1) + 78 * N
+    F_hess = 2 * N * (N + 1) * (2 * N + 1) + 9 * N * (N + 1)
+    F_fact = (2 * N) ** 3 / 3 + (2 * N) ** 2
+    F_iter = 2 * (2 * N) ** 2 + 64 * N
+    F_check = 2 * (2 * N) ** 2 + 30 * N
+    return F_lin + F_cond + F_hess + F_fact + iters * F_iter + (iters / check_every) * F_check + 150
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_traj(args):
+    """MPC/main.py:85-101 for one trajectory of the workload: oracle port, cold-started restated OSQP each step."""
+    b, n_steps, x0, u0, spec, brk, coef = args
+    from oracle import dynamics as dyn, mpc as ompc, refgen as R
+    kind = int(spec["path_kind"])
+    spline = None
+    if kind == R.PATH_SPLINE:
+        f, K = int(spec["spline_first"]), int(spec["spline_count"])
+        spline = (np.append(brk[f:f + K], np.inf), coef[f:f + K])
+    t0 = time.perf_counter()
+    X, U, st, its = ompc.closed_loop(x0, u0, n_steps, TS, N_HORIZON, path_kind=kind, path_prm=tuple(spec["path"]), spline=spline,
+                                     vref_kind=int(spec["vref_kind"]), vref_prm=tuple(spec["vref"]), vref_advance=True,
+                                     plant=dyn.PLANT_GEN1, solver="osqp")
+    return time.perf_counter() - t0, int(np.sum(its)), sum(s == "optimal" for s in st)
+
+
+def cpu_baseline(n_traj, n_steps, cores):
+    """-> (MPC steps/s over all cores, description).  Every worker runs whole trajectories of the bench workload."""
+    import multiprocessing as mp
+    x0, u0, sc = make_workload(n_traj)
+    brk, coef = sc.tables()
+    jobs = [(b, n_steps, x0[b], u0[b], sc.spec[b], brk, coef) for b in range(n_traj)]
+    t0 = time.perf_counter()
+    if cores > 1:
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_cpu_traj, jobs)
+    else:
+        res = [_cpu_traj(j) for j in jobs]
+    wall = time.perf_counter() - t0
+    steps = n_traj * n_steps
+    return steps / wall, {"wall_s": wall, "mean_osqp_iters": sum(r[1] for r in res) / steps,
+                          "optimal_frac": sum(r[2] for r in res) / steps}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_traj, n_steps = cores, 60
+    vals = []
+    for it in range(args.warmup + args.steps):
+        v, info = cpu_baseline(n_traj, n_steps, cores)
+        if it >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    sample = f"{n_traj} trajectories x {n_steps} closed-loop steps of the config-2 workload per step, one process per core"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "MPC steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * n_traj * n_steps / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2 (generation_type1-style spline/sinusoidal references), N=20, Ts=0.01",
+                       "note": "oracle/ port of MPC/main.py's loop (reference linearisation + restated CVXPY problem + restated OSQP, "
+                               "cold start per step); cvxpy/osqp are not installed and cannot be installed offline"},
+            "cpu_baseline": {"value": value, "unit": "MPC steps/s", "cores": cores, "kind": "port", "sample": sample, **info},
+            "e2e": {"value": value, "unit": "MPC steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args, rank, world, local_rank):
+    import ctypes
+    import torch
+    import trajectory_generation_b200 as tg
+    from trajectory_generation_b200 import _lib
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, T, N = args.batch, args.horizon_steps, N_HORIZON
+    traj_id0 = rank * B
+    x0, u0, sc = make_workload(B, traj_id0)
+    brk, coef = sc.tables()
+    gen = tg.ClosedLoopGenerator(device=local_rank, **GEN_KW)
+    stream = torch.cuda.Stream(device=dev)
+    gen.set_stream(stream.cuda_stream)
+    L = _lib.load()
+
+    # ---- resident inputs / outputs (torch = device memory plumbing)
+    def dev_t(a, dtype=torch.float64):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev) if a.size else torch.zeros(1, dtype=dtype, device=dev)
+    d_x0, d_u0 = dev_t(x0), dev_t(u0)
+    d_spec = torch.from_numpy(np.ascontiguousarray(sc.spec).view(np.uint8)).to(dev)
+    d_brk, d_coef = dev_t(brk), dev_t(coef)
+    d_clean = torch.empty((B, T + 1, 6), dtype=torch.float64, device=dev)
+    d_noisy = torch.empty_like(d_clean)
+    d_U = torch.empty((B, T, 2), dtype=torch.float64, device=dev)
+    d_sc = torch.zeros((B, 6), dtype=torch.int32, device=dev)
+    d_it = torch.zeros(B, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def launch():
+        _lib.check(L.tg_closed_loop(gen.handle, B, T, d_x0.data_ptr(), d_u0.data_ptr(), d_spec.data_ptr(), d_brk.data_ptr(),
+                                    d_coef.data_ptr(), traj_id0, d_clean.data_ptr(), d_noisy.data_ptr(), d_U.data_ptr(),
+                                    d_sc.data_ptr(), d_it.data_ptr()))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            launch()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = gen.kernel_launches()
+    evs = []
+    with torch.cuda.stream(stream):
+        for _ in range(args.steps):
+            flush.zero_()                                            # L2 flush between timed iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); launch(); e1.record(stream)
+            evs.append((e0, e1))
+    barrier()
+    kern_ms = [a.elapsed_time(b) for a, b in evs]
+    gpu_launches = gen.kernel_launches() - launches0
+    total_ms = float(np.sum(kern_ms))
+    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tm.item())
+    iters_total = int(d_it.sum().item())
+    status = d_sc.sum(0).cpu().numpy()
+    if dist is not None:
+        agg = torch.tensor([iters_total] + status.tolist(), dtype=torch.int64, device=dev)
+        dist.all_reduce(agg)
+        iters_total, status = int(agg[0].item()), agg[1:].cpu().numpy()
+    steps_per_launch = B * T
+    value = world * steps_per_launch * args.steps / (total_ms_max * 1e-3)
+    mean_iters = iters_total / (world * steps_per_launch)
+
+    # ---- e2e: public host API, pinned buffers, H2D + D2H inside the timed region
+    hx0, hu0 = torch.from_numpy(x0).pin_memory(), torch.from_numpy(u0).pin_memory()
+    spec_h = torch.from_numpy(np.ascontiguousarray(sc.spec).view(np.uint8)).pin_memory()
+    out = {"clean": torch.empty((B, T + 1, 6), dtype=torch.float64).pin_memory(), "noisy": torch.empty((B, T + 1, 6), dtype=torch.float64).pin_memory(),
+           "U": torch.empty((B, T, 2), dtype=torch.float64).pin_memory(), "sc": torch.zeros((B, 6), dtype=torch.int32).pin_memory(),
+           "it": torch.zeros(B, dtype=torch.int64).pin_memory()}
+
+    def e2e_call():
+        _lib.check(L.tg_closed_loop_host(gen.handle, B, T, hx0.data_ptr(), hu0.data_ptr(), spec_h.data_ptr(),
+                                         brk.ctypes.data if len(brk) else None, len(brk), coef.ctypes.data if len(coef) else None, len(coef),
+                                         traj_id0, out["clean"].data_ptr(), out["noisy"].data_ptr(), out["U"].data_ptr(),
+                                         out["sc"].data_ptr(), out["it"].data_ptr()))
+    e2e_call()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_call()
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * steps_per_launch * args.steps / float(te.item())
+    h2d = x0.nbytes + u0.nbytes + sc.spec.nbytes + brk.nbytes + coef.nbytes
+    d2h = 2 * B * (T + 1) * 6 * 8 + B * T * 2 * 8 + B * 6 * 4 + B * 8
+    e2e_ok = bool(np.array_equal(out["clean"].numpy(), d_clean.cpu().numpy()))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- p50 latency of one batched mpc_step call (device-resident, B problems)
+    lat = None
+    if rank == 0:
+        pr, vr = gen.ref_window(x0, sc)
+        ctl = tg.BatchedMPC(device=local_rank, N=N, Ts=TS)
+        ctl.set_stream(stream.cuda_stream)
+        d_pr, d_vr, d_uc = dev_t(pr), dev_t(vr), torch.empty((B, 2), dtype=torch.float64, device=dev)
+        d_st, d_its = torch.zeros(B, dtype=torch.int32, device=dev), torch.zeros(B, dtype=torch.int32, device=dev)
+        ev = []
+        with torch.cuda.stream(stream):
+            for i in range(110):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                _lib.check(L.tg_mpc_step(ctl.handle, B, d_x0.data_ptr(), d_u0.data_ptr(), d_pr.data_ptr(), d_vr.data_ptr(), d_uc.data_ptr(),
+                                         d_st.data_ptr(), d_its.data_ptr(), None, None, None, None))
+                b.record(stream)
+                ev.append((a, b))
+        torch.cuda.synchronize(dev)
+        lat = float(np.median([a.elapsed_time(b) for a, b in ev[10:]]))
+        gpu_launches += 110
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        fp64_peak = gen.fma_peak_tflops("f64")
+        kms = float(np.mean(kern_ms))
+        alg_bytes = steps_per_launch * 14 * 8 + B * (6 + 2) * 8 + B * 14 * 8      # 14 fp64 words out per MPC step + x0/u0 in + row 0
+        flops = steps_per_launch * algorithmic_flops_per_step(N, mean_iters, gen.cfg.check_every)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_closed_loop_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        cores = os.cpu_count() or 1
+        cb_traj, cb_steps = cores, 60
+        cb_val, cb_info = cpu_baseline(cb_traj, cb_steps, cores)
+        line = {
+            "metric": METRIC, "value": value, "unit": "MPC steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: generation_type1-style spline/sinusoidal references, fused closed loop",
+                       "batch_per_gpu": B, "global_batch": world * B, "horizon_N": N, "Ts": TS, "closed_loop_steps_T": T,
+                       "mpc_steps_per_bench_step": world * steps_per_launch, "plant": "generation_type1 (clipped)", "jacobian": "analytic",
+                       "solver": {"eps_abs": gen.cfg.eps_abs, "eps_rel": gen.cfg.eps_rel, "rho": gen.cfg.rho, "alpha": gen.cfg.alpha,
+                                  "check_every": gen.cfg.check_every, "warm_start": bool(gen.cfg.warm_start)},
+                       "parallelism": f"trajectory-parallel x{world}, no collective on the solve path",
+                       "l2": "256 MB buffer zeroed before every timed launch; outputs (138 MB) exceed the 126 MB L2"},
+            "mean_admm_iters_per_step": mean_iters, "status_counts": {k: int(v) for k, v in zip(tg.STATUS_STRINGS, status)},
+            "p50_step_latency_ms": lat, "p50_step_latency_note": f"one tg_mpc_step call over {B} problems, cold start, device-resident, CUDA events",
+            "e2e": {"value": e2e_value, "unit": "MPC steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "tg_closed_loop_host (pinned host buffers)", "matches_resident_run": e2e_ok},
+            "gpu_launches": int(gpu_launches),
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "tg_closed_loop_kernel", "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "the path is neither HBM- nor tensor-bound (SURVEY.md 8(d)): 112 B leave the SM per MPC step; see roofline_flop"},
+            "roofline_flop": {"bound": "fp64 CUDA-core FMA", "achieved": flops / (kms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": flops / (kms * 1e-3) / 1e12 / fp64_peak, "peak_source": "tg_fma_peak micro-benchmark in this run",
+                              "algorithmic_flops_per_mpc_step": flops / steps_per_launch},
+            "cpu_baseline": {"value": cb_val, "unit": "MPC steps/s", "cores": cores, "kind": "port",
+                             "sample": f"{cb_traj} trajectories x {cb_steps} closed-loop steps of the same workload, one process per core", **cb_info},
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="trajectories per GPU")
+    ap.add_argument("--horizon-steps", type=int, default=1200, help="closed-loop steps T per trajectory")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        args.warmup = max(args.warmup, 3) if args.warmup else 0
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
