@@ -40,7 +40,7 @@ __device__ __forceinline__ double tg_clamp(double v, double lo, double hi) { ret
 // ------------------------------------------------------------------------------------------------
 // f_cont: continuous-time dynamics, all three variants.  sd/cd = sin/cos(delta) are passed in because
 // the controller evaluates the whole horizon at the same delta (ubar_k = u_prev, mpc_6stati.py:170).
-__device__ __forceinline__ void tg_f_cont(const double *__restrict__ p, int variant, const double x[6], double d,
+__device__ __noinline__ void tg_f_cont(const double *__restrict__ p, int variant, const double x[6], double d,
                                           double delta, double sd, double cd, double f[6])
 {
     const double phi = x[2], vx = x[3], vy = x[4], om = x[5];
@@ -83,6 +83,60 @@ __device__ __forceinline__ void tg_plant_step(const DevCfg &c, double x[6], doub
     double sd, cd, f[6];
     sincos(delta, &sd, &cd);
     tg_f_cont(c.p, c.plant, x, d, delta, sd, cd, f);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = x[i] + c.Ts * f[i];
+    if (c.plant != TG_PLANT_MPC) {
+        x[3] = fmax(x[3], 0.0);
+        x[5] = tg_clamp(x[5], -6.0, 6.0);
+    }
+}
+
+// f_cont evaluated by the 4 lanes of a quad in SIMD: lane role 0 = front tyre chain (atan2 -> atan -> sin),
+// role 1 = rear tyre chain, roles 2/3 = sin(phi) / sin(phi + pi/2) = cos(phi) sharing the final sin with the
+// tyre lanes; three transcendental latencies instead of eight on the sequential rollout / plant path.  Must be
+// called by all 32 lanes of a warp; every lane returns the full f.
+__device__ __forceinline__ void tg_f_cont_lanes(const double *__restrict__ p, int variant, const double x[6], double d,
+                                                double delta, double sd, double cd, int lane, double f[6])
+{
+    const int role = lane & 3, base = lane & ~3;
+    const double phi = x[2], vx = x[3], vy = x[4], om = x[5];
+    const double vmag = fmax(fabs(vx), p[P_vx_zero]);
+    const double vx_eff = (variant == TG_MODEL_MPC) ? (double)((vx > 0.0) - (vx < 0.0)) * vmag : vmag;
+    const bool front = (role == 0);
+    const double Lt = front ? p[P_lf] : p[P_lr];
+    const double nl = front ? (om * Lt + vy) : (om * Lt - vy);
+    const double at = atan2(nl, vx_eff);
+    double alpha = front ? (-at + delta) : at;
+    if (front || variant != TG_MODEL_GEN1) alpha = tg_clamp(alpha, -p[P_maxAlpha], p[P_maxAlpha]);
+    const double th = (front ? p[P_Cf] : p[P_Cr]) * atan((front ? p[P_Bf] : p[P_Br]) * alpha);
+    const double arg = (role < 2) ? th : ((role == 2) ? phi : phi + 1.5707963267948966);
+    const double sv = sin(arg);
+    const double F = (front ? p[P_Df] : p[P_Dr]) * sv;
+    const double Fyf = __shfl_sync(0xffffffffu, F, base), Fyr = __shfl_sync(0xffffffffu, F, base + 1);
+    const double sp = __shfl_sync(0xffffffffu, sv, base + 2), cp = __shfl_sync(0xffffffffu, sv, base + 3);
+    const double vl = (variant == TG_MODEL_MPC) ? vx : vx_eff;
+    const double Frx = (p[P_Cm1] - p[P_Cm2] * vl) * d - p[P_Cr0] - p[P_Cr2] * (vl * vl);
+    const double m = p[P_m], Iz = p[P_Iz];
+    f[0] = vx * cp - vy * sp;
+    f[1] = vx * sp + vy * cp;
+    f[2] = om;
+    if (variant == TG_MODEL_MPC) {
+        f[3] = (1.0 / m) * (Frx - Fyf * sd + m * vy * om);
+        f[4] = (1.0 / m) * (Fyr + Fyf * cd - m * vx * om);
+        f[5] = (1.0 / Iz) * (Fyf * p[P_lf] * cd - Fyr * p[P_lr]);
+    } else {
+        f[3] = (Frx - Fyf * sd + m * vy * om) / m;
+        f[4] = (Fyr + Fyf * cd - m * vx * om) / m;
+        f[5] = (Fyf * p[P_lf] * cd - Fyr * p[P_lr]) / Iz;
+    }
+}
+
+// plant step by a whole warp (see tg_f_cont_lanes)
+__device__ __forceinline__ void tg_plant_step_lanes(const DevCfg &c, double x[6], double d, double delta, int lane)
+{
+    double sd, cd, f[6];
+    sincos(delta, &sd, &cd);
+    tg_f_cont_lanes(c.p, c.plant, x, d, delta, sd, cd, lane, f);
 #pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = x[i] + c.Ts * f[i];
     if (c.plant != TG_PLANT_MPC) {
@@ -193,7 +247,7 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
 
 // Central-difference linearisation, the reference's arithmetic verbatim (mpc_6stati.py:73-109):
 // 12 + 4 + 1 evaluations of f_cont, eps = 1e-5, g = xbar + Ts f - Ad xbar - Bd ubar.
-__device__ void tg_linearize_fd(const DevCfg &c, const double x[6], double d, double delta, double *__restrict__ rec)
+__device__ __noinline__ void tg_linearize_fd(const DevCfg &c, const double x[6], double d, double delta, double *__restrict__ rec)
 {
     const double eps = 1e-5;
     double Jx[6][6], Ju[6][2], f0[6], fp[6], fm[6], xx[6];

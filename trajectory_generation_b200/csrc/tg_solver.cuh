@@ -30,7 +30,7 @@ __host__ __device__ inline SmemLayout tg_make_layout(int N, int ms, int NP)
     L.xbar = take(6 * (N + 1)); L.lin = take(TG_LIN * N);
     L.Xr = take(N + 1); L.Yr = take(N + 1); L.Pr = take(N + 1); L.sn = take(N + 1); L.cs = take(N + 1); L.vref = take(N + 1);
     L.rr = take(3 * (N + 1));
-    L.w = take(2 * 3 * NP); L.v = take(2 * NP + 2);
+    L.w = take(2 * 3 * NP); L.v = take(2 * NP + 4);
     L.q = take(n); L.x = take(n); L.xt = take(NP); L.dH = take(n);
     L.z = take(m); L.y = take(m); L.l = take(m); L.u = take(m); L.rho = take(m); L.zt = take(m); L.dy = take(m);
     L.Gs = take(ms * NP);
@@ -53,30 +53,36 @@ struct StepResult {
     double objective;
 };
 
+// Block-wide max of NRED non-negative values.  The norms only feed the termination / rho tests, so they are
+// reduced in fp32 (rounded up): non-negative floats order like their bit patterns, which lets one REDUX
+// instruction per value replace a 5-stage 64-bit shuffle tree.  NaN (0x7fc00000) wins every max and is
+// detected by the caller.
 template <int NRED>
 __device__ __forceinline__ void tg_block_reduce_max(double (&vals)[NRED], double *red, int tid, int nthreads)
 {
     const int lane = tid & 31, wid = tid >> 5, nw = (nthreads + 31) >> 5;
+    unsigned int *ured = reinterpret_cast<unsigned int *>(red);
+    unsigned int u[NRED];
 #pragma unroll
     for (int i = 0; i < NRED; ++i) {
-        double v = vals[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-        vals[i] = v;
+        const float f = __double2float_ru(fabs(vals[i]));
+        u[i] = __reduce_max_sync(0xffffffffu, __float_as_uint(f));
     }
     if (nw > 1) {
         if (lane == 0)
 #pragma unroll
-            for (int i = 0; i < NRED; ++i) red[wid * 16 + i] = vals[i];
+            for (int i = 0; i < NRED; ++i) ured[wid * 16 + i] = u[i];
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < NRED; ++i) {
-            double v = red[i];
-            for (int w = 1; w < nw; ++w) v = fmax(v, red[w * 16 + i]);
-            vals[i] = v;
+            unsigned int v = ured[i];
+            for (int w = 1; w < nw; ++w) v = max(v, ured[w * 16 + i]);
+            u[i] = v;
         }
         __syncthreads();
     }
+#pragma unroll
+    for (int i = 0; i < NRED; ++i) vals[i] = (double)__uint_as_float(u[i]);
 }
 
 __device__ __forceinline__ double tg_block_reduce_sum(double v, double *red, int tid, int nthreads)
@@ -122,37 +128,52 @@ __device__ __forceinline__ void tg_build_K(const DevCfg &c, const SmemLayout &L,
     }
 }
 
-// In-register inversion of the SPD tile by n symmetric sweeps; on return a = -K^{-1}.
+// In-register inversion of the SPD tile by n symmetric sweeps (SWP_k: a_kk <- -1/a_kk, a_ik <- a_ik/a_kk,
+// a_ij <- a_ij - a_ik a_kj / a_kk); on return a = -K^{-1}.
+// Every thread of a row keeps the diagonal entry of its row in the scalar `diag`, so that no register of the
+// tile is ever indexed dynamically: the row-k threads publish their segment (row k = column k by symmetry),
+// patch v[k] = a_kk - 1 (which turns the generic update of column k into a_ik/a_kk) and v[NP] = 1/a_kk; every
+// thread then does one fused update with w = a_ik/a_kk (w = 1 - 1/a_kk on the pivot row, which turns the
+// generic update of row k into a_kj/a_kk).  The tile's own copy of the diagonal is repaired once at the end.
 template <int SEG, int S>
 __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayout &L, double *sm, double (&a)[SEG],
                                                 int row, int col0)
 {
     const int n = c.n, NP = c.NP;
     double *vb = sm + L.v;
-    for (int k = 0; k < n; ++k) {
-        double *v = vb + (k & 1) * (NP + 1);
-        if (row == k) {  // publish row k (= column k by symmetry); entry k carries a_kk - 1, slot NP the pivot
+    double diag = 0.0;
 #pragma unroll
-            for (int jj = 0; jj < SEG; ++jj) {
-                double val = a[jj];
-                if (col0 + jj == k) { v[NP] = val; val -= 1.0; }
-                v[col0 + jj] = val;
-            }
+    for (int jj = 0; jj < SEG; ++jj)
+        if (col0 + jj == row) diag = a[jj];
+#pragma unroll
+    for (int o = 1; o < S; o <<= 1) diag += __shfl_xor_sync(0xffffffffu, diag, o);   // the other segments hold 0
+    for (int k = 0; k < n; ++k) {
+        double *v = vb + (k & 1) * (NP + 2);
+        if (row == k) {
+            double2 *v2 = reinterpret_cast<double2 *>(v + col0);
+#pragma unroll
+            for (int jj = 0; jj < SEG; jj += 2) v2[jj >> 1] = make_double2(a[jj], a[jj + 1]);
+            if (k >= col0 && k < col0 + SEG) { v[k] = diag - 1.0; v[NP] = 1.0 / diag; }
         }
         __syncthreads();
         if (row < n) {
-            const double piv = v[NP];
-            const double p = 1.0 / piv;
-            if (row != k) {
-                const double wi = v[row] * p;
+            const double p = v[NP];
+            const double vi = v[row];
+            const bool piv = (row == k);
+            const double wi = piv ? (1.0 - p) : vi * p;
+            const double2 *v2 = reinterpret_cast<const double2 *>(v + col0);
 #pragma unroll
-                for (int jj = 0; jj < SEG; ++jj) a[jj] = fma(-wi, v[col0 + jj], a[jj]);
-            } else {
-#pragma unroll
-                for (int jj = 0; jj < SEG; ++jj) a[jj] = (col0 + jj == k) ? -p : v[col0 + jj] * p;
+            for (int jj = 0; jj < SEG; jj += 2) {
+                const double2 vv = v2[jj >> 1];
+                a[jj] = fma(-wi, vv.x, a[jj]);
+                a[jj + 1] = fma(-wi, vv.y, a[jj + 1]);
             }
+            diag = piv ? -p : fma(-wi, vi, diag);
         }
     }
+#pragma unroll
+    for (int jj = 0; jj < SEG; ++jj)
+        if (col0 + jj == row) a[jj] = diag;
     __syncthreads();
 }
 
@@ -178,20 +199,25 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     const double ud = up[0], udel = up[1];
 
     // ---------------- K1a: nominal rollout (mpc_6stati.py:167-172), sequential in k
-    if (tid == 0) {
+    if (tid < 32) {   // warp 0: quad-parallel f_cont, every lane carries the state
         double sd, cd, xs[6], f[6];
         sincos(udel, &sd, &cd);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { xs[i] = x0[i]; xbar[i] = xs[i]; }
+        for (int i = 0; i < 6; ++i) xs[i] = x0[i];
+        if (tid < 6) xbar[tid] = x0[tid];
         for (int k = 0; k < N; ++k) {
-            tg_f_cont(c.p, c.model, xs, ud, udel, sd, cd, f);
+            tg_f_cont_lanes(c.p, c.model, xs, ud, udel, sd, cd, tid, f);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) { xs[i] = xs[i] + c.Ts * f[i]; xbar[6 * (k + 1) + i] = xs[i]; }
+            for (int i = 0; i < 6; ++i) xs[i] = xs[i] + c.Ts * f[i];
+            if (tid == 0) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) xbar[6 * (k + 1) + i] = xs[i];
+            }
         }
     }
     // zero the W staging buffers and the mat-vec input pad while thread 0 integrates
     for (int i = tid; i < 2 * 3 * NP; i += NT) wbuf[i] = 0.0;
-    for (int i = tid; i < 2 * NP + 2; i += NT) sm[L.v + i] = 0.0;
+    for (int i = tid; i < 2 * NP + 4; i += NT) sm[L.v + i] = 0.0;
     for (int i = tid; i < NP; i += NT) xt[i] = 0.0;
     for (int i = tid; i < ms * (NP - n); i += NT) Gs[(i / (NP - n)) * NP + n + i % (NP - n)] = 0.0;  // pad columns
     for (int i = tid; i <= N; i += NT) { double s_, c_; sincos(Pr[i], &s_, &c_); sn[i] = s_; cs[i] = c_; }
@@ -379,11 +405,12 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     const double alpha = c.alpha, sigma = c.sigma;
     double *v = sm + L.v;  // mat-vec input (first NP entries)
     int status = TG_STATUS_USER_LIMIT, it = 0;
-    double obj = 0.0;
+    int until_check = c.check_every;
     if (x0_infeasible) status = TG_STATUS_INFEASIBLE;
     else
     for (it = 1; it <= c.max_iter; ++it) {
-        const bool check = (it % c.check_every == 0) || (it == c.max_iter);
+        const bool check = (--until_check == 0) || (it == c.max_iter);
+        if (check) until_check = c.check_every;
         // (a) rhs = sigma x - q + A'(rho z - y)
         if (tid < n) {
             const int j = tid;
@@ -395,11 +422,17 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         __syncthreads();
         // (b) x~ = K^{-1} rhs   (a holds -K^{-1})
         {
-            double part = 0.0;
+            double p0 = 0.0, p1 = 0.0;
             if (row < n) {
+                const double2 *v2 = reinterpret_cast<const double2 *>(v + col0);
 #pragma unroll
-                for (int jj = 0; jj < SEG; ++jj) part = fma(a[jj], v[col0 + jj], part);
+                for (int jj = 0; jj < SEG; jj += 2) {
+                    const double2 vv = v2[jj >> 1];
+                    p0 = fma(a[jj], vv.x, p0);
+                    p1 = fma(a[jj + 1], vv.y, p1);
+                }
             }
+            double part = p0 + p1;
 #pragma unroll
             for (int o = 1; o < S; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             if (row < n && seg == 0) xt[row] = -part;
@@ -415,8 +448,8 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 const double zr = alpha * xtj + (1.0 - alpha) * z[j];
                 const double zn = tg_clamp(zr + y[j] / rho[j], lb[j], ub[j]);
                 const double yn = y[j] + rho[j] * (zr - zn);
-                dy[j] = yn - y[j]; y[j] = yn; z[j] = zn; zt[j] = xtj;
-                rp = fmax(rp, fabs(xtj - zn)); nzt = fmax(nzt, fabs(xtj)); nz = fmax(nz, fabs(zn));
+                if (check) { dy[j] = yn - y[j]; zt[j] = xtj; rp = fabs(xtj - zn); nzt = fabs(xtj); nz = fabs(zn); }
+                y[j] = yn; z[j] = zn;
             }
             {   // rate row j
                 const int i = n + j;
@@ -424,8 +457,8 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 const double zr = alpha * ztl + (1.0 - alpha) * z[i];
                 const double zn = tg_clamp(zr + y[i] / rho[i], lb[i], ub[i]);
                 const double yn = y[i] + rho[i] * (zr - zn);
-                dy[i] = yn - y[i]; y[i] = yn; z[i] = zn; zt[i] = ztl;
-                rp = fmax(rp, fabs(ztl - zn)); nzt = fmax(nzt, fabs(ztl)); nz = fmax(nz, fabs(zn));
+                if (check) { dy[i] = yn - y[i]; zt[i] = ztl; rp = fmax(rp, fabs(ztl - zn)); nzt = fmax(nzt, fabs(ztl)); nz = fmax(nz, fabs(zn)); }
+                y[i] = yn; z[i] = zn;
             }
         }
         for (int r_ = tid; r_ < ms; r_ += NT) {
@@ -442,8 +475,8 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         if (!check) continue;
 
         // (d) residuals at (x~, z, y):  H x~ = rhs - sigma x~ - A'(rho .* z~)
-        double rd = 0.0, nh = 0.0, na = 0.0, natdy = 0.0, ndy = 0.0, cert = 0.0, objp = 0.0;
-        bool cert_ok = true, bad = false;
+        double rd = 0.0, nh = 0.0, na = 0.0, natdy = 0.0, ndy = 0.0;
+        bool bad = false;
         if (tid < n) {
             const int j = tid;
             double aty = y[j] + y[n + j], atr = rho[j] * zt[j] + rho[n + j] * zt[n + j], atd = dy[j] + dy[n + j];
@@ -456,19 +489,11 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
             }
             const double hx = v[j] - sigma * xt[j] - atr;
             rd = fabs(hx + q[j] + aty); nh = fabs(hx); na = fabs(aty); natdy = fabs(atd);
-            objp = xt[j] * (0.5 * hx + q[j]);
             bad = !(isfinite(hx) && isfinite(aty));
         }
-        for (int i = tid; i < m; i += NT) {
-            const double d_ = dy[i];
-            ndy = fmax(ndy, fabs(d_));
-            if (d_ > 0.0) { if (ub[i] >= TG_INF) cert_ok = cert_ok && (d_ <= 0.0); else cert += ub[i] * d_; }
-            else if (d_ < 0.0) { if (lb[i] <= -TG_INF) cert_ok = cert_ok && (d_ >= 0.0); else cert += lb[i] * d_; }
-        }
+        for (int i = tid; i < m; i += NT) ndy = fmax(ndy, fabs(dy[i]));
         double vals[9] = {rp, nzt, nz, rd, nh, na, natdy, ndy, bad ? 1.0 : 0.0};
         tg_block_reduce_max<9>(vals, red, tid, NT);
-        const double cert_sum = tg_block_reduce_sum(cert, red, tid, NT);
-        obj = tg_block_reduce_sum(objp, red, tid, NT);
         const double eps_p = c.eps_abs + c.eps_rel * fmax(vals[1], vals[2]);
         const double eps_d = c.eps_abs + c.eps_rel * fmax(fmax(vals[4], vals[5]), nq);
         if (vals[8] > 0.0 || !(vals[0] == vals[0]) || !(vals[3] == vals[3])) { status = TG_STATUS_NAN; break; }
@@ -477,21 +502,20 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
             if (vals[0] <= 10.0 * eps_p && vals[3] <= 10.0 * eps_d) status = TG_STATUS_OPTIMAL_INACCURATE;
             break;
         }
-        // primal infeasibility certificate (OSQP section 3.4); rows with an infinite bound on the side dy
-        // points to cannot certify (handled conservatively through the thresholded test below)
-        if (vals[7] > c.eps_pinf) {
-            // re-evaluate the support term with OSQP's thresholding of dy on infinite sides
-            if (cert_sum < -c.eps_pinf * vals[7] && vals[6] <= c.eps_pinf * vals[7]) {
-                // make sure no infinite side carries a significant component
-                double infc = 0.0;
-                for (int i = tid; i < m; i += NT) {
-                    const double d_ = dy[i];
-                    if ((ub[i] >= TG_INF && d_ > c.eps_pinf * vals[7]) || (lb[i] <= -TG_INF && d_ < -c.eps_pinf * vals[7])) infc = 1.0;
-                }
-                double iv[1] = {infc};
-                tg_block_reduce_max<1>(iv, red, tid, NT);
-                if (iv[0] == 0.0) { status = TG_STATUS_INFEASIBLE; break; }
+        // primal infeasibility certificate (OSQP section 3.4): ||A'dy|| <= eps ||dy||, u'(dy)+ + l'(dy)- < -eps ||dy||,
+        // and no significant component of dy on an infinite side
+        if (vals[7] > c.eps_pinf && vals[6] <= c.eps_pinf * vals[7]) {
+            double cert = 0.0, infc = 0.0;
+            const double thr = c.eps_pinf * vals[7];
+            for (int i = tid; i < m; i += NT) {
+                const double d_ = dy[i];
+                if (d_ > 0.0) { if (ub[i] >= TG_INF) { if (d_ > thr) infc = 1.0; } else cert += ub[i] * d_; }
+                else if (d_ < 0.0) { if (lb[i] <= -TG_INF) { if (d_ < -thr) infc = 1.0; } else cert += lb[i] * d_; }
             }
+            const double cert_sum = tg_block_reduce_sum(cert, red, tid, NT);
+            double iv[1] = {infc};
+            tg_block_reduce_max<1>(iv, red, tid, NT);
+            if (iv[0] == 0.0 && cert_sum < -thr) { status = TG_STATUS_INFEASIBLE; break; }
         }
         // adaptive rho (OSQP section 5.2), iteration-triggered so runs are reproducible
         if (c.adaptive_rho && Hws && it >= c.adaptive_rho_min_iter) {
@@ -511,6 +535,20 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 tg_sweep_invert<SEG, S>(c, L, sm, a, row, col0);
             }
         }
+    }
+    // objective at the returned point: c0 + q'x~ + 1/2 x~'H x~ with H x~ = rhs - sigma x~ - A'(rho .* z~)
+    double obj = 0.0;
+    if (status == TG_STATUS_OPTIMAL || status == TG_STATUS_OPTIMAL_INACCURATE) {
+        double objp = 0.0;
+        if (tid < n) {
+            const int j = tid;
+            double atr = rho[j] * zt[j] + rho[n + j] * zt[n + j];
+            if (j + 2 < n) atr -= rho[n + j + 2] * zt[n + j + 2];
+            for (int i = 0; i < ms; ++i) atr = fma(Gs[i * NP + j], rho[2 * n + i] * zt[2 * n + i], atr);
+            const double hx = v[j] - sigma * xt[j] - atr;
+            objp = xt[j] * (0.5 * hx + q[j]);
+        }
+        obj = tg_block_reduce_sum(objp, red, tid, NT);
     }
     if (it > c.max_iter) it = c.max_iter;
     res.status = status;

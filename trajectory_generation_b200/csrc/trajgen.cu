@@ -17,6 +17,10 @@
 
 #include "tg_solver.cuh"
 
+// threads per CTA of a shape and the residency the register allocator must allow (<= 65536 / (NT * MINB) registers)
+#define TG_NT(SEG, S) ((((SEG) * (S) * (S) + 31) / 32) * 32 < 64 ? 64 : (((SEG) * (S) * (S) + 31) / 32) * 32)
+#define TG_MINB(SEG, S) ((S) == 2 ? ((SEG) <= 12 ? 8 : 5) : 1)
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #define CK(call)                                                                                       \
@@ -38,7 +42,7 @@ struct StepArgs {
 };
 
 template <int SEG, int S>
-__global__ void __launch_bounds__(((SEG * S * S + 31) / 32) * 32 < 64 ? 64 : ((SEG * S * S + 31) / 32) * 32)
+__global__ void __launch_bounds__(TG_NT(SEG, S), TG_MINB(SEG, S))
 tg_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, const __grid_constant__ StepArgs a)
 {
     extern __shared__ __align__(16) double sm[];
@@ -153,7 +157,7 @@ struct LoopArgs {
 };
 
 template <int SEG, int S>
-__global__ void __launch_bounds__(((SEG * S * S + 31) / 32) * 32 < 64 ? 64 : ((SEG * S * S + 31) / 32) * 32)
+__global__ void __launch_bounds__(TG_NT(SEG, S), TG_MINB(SEG, S))
 tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, const __grid_constant__ LoopArgs a)
 {
     extern __shared__ __align__(16) double sm[];
@@ -198,17 +202,19 @@ tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
                 nx = ((tid + 2 < n) ? sm[L.xt + tid + 2] : sm[L.xt + tid]) - d0;
                 if (tid + 2 < n) { nyb = sm[L.y + tid + 2]; nyr = sm[L.y + n + tid + 2]; }
             }
-            if (tid == 0) {   // plant (MPC/main.py:97) + outputs
+            if (tid < 32) {   // plant (MPC/main.py:97) + outputs, warp 0 (quad-parallel f_cont)
                 const double ud = sm[L.uprev], udel = sm[L.uprev + 1];
                 const double u0 = ok ? ud + sm[L.xt] : ud, u1 = ok ? udel + sm[L.xt + 1] : udel;
                 double xs[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) xs[i] = sm[L.x0 + i];
-                tg_plant_step(c, xs, u0, u1);
+                tg_plant_step_lanes(c, xs, u0, u1, tid);
+                if (tid == 0) {
 #pragma unroll
-                for (int i = 0; i < 6; ++i) { sm[L.misc + 8 + i] = xs[i]; clean[6 * (size_t)(t + 1) + i] = xs[i]; }
-                U[2 * (size_t)t] = u0; U[2 * (size_t)t + 1] = u1;
-                sm[L.misc + 14] = u0; sm[L.misc + 15] = u1;
+                    for (int i = 0; i < 6; ++i) { sm[L.misc + 8 + i] = xs[i]; clean[6 * (size_t)(t + 1) + i] = xs[i]; }
+                    U[2 * (size_t)t] = u0; U[2 * (size_t)t + 1] = u1;
+                    sm[L.misc + 14] = u0; sm[L.misc + 15] = u1;
+                }
             }
             __syncthreads();
             // commit the new state / warm start
