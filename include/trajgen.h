@@ -118,6 +118,8 @@ int tg_destroy(tg_handle *h);
 int tg_set_stream(tg_handle *h, void *cuda_stream);
 int tg_synchronize(tg_handle *h);
 int tg_kernel_launches(tg_handle *h, int64_t *count); /* kernels launched through this handle so far */
+/* launch geometry the handle chose: resident CTAs per SM, threads per CTA (= per problem), dynamic shared memory per CTA, SM count */
+int tg_info(tg_handle *h, int32_t *ctas_per_sm, int32_t *threads_per_cta, int32_t *smem_bytes, int32_t *num_sms);
 
 /* K1 tap -- replaces MPC/mpc_6stati.py:165-178 (rollout + N x linearize_discretize).
  * x0[B][6], u_prev[B][2] -> A[B][N][6][6], Bm[B][N][6][2], g[B][N][6], xbar[B][N+1][6] (any output may be NULL) */

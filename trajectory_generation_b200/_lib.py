@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtrajgen.so")
+LIB_PATH = os.environ.get("TRAJGEN_LIB", os.path.join(_HERE, "libtrajgen.so"))
 CSRC = os.path.join(_HERE, "csrc")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -48,7 +48,7 @@ assert REF_SPEC_DTYPE.itemsize == 96
 # every symbol include/trajgen.h declares
 EXPORTS = (
     "tg_last_error", "tg_version", "tg_default_config", "tg_create", "tg_destroy", "tg_set_stream", "tg_synchronize",
-    "tg_kernel_launches", "tg_linearize", "tg_assemble", "tg_mpc_step", "tg_mpc_step_host", "tg_ref_window",
+    "tg_kernel_launches", "tg_info", "tg_linearize", "tg_assemble", "tg_mpc_step", "tg_mpc_step_host", "tg_ref_window",
     "tg_closed_loop", "tg_closed_loop_host", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
     "tg_device_count", "tg_malloc", "tg_free", "tg_memcpy_h2d", "tg_memcpy_d2h", "tg_malloc_host", "tg_free_host",
 )
@@ -90,6 +90,7 @@ def load():
     L.tg_set_stream.argtypes = [vp, vp]
     L.tg_synchronize.argtypes = [vp]
     L.tg_kernel_launches.argtypes = [vp, ctypes.POINTER(i64)]
+    L.tg_info.argtypes = [vp] + [ctypes.POINTER(i32)] * 4
     L.tg_linearize.argtypes = [vp, ctypes.c_int] + [vp] * 6
     L.tg_assemble.argtypes = [vp, ctypes.c_int] + [vp] * 10
     L.tg_mpc_step.argtypes = [vp, ctypes.c_int] + [vp] * 11

@@ -34,7 +34,7 @@ __host__ __device__ inline SmemLayout tg_make_layout(int N, int ms, int NP)
     L.q = take(n); L.x = take(n); L.xt = take(NP); L.dH = take(n);
     L.z = take(m); L.y = take(m); L.l = take(m); L.u = take(m); L.rho = take(m); L.zt = take(m); L.dy = take(m);
     L.Gs = take(ms * NP);
-    L.red = take(16 * 32);
+    L.red = take(16 * 16);
     L.total = o;
     return L;
 }

@@ -19,7 +19,10 @@
 
 // threads per CTA of a shape and the residency the register allocator must allow (<= 65536 / (NT * MINB) registers)
 #define TG_NT(SEG, S) ((((SEG) * (S) * (S) + 31) / 32) * 32 < 64 ? 64 : (((SEG) * (S) * (S) + 31) / 32) * 32)
-#define TG_MINB(SEG, S) ((S) == 2 ? ((SEG) <= 12 ? 8 : 5) : 1)
+#ifndef TG_MINB_20_2
+#define TG_MINB_20_2 7
+#endif
+#define TG_MINB(SEG, S) ((S) == 2 ? ((SEG) <= 12 ? 8 : TG_MINB_20_2) : ((SEG) == 16 ? 2 : 1))
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
@@ -352,11 +355,15 @@ struct tg_handle {
 template <typename F>
 static int dispatch_shape(const Shape &s, F &&f)
 {
+#ifndef TG_ONLY_SHAPE_20_2
     if (s.SEG == 12 && s.S == 2) return f(std::integral_constant<int, 12>(), std::integral_constant<int, 2>());
+#endif
     if (s.SEG == 20 && s.S == 2) return f(std::integral_constant<int, 20>(), std::integral_constant<int, 2>());
+#ifndef TG_ONLY_SHAPE_20_2
     if (s.SEG == 16 && s.S == 4) return f(std::integral_constant<int, 16>(), std::integral_constant<int, 4>());
     if (s.SEG == 20 && s.S == 4) return f(std::integral_constant<int, 20>(), std::integral_constant<int, 4>());
     if (s.SEG == 28 && s.S == 4) return f(std::integral_constant<int, 28>(), std::integral_constant<int, 4>());
+#endif
     return fail(TG_ERR_UNSUPPORTED, "no kernel shape for this horizon");
 }
 
@@ -445,6 +452,8 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
         auto k2 = tg_closed_loop_kernel<decltype(SEG)::value, decltype(S)::value>;
         CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
         CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        CK(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(k2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int o1 = 0, o2 = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k1, sh.NT, h->smem_bytes));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k2, sh.NT, h->smem_bytes));
@@ -476,6 +485,15 @@ int tg_destroy(tg_handle *h)
 
 int tg_set_stream(tg_handle *h, void *s) { if (!h) return fail(TG_ERR_INVALID, "null handle"); h->stream = (cudaStream_t)s; return TG_OK; }
 int tg_synchronize(tg_handle *h) { if (!h) return fail(TG_ERR_INVALID, "null handle"); CK(cudaStreamSynchronize(h->stream)); return TG_OK; }
+int tg_info(tg_handle *h, int32_t *ctas_per_sm, int32_t *threads_per_cta, int32_t *smem_bytes, int32_t *num_sms)
+{
+    if (!h) return fail(TG_ERR_INVALID, "null handle");
+    if (ctas_per_sm) *ctas_per_sm = h->grid_cap / h->num_sms;
+    if (threads_per_cta) *threads_per_cta = h->shape.NT;
+    if (smem_bytes) *smem_bytes = (int32_t)h->smem_bytes;
+    if (num_sms) *num_sms = h->num_sms;
+    return TG_OK;
+}
 int tg_kernel_launches(tg_handle *h, int64_t *count) { if (!h || !count) return fail(TG_ERR_INVALID, "null argument"); *count = h->launches; return TG_OK; }
 
 static int launch_step(tg_handle *h, StepArgs &a)

@@ -102,6 +102,12 @@ class BatchedMPC:
         _lib.check(_lib.load().tg_kernel_launches(self._h, ctypes.byref(c)))
         return c.value
 
+    def info(self):
+        """launch geometry: dict(ctas_per_sm, threads_per_cta, smem_bytes, num_sms)."""
+        v = [ctypes.c_int32() for _ in range(4)]
+        _lib.check(_lib.load().tg_info(self._h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("ctas_per_sm", "threads_per_cta", "smem_bytes", "num_sms"), [x.value for x in v]))
+
     # -- host-array API
     @staticmethod
     def _arr(a, shape):
