@@ -192,7 +192,10 @@ def run_gpu(args, rank, world, local_rank):
     traj_id0 = rank * B
     x0, u0, sc = make_workload(B, traj_id0)
     brk, coef = sc.tables()
-    gen = tg.ClosedLoopGenerator(device=local_rank, **GEN_KW)
+    kw = dict(GEN_KW)
+    if args.check_every:
+        kw["solver_opts"] = {"check_every": args.check_every}
+    gen = tg.ClosedLoopGenerator(device=local_rank, **kw)
     stream = torch.cuda.Stream(device=dev)
     gen.set_stream(stream.cuda_stream)
     L = _lib.load()
@@ -322,7 +325,7 @@ def run_gpu(args, rank, world, local_rank):
             pass
         cores = os.cpu_count() or 1
         cb_traj, cb_steps = cores, 60
-        cb_val, cb_info = cpu_baseline(cb_traj, cb_steps, cores)
+        cb_val, cb_info = (0.0, {"skipped": True}) if args.no_cpu else cpu_baseline(cb_traj, cb_steps, cores)
         line = {
             "metric": METRIC, "value": value, "unit": "MPC steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -364,6 +367,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="trajectories per GPU")
     ap.add_argument("--horizon-steps", type=int, default=1200, help="closed-loop steps T per trajectory")
+    ap.add_argument("--check-every", type=int, default=0, help="override the ADMM termination-check interval (0 = library default)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (development runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

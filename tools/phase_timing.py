@@ -1,0 +1,25 @@
+"""dev: per-phase clock64 breakdown of the step body (needs a -DTG_PHASE_TIMING build via TRAJGEN_LIB)."""
+import ctypes, sys
+import numpy as np
+sys.path.insert(0, ".")
+import bench
+import trajectory_generation_b200 as tg
+from trajectory_generation_b200 import _lib
+B, T = int(sys.argv[1]), int(sys.argv[2])
+x0, u0, sc = bench.make_workload(B)
+gen = tg.ClosedLoopGenerator(**bench.GEN_KW)
+gen.generate(x0, u0, sc, 5)
+L = _lib.load()
+L.tg_debug_phases.argtypes = [ctypes.c_void_p, ctypes.c_int]
+out = (ctypes.c_longlong * 16)()
+L.tg_debug_phases(None, 1)
+import time; t = time.time(); res = gen.generate(x0, u0, sc, T); dt = time.time() - t
+L.tg_debug_phases(out, 0)
+v = np.array(out[:8], dtype=float)
+names = ["rollout(+zero,sincos)", "linearise+resid", "K2 condense", "R-terms,bounds,rho", "buildK+sweep", "ADMM loop", "objective/exit", "-"]
+ntraj0 = len(range(0, B, min(B, gen.info()["ctas_per_sm"] * gen.info()["num_sms"])))
+steps = T * ntraj0
+print(f"B={B} T={T} wall {dt*1e3:.1f} ms  -> {B*T/dt:.3e} steps/s; CTA0 ran {ntraj0} trajectories")
+for nme, c in zip(names, v):
+    print(f"  {nme:24s} {c/steps:10.0f} cycles/step  {100*c/v.sum():5.1f}%")
+print(f"  body total {v.sum()/steps:.0f} cycles/step; wall per step {dt/T*1.965e9/ntraj0:.0f} cycles")

@@ -37,6 +37,23 @@ enum { P_Cm1 = 0, P_Cm2, P_Cr0, P_Cr2, P_Br, P_Cr, P_Dr, P_Bf, P_Cf, P_Df, P_m, 
 
 __device__ __forceinline__ double tg_clamp(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
+// One copy of each fp64 transcendental per kernel: the libdevice bodies are 120-350 SASS instructions each, and
+// the step body calls them from eight places; inlining every call made the per-step instruction footprint
+// several times the 32 KB L1.5 instruction cache (ncu: stall_no_instruction 3.6 cycles per issue).
+#ifndef TG_NOINLINE_MATH
+#define TG_NOINLINE_MATH 0
+#endif
+#if TG_NOINLINE_MATH
+#define TG_MATH_ATTR __noinline__
+#else
+#define TG_MATH_ATTR __forceinline__
+#endif
+__device__ TG_MATH_ATTR double2 tg_sincos2(double x) { double s_, c_; sincos(x, &s_, &c_); return make_double2(s_, c_); }
+__device__ TG_MATH_ATTR double tg_atan2(double y, double x) { return atan2(y, x); }
+__device__ TG_MATH_ATTR double tg_atan(double x) { return atan(x); }
+__device__ TG_MATH_ATTR double tg_sin(double x) { return sin(x); }
+__device__ __forceinline__ void TG_SINCOS(double x_, double &s_, double &c_) { const double2 r_ = tg_sincos2(x_); s_ = r_.x; c_ = r_.y; }
+
 // ------------------------------------------------------------------------------------------------
 // f_cont: continuous-time dynamics, all three variants.  sd/cd = sin/cos(delta) are passed in because
 // the controller evaluates the whole horizon at the same delta (ubar_k = u_prev, mpc_6stati.py:170).
@@ -52,16 +69,16 @@ __device__ __noinline__ void tg_f_cont(const double *__restrict__ p, int variant
     } else {
         vx_eff = vmag;  // generation_type1.py:41
     }
-    double af = -atan2(om * p[P_lf] + vy, vx_eff) + delta;
-    double ar = atan2(om * p[P_lr] - vy, vx_eff);
+    double af = -tg_atan2(om * p[P_lf] + vy, vx_eff) + delta;
+    double ar = tg_atan2(om * p[P_lr] - vy, vx_eff);
     af = tg_clamp(af, -p[P_maxAlpha], p[P_maxAlpha]);
     if (variant != TG_MODEL_GEN1) ar = tg_clamp(ar, -p[P_maxAlpha], p[P_maxAlpha]);  // gen1 leaves alpha_r free (:46)
-    const double Fyf = p[P_Df] * sin(p[P_Cf] * atan(p[P_Bf] * af));
-    const double Fyr = p[P_Dr] * sin(p[P_Cr] * atan(p[P_Br] * ar));
+    const double Fyf = p[P_Df] * tg_sin(p[P_Cf] * tg_atan(p[P_Bf] * af));
+    const double Fyr = p[P_Dr] * tg_sin(p[P_Cr] * tg_atan(p[P_Br] * ar));
     const double vl = (variant == TG_MODEL_MPC) ? vx : vx_eff;  // :51 vs generation_type1.py:53
     const double Frx = (p[P_Cm1] - p[P_Cm2] * vl) * d - p[P_Cr0] - p[P_Cr2] * (vl * vl);
     double sp, cp;
-    sincos(phi, &sp, &cp);
+    TG_SINCOS(phi, sp, cp);
     const double m = p[P_m], Iz = p[P_Iz];
     f[0] = vx * cp - vy * sp;
     f[1] = vx * sp + vy * cp;
@@ -81,7 +98,7 @@ __device__ __noinline__ void tg_f_cont(const double *__restrict__ p, int variant
 __device__ __forceinline__ void tg_plant_step(const DevCfg &c, double x[6], double d, double delta)
 {
     double sd, cd, f[6];
-    sincos(delta, &sd, &cd);
+    TG_SINCOS(delta, sd, cd);
     tg_f_cont(c.p, c.plant, x, d, delta, sd, cd, f);
 #pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = x[i] + c.Ts * f[i];
@@ -92,7 +109,7 @@ __device__ __forceinline__ void tg_plant_step(const DevCfg &c, double x[6], doub
 }
 
 // f_cont evaluated by the 4 lanes of a quad in SIMD: lane role 0 = front tyre chain (atan2 -> atan -> sin),
-// role 1 = rear tyre chain, roles 2/3 = sin(phi) / sin(phi + pi/2) = cos(phi) sharing the final sin with the
+// role 1 = rear tyre chain, roles 2/3 = tg_sin(phi) / tg_sin(phi + pi/2) = cos(phi) sharing the final sin with the
 // tyre lanes; three transcendental latencies instead of eight on the sequential rollout / plant path.  Must be
 // called by all 32 lanes of a warp; every lane returns the full f.
 __device__ __forceinline__ void tg_f_cont_lanes(const double *__restrict__ p, int variant, const double x[6], double d,
@@ -105,12 +122,12 @@ __device__ __forceinline__ void tg_f_cont_lanes(const double *__restrict__ p, in
     const bool front = (role == 0);
     const double Lt = front ? p[P_lf] : p[P_lr];
     const double nl = front ? (om * Lt + vy) : (om * Lt - vy);
-    const double at = atan2(nl, vx_eff);
+    const double at = tg_atan2(nl, vx_eff);
     double alpha = front ? (-at + delta) : at;
     if (front || variant != TG_MODEL_GEN1) alpha = tg_clamp(alpha, -p[P_maxAlpha], p[P_maxAlpha]);
-    const double th = (front ? p[P_Cf] : p[P_Cr]) * atan((front ? p[P_Bf] : p[P_Br]) * alpha);
+    const double th = (front ? p[P_Cf] : p[P_Cr]) * tg_atan((front ? p[P_Bf] : p[P_Br]) * alpha);
     const double arg = (role < 2) ? th : ((role == 2) ? phi : phi + 1.5707963267948966);
-    const double sv = sin(arg);
+    const double sv = tg_sin(arg);
     const double F = (front ? p[P_Df] : p[P_Dr]) * sv;
     const double Fyf = __shfl_sync(0xffffffffu, F, base), Fyr = __shfl_sync(0xffffffffu, F, base + 1);
     const double sp = __shfl_sync(0xffffffffu, sv, base + 2), cp = __shfl_sync(0xffffffffu, sv, base + 3);
@@ -135,7 +152,7 @@ __device__ __forceinline__ void tg_f_cont_lanes(const double *__restrict__ p, in
 __device__ __forceinline__ void tg_plant_step_lanes(const DevCfg &c, double x[6], double d, double delta, int lane)
 {
     double sd, cd, f[6];
-    sincos(delta, &sd, &cd);
+    TG_SINCOS(delta, sd, cd);
     tg_f_cont_lanes(c.p, c.plant, x, d, delta, sd, cd, lane, f);
 #pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = x[i] + c.Ts * f[i];
@@ -188,8 +205,8 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
     else                         { vx_eff = vmag;       dveff = free_v ? sgn : 0.0; }
     const double nf = om * lf + vy, nr = om * lr - vy;
     const double denf = nf * nf + vx_eff * vx_eff, denr = nr * nr + vx_eff * vx_eff;
-    double af = -atan2(nf, vx_eff) + delta;
-    double ar = atan2(nr, vx_eff);
+    double af = -tg_atan2(nf, vx_eff) + delta;
+    double ar = tg_atan2(nr, vx_eff);
     // partials of the slip angles (zero where the clamp is active)
     double af_vx = (nf / denf) * dveff, af_vy = -vx_eff / denf, af_om = -lf * vx_eff / denf, af_de = 1.0;
     double ar_vx = -(nr / denr) * dveff, ar_vy = -vx_eff / denr, ar_om = lr * vx_eff / denr;
@@ -197,8 +214,8 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
     if (variant != TG_MODEL_GEN1 && (ar > ma || ar < -ma)) { ar = tg_clamp(ar, -ma, ma); ar_vx = ar_vy = ar_om = 0.0; }
     double s1, c1, s2, c2;
     const double Bf = p[P_Bf], Br = p[P_Br];
-    sincos(p[P_Cf] * atan(Bf * af), &s1, &c1);
-    sincos(p[P_Cr] * atan(Br * ar), &s2, &c2);
+    TG_SINCOS(p[P_Cf] * tg_atan(Bf * af), s1, c1);
+    TG_SINCOS(p[P_Cr] * tg_atan(Br * ar), s2, c2);
     const double Fyf = p[P_Df] * s1, Fyr = p[P_Dr] * s2;
     const double dFf = p[P_Df] * c1 * p[P_Cf] * Bf / (1.0 + (Bf * af) * (Bf * af));  // dFyf / d alpha_f
     const double dFr = p[P_Dr] * c2 * p[P_Cr] * Br / (1.0 + (Br * ar) * (Br * ar));
@@ -210,7 +227,7 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
     const double Frx_vx = (-p[P_Cm2] * d - 2.0 * p[P_Cr2] * vl) * dvl;
     const double Frx_d = p[P_Cm1] - p[P_Cm2] * vl;
     double sp, cp;
-    sincos(phi, &sp, &cp);
+    TG_SINCOS(phi, sp, cp);
     double f[6];
     f[0] = vx * cp - vy * sp;
     f[1] = vx * sp + vy * cp;
@@ -252,7 +269,7 @@ __device__ __noinline__ void tg_linearize_fd(const DevCfg &c, const double x[6],
     const double eps = 1e-5;
     double Jx[6][6], Ju[6][2], f0[6], fp[6], fm[6], xx[6];
     double sd, cd;
-    sincos(delta, &sd, &cd);
+    TG_SINCOS(delta, sd, cd);
     for (int i = 0; i < 6; ++i) {
         for (int j = 0; j < 6; ++j) xx[j] = x[j];
         xx[i] = x[i] + eps;
@@ -266,9 +283,9 @@ __device__ __noinline__ void tg_linearize_fd(const DevCfg &c, const double x[6],
     for (int r = 0; r < 6; ++r) Ju[r][0] = (fp[r] - fm[r]) / (2.0 * eps);
     {
         double s2, c2;
-        sincos(delta + eps, &s2, &c2);
+        TG_SINCOS(delta + eps, s2, c2);
         tg_f_cont(c.p, c.model, x, d, delta + eps, s2, c2, fp);
-        sincos(delta - eps, &s2, &c2);
+        TG_SINCOS(delta - eps, s2, c2);
         tg_f_cont(c.p, c.model, x, d, delta - eps, s2, c2, fm);
         for (int r = 0; r < 6; ++r) Ju[r][1] = (fp[r] - fm[r]) / (2.0 * eps);
     }
@@ -308,7 +325,7 @@ __device__ __forceinline__ double tg_vref_at(int kind, const double *__restrict_
             if (t > t_acc + t_flat) r = vmax - (vmax - v0) * ((t - (t_acc + t_flat)) / t_dec);
             return tg_clamp(r, v0, vmax);
         }
-        default: return v[0] + v[1] * sin(2.0 * 3.141592653589793 * t / v[2]);
+        default: return v[0] + v[1] * tg_sin(2.0 * 3.141592653589793 * t / v[2]);
     }
 }
 
@@ -320,7 +337,7 @@ __device__ __forceinline__ void tg_path_at(const tg_ref_spec &s, const double *_
         dy = 2.0 * s.path[0] * xs + s.path[1];
     } else if (s.path_kind == TG_PATH_SINE) {
         double sn, cs;
-        sincos(s.path[1] * xs + s.path[2], &sn, &cs);
+        TG_SINCOS(s.path[1] * xs + s.path[2], sn, cs);
         y = s.path[0] * sn + s.path[3];
         dy = s.path[0] * s.path[1] * cs;
     } else {

@@ -2,21 +2,56 @@
 //
 // Replaces MPC/mpc_6stati.py:165-275 (nominal rollout, N x linearize_discretize, CVXPY problem
 // construction, OSQP solve, receding-horizon output) with:
-//   K1  rollout + per-stage linearisation (compact 28-word records in shared memory)
+//   K1  rollout (warp 0, quad-parallel f_cont) + per-stage linearisation (compact 28-word records in
+//       shared memory); in the fused closed loop warps 1 and 2 build the reference window and the sensor
+//       noise of the current row while warp 0 integrates
 //   K2  condensing in dU = U - u_prev: the columns of G_k live in registers (one column per thread)
-//       and stream through the horizon; H = 2 (sum_k W_k' L W_k + Rbar + D' Rdbar D) accumulates in a
-//       register-resident n x n matrix distributed as (row, column segment) over the CTA
+//       and stream through the horizon TG_KB stages per barrier; H = 2 (sum_k W_k' L W_k + Rbar + D' Rdbar D)
+//       accumulates in a register-resident n x n matrix distributed as (row, column segment) over the CTA
 //   K3  ADMM (OSQP iteration) with per-row rho scaled by diag(H); K = H + sigma I + A' diag(rho) A is
 //       inverted in registers by n symmetric sweep steps; every iteration is one register mat-vec plus
-//       O(n) vector work; warp-shuffle reductions for the residual norms; adaptive rho refactors from a
-//       copy of H kept in an L2-resident per-CTA workspace.
+//       O(n) vector work on register-resident (x, z, y) with two barriers; REDUX reductions for the
+//       residual norms; adaptive rho refactors from a copy of H kept in an L2-resident per-CTA workspace.
 // Thread layout: thread t -> matrix row t / S, column segment t % S of width SEG (n <= S*SEG = NP).
 #pragma once
 #include "tg_device.cuh"
 
+#ifndef TG_KB
+#define TG_KB 4   // horizon stages condensed per barrier in K2
+#endif
+// register-resident ADMM vectors: fewer barriers but it does not fit the 80-register budget of 8 CTAs/SM
+// (measured 7.1 M vs 8.6 M steps/s with the shared-memory path), so it is off
+#ifndef TG_FAST_ADMM
+#define TG_FAST_ADMM 0
+#endif
+
+// Scheduling fence: an empty asm that "modifies" the listed values.  NVVM otherwise sinks each shared-memory load
+// next to its first use, and ptxas keeps that order, so every DFMA waits a full LDS latency (ncu: short_scoreboard
+// on 60 of 60 FMAs per stage).  Routing all loaded values through one asm forces the loads to be issued as a batch.
+#define TG_FENCE2(a, b) asm volatile("" : "+d"((a).x), "+d"((a).y), "+d"((b).x), "+d"((b).y))
+#define TG_FENCE6(a, b, c_, d_, e, f) asm volatile("" : "+d"((a).x), "+d"((a).y), "+d"((b).x), "+d"((b).y), "+d"((c_).x), "+d"((c_).y), \
+                                                   "+d"((d_).x), "+d"((d_).y), "+d"((e).x), "+d"((e).y), "+d"((f).x), "+d"((f).y))
+template <int NV>
+__device__ __forceinline__ void tg_fence_all(double2 (&vv)[NV])
+{
+    static_assert(NV % 2 == 0, "even count");
+#pragma unroll
+    for (int i = 0; i < NV; i += 2) TG_FENCE2(vv[i], vv[i + 1]);
+}
+
+// optional phase timing (development): -DTG_PHASE_TIMING accumulates clock64 deltas of CTA 0 / thread 0 per phase
+#ifdef TG_PHASE_TIMING
+__device__ long long g_tg_phase[16];
+#define TG_TICK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t__ = clock64(); g_tg_phase[i] += t__ - tg_last_tick; tg_last_tick = t__; } } while (0)
+#define TG_TICK_DECL long long tg_last_tick = clock64()
+#else
+#define TG_TICK(i) do { } while (0)
+#define TG_TICK_DECL do { } while (0)
+#endif
+
 // shared-memory layout (offsets in doubles), identical on host and device
 struct SmemLayout {
-    int x0, uprev, misc, xbar, lin, Xr, Yr, Pr, sn, cs, vref, rr, w, v, q, x, xt, dH, z, y, l, u, rho, zt, dy, Gs, red;
+    int x0, uprev, misc, spec, xbar, lin, Xr, Yr, Pr, sn, cs, vref, rr, w, v, q, x, xt, dH, z, y, l, u, rho, rinv, zt, dy, Gs, red;
     int total;
 };
 
@@ -26,26 +61,33 @@ __host__ __device__ inline SmemLayout tg_make_layout(int N, int ms, int NP)
     int o = 0;
     const int n = 2 * N, m = 4 * N + ms;
     auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };  // keep 16-byte alignment
-    L.x0 = take(6); L.uprev = take(2); L.misc = take(16);
+    L.x0 = take(6); L.uprev = take(2); L.misc = take(24); L.spec = take(12);
     L.xbar = take(6 * (N + 1)); L.lin = take(TG_LIN * N);
     L.Xr = take(N + 1); L.Yr = take(N + 1); L.Pr = take(N + 1); L.sn = take(N + 1); L.cs = take(N + 1); L.vref = take(N + 1);
     L.rr = take(3 * (N + 1));
-    L.w = take(2 * 3 * NP); L.v = take(2 * NP + 4);
-    L.q = take(n); L.x = take(n); L.xt = take(NP); L.dH = take(n);
-    L.z = take(m); L.y = take(m); L.l = take(m); L.u = take(m); L.rho = take(m); L.zt = take(m); L.dy = take(m);
+    L.w = take(2 * TG_KB * 3 * NP); L.v = take(2 * NP + 4);
+    L.q = take(n); L.x = take(n); L.xt = take(NP + 2); L.dH = take(n);
+    L.z = take(m); L.y = take(m); L.l = take(m); L.u = take(m); L.rho = take(m + 2); L.rinv = take(m + 2); L.zt = take(m); L.dy = take(m);
     L.Gs = take(ms * NP);
     L.red = take(16 * 16);
     L.total = o;
     return L;
 }
 
-// misc slots
-enum { M_C0 = 0, M_FLAG = 1, M_RHOSCALE = 2, M_NORMQ = 3, M_PIV0 = 4, M_PIV1 = 5, M_OBJ = 6 };
+// misc slots (doubles): 0 c0, 2 rho scale, 8..13 next state, 14..15 applied input, 16..19 counters (as 32/64-bit ints)
+enum { M_C0 = 0, M_RHOSCALE = 2, M_XNEXT = 8, M_UCMD = 14, M_CNT = 16 };
 
 struct StepTaps {   // optional debug/parity outputs of this problem (global memory, may be null)
     double *A, *Bm, *g, *xbar;          // tg_linearize
     double *H, *q, *c0, *l, *u, *Gs;    // tg_assemble
     int stop;                           // 0 = full step, 1 = stop after linearisation, 2 = stop after assembly
+};
+
+struct FusedCtx {   // closed-loop extras handled inside the step body while warp 0 integrates
+    const double *brk, *coef;   // spline tables (global)
+    double *noisy_row;          // where the noisy copy of the CURRENT state goes (global), or null
+    unsigned long long seed;
+    int t_index;
 };
 
 struct StepResult {
@@ -91,10 +133,10 @@ __device__ __forceinline__ double tg_block_reduce_sum(double v, double *red, int
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (nw > 1) {
-        if (lane == 0) red[wid * 16] = v;
+        if (lane == 0) red[wid * 8] = v;
         __syncthreads();
         v = red[0];
-        for (int w = 1; w < nw; ++w) v += red[w * 16];
+        for (int w = 1; w < nw; ++w) v += red[w * 8];
         __syncthreads();
     }
     return v;
@@ -147,6 +189,7 @@ __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayou
         if (col0 + jj == row) diag = a[jj];
 #pragma unroll
     for (int o = 1; o < S; o <<= 1) diag += __shfl_xor_sync(0xffffffffu, diag, o);   // the other segments hold 0
+#pragma unroll 1
     for (int k = 0; k < n; ++k) {
         double *v = vb + (k & 1) * (NP + 2);
         if (row == k) {
@@ -157,16 +200,19 @@ __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayou
         }
         __syncthreads();
         if (row < n) {
+            const double2 *v2 = reinterpret_cast<const double2 *>(v + col0);
+            double2 vv[SEG / 2];
+#pragma unroll
+            for (int jj = 0; jj < SEG / 2; ++jj) vv[jj] = v2[jj];
+            tg_fence_all(vv);
             const double p = v[NP];
             const double vi = v[row];
             const bool piv = (row == k);
             const double wi = piv ? (1.0 - p) : vi * p;
-            const double2 *v2 = reinterpret_cast<const double2 *>(v + col0);
 #pragma unroll
             for (int jj = 0; jj < SEG; jj += 2) {
-                const double2 vv = v2[jj >> 1];
-                a[jj] = fma(-wi, vv.x, a[jj]);
-                a[jj + 1] = fma(-wi, vv.y, a[jj + 1]);
+                a[jj] = fma(-wi, vv[jj >> 1].x, a[jj]);
+                a[jj + 1] = fma(-wi, vv[jj >> 1].y, a[jj + 1]);
             }
             diag = piv ? -p : fma(-wi, vi, diag);
         }
@@ -177,12 +223,61 @@ __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayou
     __syncthreads();
 }
 
-// One MPC step.  On entry shared memory holds x0, uprev, the reference window (Xr, Yr, Pr, vref) and, if
-// `warm`, the warm-start dU in sm[L.x] and duals in sm[L.y].  On exit sm[L.xt] holds dU* (x-tilde of the
-// last check), sm[L.y] the duals, sm[L.zt] = A dU*, and the result is returned to every thread.
+// x~ = K^{-1} v for the register tile (a = -K^{-1}); result to xt[row]
+template <int SEG, int S>
+__device__ __forceinline__ void tg_matvec(const double (&a)[SEG], const double *v, double *xt, int row, int seg, int col0, int n)
+{
+    double p0 = 0.0, p1 = 0.0;
+    if (row < n) {
+        const double2 *v2 = reinterpret_cast<const double2 *>(v + col0);
+        double2 vv[SEG / 2];
+#pragma unroll
+        for (int jj = 0; jj < SEG / 2; ++jj) vv[jj] = v2[jj];
+        tg_fence_all(vv);
+#pragma unroll
+        for (int jj = 0; jj < SEG; jj += 2) {
+            p0 = fma(a[jj], vv[jj >> 1].x, p0);
+            p1 = fma(a[jj + 1], vv[jj >> 1].y, p1);
+        }
+    }
+    double part = p0 + p1;
+#pragma unroll
+    for (int o = 1; o < S; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (row < n && seg == 0) xt[row] = -part;
+}
+
+// reference window by ONE warp (MPC/main.py:87-90): vref over the horizon, xs by sequential accumulation
+// (the reference's own summation order), y = path(xs), phi* = atan(path'(xs)), and sin/cos(phi*).
+__device__ __forceinline__ void tg_ref_window_warp(const DevCfg &c, const SmemLayout &L, double *sm, const tg_ref_spec &sp,
+                                                   const double *brk, const double *coef, int t_index, int lane)
+{
+    const int N = c.N;
+    const double t0 = c.vref_advance ? (double)t_index * c.Ts : 0.0;
+    const double vx0 = sm[L.x0 + 3];
+    for (int k = lane; k <= N; k += 32) sm[L.vref + k] = tg_vref_at(sp.vref_kind, sp.vref, t0 + (double)k * c.Ts, vx0);
+    __syncwarp();
+    if (lane == 0) {
+        double xs = sm[L.x0];
+        sm[L.Xr] = xs;
+        for (int k = 0; k < N; ++k) { xs = xs + sm[L.vref + k] * c.Ts; sm[L.Xr + k + 1] = xs; }   // :59-61
+    }
+    __syncwarp();
+    for (int k = lane; k <= N; k += 32) {
+        double y, dy, s_, c_;
+        tg_path_at(sp, brk, coef, sm[L.Xr + k], y, dy);
+        const double ph = tg_atan(dy);   // :66
+        TG_SINCOS(ph, s_, c_);
+        sm[L.Yr + k] = y; sm[L.Pr + k] = ph; sm[L.sn + k] = s_; sm[L.cs + k] = c_;
+    }
+}
+
+// One MPC step.  On entry shared memory holds x0, uprev and -- unless `fx` is given, in which case the body
+// builds it from the scenario in sm[L.spec] -- the reference window (Xr, Yr, Pr, vref); if `warm`, the
+// warm-start dU in sm[L.x] and duals in sm[L.y].  On exit sm[L.xt] holds dU* (x-tilde of the last check),
+// sm[L.y] the duals, and the result is returned to every thread.
 template <int SEG, int S>
 __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, double *sm, bool warm, double *Hws,
-                                       const StepTaps &tap)
+                                       const StepTaps &tap, const FusedCtx *fx)
 {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int N = c.N, n = c.n, NP = c.NP, ms = c.ms, m = c.m, ns = c.ns;
@@ -190,21 +285,22 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     StepResult res;
     res.status = TG_STATUS_NAN; res.iters = 0; res.objective = 0.0;
 
-    double *x0 = sm + L.x0, *up = sm + L.uprev, *misc = sm + L.misc, *xbar = sm + L.xbar, *lin = sm + L.lin;
-    double *Xr = sm + L.Xr, *Yr = sm + L.Yr, *Pr = sm + L.Pr, *sn = sm + L.sn, *cs = sm + L.cs, *vref = sm + L.vref;
+    double *misc = sm + L.misc, *xbar = sm + L.xbar, *lin = sm + L.lin;
+    double *sn = sm + L.sn, *cs = sm + L.cs;
     double *rr = sm + L.rr, *wbuf = sm + L.w, *q = sm + L.q, *x = sm + L.x, *xt = sm + L.xt, *dH = sm + L.dH;
-    double *z = sm + L.z, *y = sm + L.y, *lb = sm + L.l, *ub = sm + L.u, *rho = sm + L.rho, *zt = sm + L.zt, *dy = sm + L.dy;
-    double *Gs = sm + L.Gs, *red = sm + L.red;
+    double *z = sm + L.z, *y = sm + L.y, *lb = sm + L.l, *ub = sm + L.u, *rho = sm + L.rho, *rinv = sm + L.rinv;
+    double *zt = sm + L.zt, *dy = sm + L.dy, *Gs = sm + L.Gs, *red = sm + L.red;
+    TG_TICK_DECL;
 
-    const double ud = up[0], udel = up[1];
-
-    // ---------------- K1a: nominal rollout (mpc_6stati.py:167-172), sequential in k
-    if (tid < 32) {   // warp 0: quad-parallel f_cont, every lane carries the state
+    // ---------------- K1a: nominal rollout (mpc_6stati.py:167-172), sequential in k, by warp 0
+    if (tid < 32) {   // quad-parallel f_cont, every lane carries the state
+        const double ud = sm[L.uprev], udel = sm[L.uprev + 1];
         double sd, cd, xs[6], f[6];
-        sincos(udel, &sd, &cd);
+        TG_SINCOS(udel, sd, cd);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) xs[i] = x0[i];
-        if (tid < 6) xbar[tid] = x0[tid];
+        for (int i = 0; i < 6; ++i) xs[i] = sm[L.x0 + i];
+        if (tid < 6) xbar[tid] = sm[L.x0 + tid];
+#pragma unroll 1
         for (int k = 0; k < N; ++k) {
             tg_f_cont_lanes(c.p, c.model, xs, ud, udel, sd, cd, tid, f);
 #pragma unroll
@@ -214,35 +310,62 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 for (int i = 0; i < 6; ++i) xbar[6 * (k + 1) + i] = xs[i];
             }
         }
-    }
-    // zero the W staging buffers and the mat-vec input pad while thread 0 integrates
-    for (int i = tid; i < 2 * 3 * NP; i += NT) wbuf[i] = 0.0;
-    for (int i = tid; i < 2 * NP + 4; i += NT) sm[L.v + i] = 0.0;
-    for (int i = tid; i < NP; i += NT) xt[i] = 0.0;
-    for (int i = tid; i < ms * (NP - n); i += NT) Gs[(i / (NP - n)) * NP + n + i % (NP - n)] = 0.0;  // pad columns
-    for (int i = tid; i <= N; i += NT) { double s_, c_; sincos(Pr[i], &s_, &c_); sn[i] = s_; cs[i] = c_; }
-    __syncthreads();
-
-    // ---------------- K1b: linearise every stage (mpc_6stati.py:175-178) + tracking residuals at xbar
-    for (int k = tid; k < N; k += NT) {
-        double xs[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) xs[i] = xbar[6 * k + i];
-        if (c.jacobian == TG_JAC_FD) {
-            tg_linearize_fd(c, xs, ud, udel, lin + TG_LIN * k);
+    } else if (tid < 64) {
+        if (fx) {   // warp 1: reference window of this step
+            const tg_ref_spec &sp = *reinterpret_cast<const tg_ref_spec *>(sm + L.spec);
+            tg_ref_window_warp(c, L, sm, sp, fx->brk, fx->coef, fx->t_index, tid - 32);
         } else {
-            double sd, cd;
-            sincos(udel, &sd, &cd);
-            tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k);
+            for (int i = tid - 32; i <= N; i += 32) { double s_, c_; TG_SINCOS(sm[L.Pr + i], s_, c_); sn[i] = s_; cs[i] = c_; }
         }
     }
-    double c0_part = 0.0;
-    for (int k = tid; k <= N; k += NT) {
-        const double *xk = xbar + 6 * k;
-        const double rc = sn[k] * (xk[0] - Xr[k]) - cs[k] * (xk[1] - Yr[k]);  // lateral_error :111-117
-        const double rp = xk[2] - Pr[k], rv = xk[3] - vref[k];
-        rr[3 * k] = rc; rr[3 * k + 1] = rp; rr[3 * k + 2] = rv;
-        c0_part += c.q_c * rc * rc + c.q_phi * rp * rp + c.q_vx * rv * rv;
+    {   // sensor noise of the current row (never fed back): three lanes of warp 2 (warp 1 when the CTA has two warps)
+        const int nbase = (NT >= 96) ? 64 : 32;
+        if (fx && fx->noisy_row && tid >= nbase && tid < nbase + 3) {
+            const int pr = tid - nbase;
+            uint32_t r4[4];
+            tg_philox4x32_10((uint32_t)fx->t_index, (uint32_t)(pr >> 1), 0u, 0u, (uint32_t)fx->seed, (uint32_t)(fx->seed >> 32), r4);
+            double n0, n1;
+            tg_box_muller(r4[(pr & 1) * 2], r4[(pr & 1) * 2 + 1], n0, n1);
+            fx->noisy_row[2 * pr] = sm[L.x0 + 2 * pr] + c.noise_std[2 * pr] * n0;
+            fx->noisy_row[2 * pr + 1] = sm[L.x0 + 2 * pr + 1] + c.noise_std[2 * pr + 1] * n1;
+        }
+    }
+    // zero the W staging buffers and the mat-vec pads (threads beyond warp 0 get here first)
+    for (int i = tid; i < 2 * TG_KB * 3 * NP; i += NT) wbuf[i] = 0.0;
+    for (int i = tid; i < 2 * NP + 4; i += NT) sm[L.v + i] = 0.0;
+    for (int i = tid; i < NP + 2; i += NT) xt[i] = 0.0;
+    for (int i = tid; i < ms * (NP - n); i += NT) Gs[(i / (NP - n)) * NP + n + i % (NP - n)] = 0.0;  // pad columns
+    __syncthreads();
+    TG_TICK(0);
+
+    // ---------------- K1b: linearise every stage (mpc_6stati.py:175-178) + tracking residuals at xbar
+    {
+        const double ud = sm[L.uprev], udel = sm[L.uprev + 1];
+        for (int k = tid; k < N; k += NT) {
+            double xs[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) xs[i] = xbar[6 * k + i];
+            if (c.jacobian == TG_JAC_FD) {
+                tg_linearize_fd(c, xs, ud, udel, lin + TG_LIN * k);
+            } else {
+                double sd, cd;
+                TG_SINCOS(udel, sd, cd);
+                tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k);
+            }
+        }
+        // stage costs at xbar: threads of the LAST warp, so that they overlap the linearisation in warp 0
+        double c0_part = 0.0;
+        for (int k = NT - 1 - tid; k <= N; k += NT) {
+            const double *xk = xbar + 6 * k;
+            const double rc = sn[k] * (xk[0] - sm[L.Xr + k]) - cs[k] * (xk[1] - sm[L.Yr + k]);  // lateral_error :111-117
+            const double rp = xk[2] - sm[L.Pr + k], rv = xk[3] - sm[L.vref + k];
+            rr[3 * k] = rc; rr[3 * k + 1] = rp; rr[3 * k + 2] = rv;
+            c0_part += c.q_c * rc * rc + c.q_phi * rp * rp + c.q_vx * rv * rv;
+        }
+        // constant term: stage costs at xbar + N u_prev' R u_prev
+        double c0 = tg_block_reduce_sum(c0_part, red, tid, NT);
+        c0 += (double)N * (ud * (c.Rs[0] * ud + c.Rs[1] * udel) + udel * (c.Rs[2] * ud + c.Rs[3] * udel));
+        if (tid == 0) misc[M_C0] = c0;
     }
     __syncthreads();
     if (tap.A || tap.Bm || tap.g || tap.xbar) {
@@ -253,54 +376,82 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
             for (int i = tid; i < 6 * (N + 1); i += NT) tap.xbar[i] = xbar[i];
     }
     if (tap.stop == 1) return res;
+    TG_TICK(1);
 
     // ---------------- K2: condensing.  Thread j < n owns column j of G_k (6 registers).
     double a[SEG];
 #pragma unroll
     for (int jj = 0; jj < SEG; ++jj) a[jj] = 0.0;
-    double G0 = 0, G1 = 0, G2 = 0, G3 = 0, G4 = 0, G5 = 0, qacc = 0.0;
-    const double tqc = 2.0 * c.q_c, tqp = 2.0 * c.q_phi, tqv = 2.0 * c.q_vx;
-    for (int k = 0; k < N; ++k) {
-        double *wb = wbuf + (k & 1) * 3 * NP;
-        if (tid < n) {
-            const double *r = lin + TG_LIN * k;
-            const int j = tid;
-            if (j < 2 * k) {  // G_{k+1} = A_k G_k
-                const double n0 = G0 + r[0] * G2 + r[1] * G3 + r[2] * G4;
-                const double n1 = G1 + r[3] * G2 + r[4] * G3 + r[5] * G4;
-                const double n2 = G2 + r[6] * G5;
-                const double n3 = r[7] * G3 + r[8] * G4 + r[9] * G5;
-                const double n4 = r[10] * G3 + r[11] * G4 + r[12] * G5;
-                const double n5 = r[13] * G3 + r[14] * G4 + r[15] * G5;
-                G0 = n0; G1 = n1; G2 = n2; G3 = n3; G4 = n4; G5 = n5;
-            } else if (j < 2 * k + 2) {  // new block column: B_k
-                const int cc = j - 2 * k;
-                G0 = 0.0; G1 = 0.0; G2 = 0.0;
-                G3 = r[16 + cc]; G4 = r[18 + cc]; G5 = r[20 + cc];
+    {
+        double G0 = 0, G1 = 0, G2 = 0, G3 = 0, G4 = 0, G5 = 0, qacc = 0.0;
+        const double tqc = 2.0 * c.q_c, tqp = 2.0 * c.q_phi, tqv = 2.0 * c.q_vx;
+#pragma unroll 1
+        for (int k0 = 0; k0 < N; k0 += TG_KB) {   // TG_KB stages per barrier
+            const int kb = (N - k0 < TG_KB) ? N - k0 : TG_KB;
+            double *wblk = wbuf + ((k0 / TG_KB) & 1) * TG_KB * 3 * NP;
+            if (tid < n) {
+                const int j = tid;
+#pragma unroll 1
+                for (int s_i = 0; s_i < kb; ++s_i) {
+                    const int k = k0 + s_i;
+                    const double *r = lin + TG_LIN * k;
+                    double *wb = wblk + s_i * 3 * NP;
+                    if (j < 2 * k) {  // G_{k+1} = A_k G_k
+                        const double n0 = G0 + r[0] * G2 + r[1] * G3 + r[2] * G4;
+                        const double n1 = G1 + r[3] * G2 + r[4] * G3 + r[5] * G4;
+                        const double n2 = G2 + r[6] * G5;
+                        const double n3 = r[7] * G3 + r[8] * G4 + r[9] * G5;
+                        const double n4 = r[10] * G3 + r[11] * G4 + r[12] * G5;
+                        const double n5 = r[13] * G3 + r[14] * G4 + r[15] * G5;
+                        G0 = n0; G1 = n1; G2 = n2; G3 = n3; G4 = n4; G5 = n5;
+                    } else if (j < 2 * k + 2) {  // new block column: B_k
+                        const int cc = j - 2 * k;
+                        G0 = 0.0; G1 = 0.0; G2 = 0.0;
+                        G3 = r[16 + cc]; G4 = r[18 + cc]; G5 = r[20 + cc];
+                    }
+                    const int kk = k + 1;
+                    const double wc = sn[kk] * G0 - cs[kk] * G1;
+                    wb[j] = wc; wb[NP + j] = G2; wb[2 * NP + j] = G3;
+                    qacc += tqc * rr[3 * kk] * wc + tqp * rr[3 * kk + 1] * G2 + tqv * rr[3 * kk + 2] * G3;
+                    for (int si = 0; si < ns; ++si) {
+                        const int sx = c.sidx[si];
+                        const double gv = (sx == 0) ? G0 : (sx == 1) ? G1 : (sx == 2) ? G2 : (sx == 3) ? G3 : (sx == 4) ? G4 : G5;
+                        Gs[(k * ns + si) * NP + j] = gv;
+                    }
+                }
             }
-            const int kk = k + 1;
-            const double wc = sn[kk] * G0 - cs[kk] * G1;
-            wb[j] = wc; wb[NP + j] = G2; wb[2 * NP + j] = G3;
-            qacc += tqc * rr[3 * kk] * wc + tqp * rr[3 * kk + 1] * G2 + tqv * rr[3 * kk + 2] * G3;
-            for (int si = 0; si < ns; ++si) {
-                const int s_ = c.sidx[si];
-                const double gv = (s_ == 0) ? G0 : (s_ == 1) ? G1 : (s_ == 2) ? G2 : (s_ == 3) ? G3 : (s_ == 4) ? G4 : G5;
-                Gs[(k * ns + si) * NP + j] = gv;
+            __syncthreads();
+            if (row < n) {
+#pragma unroll 1
+                for (int s_i = 0; s_i < kb; ++s_i) {
+                    const int k = k0 + s_i;
+                    if (row < 2 * k + 2 && col0 < 2 * k + 2) {
+                        const double *wb = wblk + s_i * 3 * NP;
+                        const double w0 = wb[row] * tqc, w1 = wb[NP + row] * tqp, w2 = wb[2 * NP + row] * tqv;
+                        const double2 *wa = reinterpret_cast<const double2 *>(wb + col0);
+                        const double2 *wp = reinterpret_cast<const double2 *>(wb + NP + col0);
+                        const double2 *wv = reinterpret_cast<const double2 *>(wb + 2 * NP + col0);
+#pragma unroll
+                        for (int cc = 0; cc < SEG; cc += 4) {   // 6 x 128-bit loads in flight, then 12 FMAs
+                            double2 xa0 = wa[cc >> 1], xa1 = wa[(cc >> 1) + 1];
+                            double2 xp0 = wp[cc >> 1], xp1 = wp[(cc >> 1) + 1];
+                            double2 xv0 = wv[cc >> 1], xv1 = wv[(cc >> 1) + 1];
+                            TG_FENCE6(xa0, xa1, xp0, xp1, xv0, xv1);
+                            a[cc] = fma(w2, xv0.x, fma(w1, xp0.x, fma(w0, xa0.x, a[cc])));
+                            a[cc + 1] = fma(w2, xv0.y, fma(w1, xp0.y, fma(w0, xa0.y, a[cc + 1])));
+                            a[cc + 2] = fma(w2, xv1.x, fma(w1, xp1.x, fma(w0, xa1.x, a[cc + 2])));
+                            a[cc + 3] = fma(w2, xv1.y, fma(w1, xp1.y, fma(w0, xa1.y, a[cc + 3])));
+                        }
+                    }
+                }
             }
         }
-        __syncthreads();
-        if (row < 2 * k + 2 && col0 < 2 * k + 2 && row < n) {
-            const double w0 = wb[row] * tqc, w1 = wb[NP + row] * tqp, w2 = wb[2 * NP + row] * tqv;
-#pragma unroll
-            for (int jj = 0; jj < SEG; ++jj) {
-                double t = a[jj];
-                t = fma(w0, wb[col0 + jj], t);
-                t = fma(w1, wb[NP + col0 + jj], t);
-                t = fma(w2, wb[2 * NP + col0 + jj], t);
-                a[jj] = t;
-            }
+        if (tid < n) {
+            const int cc = tid & 1;
+            q[tid] = qacc + 2.0 * (c.Rs[cc * 2] * sm[L.uprev] + c.Rs[cc * 2 + 1] * sm[L.uprev + 1]);
         }
     }
+    TG_TICK(2);
     // input and input-rate penalties (mpc_6stati.py:238-245), expressed in dU
     if (row < n) {
         const int kr = row >> 1, cr = row & 1;
@@ -317,39 +468,34 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
             if (col == row) dH[row] = a[jj];
         }
     }
-    if (tid < n) {
-        const int cc = tid & 1;
-        q[tid] = qacc + 2.0 * (c.Rs[cc * 2] * ud + c.Rs[cc * 2 + 1] * udel);
-    }
-    // constant term: stage costs at xbar + N u_prev' R u_prev
-    {
-        double c0 = tg_block_reduce_sum(c0_part, red, tid, NT);
-        c0 += (double)N * (ud * (c.Rs[0] * ud + c.Rs[1] * udel) + udel * (c.Rs[2] * ud + c.Rs[3] * udel));
-        if (tid == 0) misc[M_C0] = c0;
-    }
     __syncthreads();
 
     // ---------------- bounds (mpc_6stati.py:198-221) and per-row rho = rho0 / max_j(a_ij^2 / H_jj)
     bool x0_infeasible = false;
     for (int si = 0; si < ns; ++si) {
-        const int s_ = c.sidx[si];
-        if (x0[s_] < c.x_lo[s_] - c.eps_abs || x0[s_] > c.x_hi[s_] + c.eps_abs) x0_infeasible = true;  // k = 0 rows (:217,:220)
+        const int sx = c.sidx[si];
+        const double xv = sm[L.x0 + sx];
+        if (xv < c.x_lo[sx] - c.eps_abs || xv > c.x_hi[sx] + c.eps_abs) x0_infeasible = true;  // k = 0 rows (:217,:220)
     }
+    double rho_scale = c.rho;
     if (tid < n) {
         const int j = tid, cc = j & 1;
-        lb[j] = c.u_lo[cc] - up[cc]; ub[j] = c.u_hi[cc] - up[cc];
-        lb[n + j] = c.du_lo[cc];     ub[n + j] = c.du_hi[cc];
-        rho[j] = dH[j];
-        rho[n + j] = (j >= 2) ? fmin(dH[j], dH[j - 2]) : dH[j];
+        const double upc = sm[L.uprev + cc];
+        lb[j] = c.u_lo[cc] - upc; ub[j] = c.u_hi[cc] - upc;
+        lb[n + j] = c.du_lo[cc];  ub[n + j] = c.du_hi[cc];
+        const double rb = rho_scale * dH[j], rr_ = rho_scale * ((j >= 2) ? fmin(dH[j], dH[j - 2]) : dH[j]);
+        rho[j] = rb; rho[n + j] = rr_;
+        rinv[j] = 1.0 / rb; rinv[n + j] = 1.0 / rr_;
     }
     for (int i = tid; i < ms; i += NT) {
-        const int kk = i / ns + 1, s_ = c.sidx[i % ns];
-        const double xb = xbar[6 * kk + s_];
-        lb[2 * n + i] = (c.x_lo[s_] <= -TG_INF) ? -TG_INF : c.x_lo[s_] - xb;
-        ub[2 * n + i] = (c.x_hi[s_] >= TG_INF) ? TG_INF : c.x_hi[s_] - xb;
+        const int kk = i / ns + 1, sx = c.sidx[i % ns];
+        const double xb = xbar[6 * kk + sx];
+        lb[2 * n + i] = (c.x_lo[sx] <= -TG_INF) ? -TG_INF : c.x_lo[sx] - xb;
+        ub[2 * n + i] = (c.x_hi[sx] >= TG_INF) ? TG_INF : c.x_hi[sx] - xb;
         double mx = 0.0;
         for (int j = 0; j < n; ++j) { const double gij = Gs[i * NP + j]; mx = fmax(mx, gij * gij / dH[j]); }
-        rho[2 * n + i] = (mx > 1e-30) ? 1.0 / mx : 1.0;
+        const double rs = rho_scale * ((mx > 1e-30) ? 1.0 / mx : 1.0);
+        rho[2 * n + i] = rs; rinv[2 * n + i] = 1.0 / rs;
     }
     if (tap.H && row < n) {
 #pragma unroll
@@ -357,19 +503,10 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
             if (col0 + jj < n) tap.H[row * n + col0 + jj] = a[jj];
     }
     if (Hws && row < n) {
+        double2 *h2 = reinterpret_cast<double2 *>(Hws + row * NP + col0);
 #pragma unroll
-        for (int jj = 0; jj < SEG; ++jj) Hws[row * NP + col0 + jj] = a[jj];
+        for (int jj = 0; jj < SEG; jj += 2) h2[jj >> 1] = make_double2(a[jj], a[jj + 1]);
     }
-    __syncthreads();
-    if (tap.q) for (int i = tid; i < n; i += NT) tap.q[i] = q[i];
-    if (tap.c0 && tid == 0) tap.c0[0] = misc[M_C0];
-    if (tap.l) for (int i = tid; i < m; i += NT) { tap.l[i] = lb[i]; tap.u[i] = ub[i]; }
-    if (tap.Gs) for (int i = tid; i < ms * n; i += NT) tap.Gs[i] = Gs[(i / n) * NP + (i % n)];
-    if (tap.stop == 2) return res;
-
-    // scale the unit rho pattern by rho0 (kept separately so adaptive rho can rescale)
-    double rho_scale = c.rho;
-    for (int i = tid; i < m; i += NT) rho[i] *= rho_scale;
     double nq = 0.0;
     for (int i = tid; i < n; i += NT) nq = fmax(nq, fabs(q[i]));
     {
@@ -377,184 +514,298 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         tg_block_reduce_max<1>(vals, red, tid, NT);
         nq = vals[0];
     }
-    __syncthreads();
+    __syncthreads();   // bounds / rho / q visible to every thread
+    if (tap.q) for (int i = tid; i < n; i += NT) tap.q[i] = q[i];
+    if (tap.c0 && tid == 0) tap.c0[0] = misc[M_C0];
+    if (tap.l) for (int i = tid; i < m; i += NT) { tap.l[i] = lb[i]; tap.u[i] = ub[i]; }
+    if (tap.Gs) for (int i = tid; i < ms * n; i += NT) tap.Gs[i] = Gs[(i / n) * NP + (i % n)];
+    if (tap.stop == 2) return res;
+    TG_TICK(3);
 
     // ---------------- K3: factor
     tg_build_K<SEG>(c, L, sm, a, row, col0);
     tg_sweep_invert<SEG, S>(c, L, sm, a, row, col0);
+    TG_TICK(4);
 
     // ---------------- ADMM
-    if (!warm) {
-        for (int i = tid; i < n; i += NT) x[i] = 0.0;
-        for (int i = tid; i < m; i += NT) { z[i] = 0.0; y[i] = 0.0; }
-    } else {
-        // z = clip(A x, l, u) for the warm-start point
-        for (int j = tid; j < n; j += NT) {
-            z[j] = tg_clamp(x[j], lb[j], ub[j]);
-            const double r_ = x[j] - ((j >= 2) ? x[j - 2] : 0.0);
-            z[n + j] = tg_clamp(r_, lb[n + j], ub[n + j]);
-        }
-        for (int i = tid; i < ms; i += NT) {
-            double acc = 0.0;
-            for (int j = 0; j < n; ++j) acc = fma(Gs[i * NP + j], x[j], acc);
-            z[2 * n + i] = tg_clamp(acc, lb[2 * n + i], ub[2 * n + i]);
-        }
-    }
-    __syncthreads();
-
     const double alpha = c.alpha, sigma = c.sigma;
     double *v = sm + L.v;  // mat-vec input (first NP entries)
     int status = TG_STATUS_USER_LIMIT, it = 0;
     int until_check = c.check_every;
-    if (x0_infeasible) status = TG_STATUS_INFEASIBLE;
-    else
-    for (it = 1; it <= c.max_iter; ++it) {
-        const bool check = (--until_check == 0) || (it == c.max_iter);
-        if (check) until_check = c.check_every;
-        // (a) rhs = sigma x - q + A'(rho z - y)
-        if (tid < n) {
-            const int j = tid;
-            double r_ = sigma * x[j] - q[j] + (rho[j] * z[j] - y[j]) + (rho[n + j] * z[n + j] - y[n + j]);
-            if (j + 2 < n) r_ -= (rho[n + j + 2] * z[n + j + 2] - y[n + j + 2]);
-            for (int i = 0; i < ms; ++i) r_ = fma(Gs[i * NP + j], rho[2 * n + i] * z[2 * n + i] - y[2 * n + i], r_);
-            v[j] = r_;
-        }
-        __syncthreads();
-        // (b) x~ = K^{-1} rhs   (a holds -K^{-1})
-        {
-            double p0 = 0.0, p1 = 0.0;
-            if (row < n) {
-                const double2 *v2 = reinterpret_cast<const double2 *>(v + col0);
-#pragma unroll
-                for (int jj = 0; jj < SEG; jj += 2) {
-                    const double2 vv = v2[jj >> 1];
-                    p0 = fma(a[jj], vv.x, p0);
-                    p1 = fma(a[jj + 1], vv.y, p1);
-                }
-            }
-            double part = p0 + p1;
-#pragma unroll
-            for (int o = 1; o < S; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            if (row < n && seg == 0) xt[row] = -part;
-        }
-        __syncthreads();
-        // (c) relaxation, projection, dual update
-        double rp = 0.0, nzt = 0.0, nz = 0.0;
-        if (tid < n) {
-            const int j = tid;
-            const double xtj = xt[j];
-            x[j] = alpha * xtj + (1.0 - alpha) * x[j];
-            {   // box row j
-                const double zr = alpha * xtj + (1.0 - alpha) * z[j];
-                const double zn = tg_clamp(zr + y[j] / rho[j], lb[j], ub[j]);
-                const double yn = y[j] + rho[j] * (zr - zn);
-                if (check) { dy[j] = yn - y[j]; zt[j] = xtj; rp = fabs(xtj - zn); nzt = fabs(xtj); nz = fabs(zn); }
-                y[j] = yn; z[j] = zn;
-            }
-            {   // rate row j
-                const int i = n + j;
-                const double ztl = xtj - ((j >= 2) ? xt[j - 2] : 0.0);
-                const double zr = alpha * ztl + (1.0 - alpha) * z[i];
-                const double zn = tg_clamp(zr + y[i] / rho[i], lb[i], ub[i]);
-                const double yn = y[i] + rho[i] * (zr - zn);
-                if (check) { dy[i] = yn - y[i]; zt[i] = ztl; rp = fmax(rp, fabs(ztl - zn)); nzt = fmax(nzt, fabs(ztl)); nz = fmax(nz, fabs(zn)); }
-                y[i] = yn; z[i] = zn;
-            }
-        }
-        for (int r_ = tid; r_ < ms; r_ += NT) {
-            const int i = 2 * n + r_;
-            double ztl = 0.0;
-            for (int j = 0; j < n; ++j) ztl = fma(Gs[r_ * NP + j], xt[j], ztl);
-            const double zr = alpha * ztl + (1.0 - alpha) * z[i];
-            const double zn = tg_clamp(zr + y[i] / rho[i], lb[i], ub[i]);
-            const double yn = y[i] + rho[i] * (zr - zn);
-            dy[i] = yn - y[i]; y[i] = yn; z[i] = zn; zt[i] = ztl;
-            rp = fmax(rp, fabs(ztl - zn)); nzt = fmax(nzt, fabs(ztl)); nz = fmax(nz, fabs(zn));
-        }
-        __syncthreads();
-        if (!check) continue;
-
-        // (d) residuals at (x~, z, y):  H x~ = rhs - sigma x~ - A'(rho .* z~)
-        double rd = 0.0, nh = 0.0, na = 0.0, natdy = 0.0, ndy = 0.0;
-        bool bad = false;
-        if (tid < n) {
-            const int j = tid;
-            double aty = y[j] + y[n + j], atr = rho[j] * zt[j] + rho[n + j] * zt[n + j], atd = dy[j] + dy[n + j];
-            if (j + 2 < n) { aty -= y[n + j + 2]; atr -= rho[n + j + 2] * zt[n + j + 2]; atd -= dy[n + j + 2]; }
-            for (int i = 0; i < ms; ++i) {
-                const double gij = Gs[i * NP + j];
-                aty = fma(gij, y[2 * n + i], aty);
-                atr = fma(gij, rho[2 * n + i] * zt[2 * n + i], atr);
-                atd = fma(gij, dy[2 * n + i], atd);
-            }
-            const double hx = v[j] - sigma * xt[j] - atr;
-            rd = fabs(hx + q[j] + aty); nh = fabs(hx); na = fabs(aty); natdy = fabs(atd);
-            bad = !(isfinite(hx) && isfinite(aty));
-        }
-        for (int i = tid; i < m; i += NT) ndy = fmax(ndy, fabs(dy[i]));
-        double vals[9] = {rp, nzt, nz, rd, nh, na, natdy, ndy, bad ? 1.0 : 0.0};
-        tg_block_reduce_max<9>(vals, red, tid, NT);
-        const double eps_p = c.eps_abs + c.eps_rel * fmax(vals[1], vals[2]);
-        const double eps_d = c.eps_abs + c.eps_rel * fmax(fmax(vals[4], vals[5]), nq);
-        if (vals[8] > 0.0 || !(vals[0] == vals[0]) || !(vals[3] == vals[3])) { status = TG_STATUS_NAN; break; }
-        if (vals[0] <= eps_p && vals[3] <= eps_d) { status = TG_STATUS_OPTIMAL; break; }
-        if (it == c.max_iter) {
-            if (vals[0] <= 10.0 * eps_p && vals[3] <= 10.0 * eps_d) status = TG_STATUS_OPTIMAL_INACCURATE;
-            break;
-        }
-        // primal infeasibility certificate (OSQP section 3.4): ||A'dy|| <= eps ||dy||, u'(dy)+ + l'(dy)- < -eps ||dy||,
-        // and no significant component of dy on an infinite side
-        if (vals[7] > c.eps_pinf && vals[6] <= c.eps_pinf * vals[7]) {
-            double cert = 0.0, infc = 0.0;
-            const double thr = c.eps_pinf * vals[7];
-            for (int i = tid; i < m; i += NT) {
-                const double d_ = dy[i];
-                if (d_ > 0.0) { if (ub[i] >= TG_INF) { if (d_ > thr) infc = 1.0; } else cert += ub[i] * d_; }
-                else if (d_ < 0.0) { if (lb[i] <= -TG_INF) { if (d_ < -thr) infc = 1.0; } else cert += lb[i] * d_; }
-            }
-            const double cert_sum = tg_block_reduce_sum(cert, red, tid, NT);
-            double iv[1] = {infc};
-            tg_block_reduce_max<1>(iv, red, tid, NT);
-            if (iv[0] == 0.0 && cert_sum < -thr) { status = TG_STATUS_INFEASIBLE; break; }
-        }
-        // adaptive rho (OSQP section 5.2), iteration-triggered so runs are reproducible
-        if (c.adaptive_rho && Hws && it >= c.adaptive_rho_min_iter) {
-            const double sp = fmax(vals[1], vals[2]), sd = fmax(fmax(vals[4], vals[5]), nq);
-            const double ratio = sqrt((vals[0] / (sp + 1e-10)) / (vals[3] / (sd + 1e-10) + 1e-10));
-            double ns_ = fmin(fmax(rho_scale * ratio, 1e-6), 1e6);
-            if (ns_ > rho_scale * c.adapt_tol || ns_ * c.adapt_tol < rho_scale) {
-                const double f_ = ns_ / rho_scale;
-                rho_scale = ns_;
-                for (int i = tid; i < m; i += NT) rho[i] *= f_;
-                if (row < n) {
-#pragma unroll
-                    for (int jj = 0; jj < SEG; ++jj) a[jj] = Hws[row * NP + col0 + jj];
-                }
-                __syncthreads();
-                tg_build_K<SEG>(c, L, sm, a, row, col0);
-                tg_sweep_invert<SEG, S>(c, L, sm, a, row, col0);
-            }
-        }
-    }
-    // objective at the returned point: c0 + q'x~ + 1/2 x~'H x~ with H x~ = rhs - sigma x~ - A'(rho .* z~)
     double obj = 0.0;
-    if (status == TG_STATUS_OPTIMAL || status == TG_STATUS_OPTIMAL_INACCURATE) {
-        double objp = 0.0;
-        if (tid < n) {
-            const int j = tid;
-            double atr = rho[j] * zt[j] + rho[n + j] * zt[n + j];
-            if (j + 2 < n) atr -= rho[n + j + 2] * zt[n + j + 2];
-            for (int i = 0; i < ms; ++i) atr = fma(Gs[i * NP + j], rho[2 * n + i] * zt[2 * n + i], atr);
-            const double hx = v[j] - sigma * xt[j] - atr;
-            objp = xt[j] * (0.5 * hx + q[j]);
+
+    if (x0_infeasible) {
+        status = TG_STATUS_INFEASIBLE;
+    } else if (TG_FAST_ADMM && ms == 0) {
+        // ---- fast path (input and rate rows only): x, z, y of "my" rows live in registers.  Thread j < n owns
+        // variable j, box row j, rate row j, and a redundant bit-identical copy of rate row j+2 (needed for A'),
+        // so one iteration is: mat-vec | barrier | local vector update + next rhs | barrier.
+        const int j = tid;
+        const bool own = (j < n), has2 = (j + 2 < n);
+        const int jc = own ? j : 0, j2 = has2 ? j + 2 : jc;
+        double xj = 0.0, zb = 0.0, yb = 0.0, zr = 0.0, yr = 0.0, zr2 = 0.0, yr2 = 0.0;
+        const double lbb = lb[jc], ubb = ub[jc], lrr = lb[n + jc], urr = ub[n + jc];
+        if (warm && own) {
+            xj = x[j];
+            const double xm = (j >= 2) ? x[j - 2] : 0.0, xp = has2 ? x[j + 2] : 0.0;
+            zb = tg_clamp(xj, lbb, ubb); yb = y[j];
+            zr = tg_clamp(xj - xm, lrr, urr); yr = y[n + j];
+            if (has2) { zr2 = tg_clamp(xp - xj, lrr, urr); yr2 = y[n + j + 2]; }
         }
-        obj = tg_block_reduce_sum(objp, red, tid, NT);
+        const double qj = q[jc];
+        double rhs = 0.0, hx_last = 0.0;
+        if (own) {
+            rhs = sigma * xj - qj + (rho[jc] * zb - yb) + (rho[n + jc] * zr - yr) - (has2 ? (rho[n + j2] * zr2 - yr2) : 0.0);
+            v[j] = rhs;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (it = 1; it <= c.max_iter; ++it) {
+            const bool check = (--until_check == 0) || (it == c.max_iter);
+            if (check) until_check = c.check_every;
+            tg_matvec<SEG, S>(a, v, xt, row, seg, col0, n);
+            __syncthreads();
+            double vals[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            double cert = 0.0;
+            if (own) {
+                const double rb = rho[j], rbi = rinv[j], rt = rho[n + j], rti = rinv[n + j];
+                const double rt2 = has2 ? rho[n + j2] : 0.0, rti2 = has2 ? rinv[n + j2] : 0.0;
+                const double xtj = xt[j], xtm = (j >= 2) ? xt[j - 2] : 0.0, xtp = xt[j + 2];   // xt is padded with zeros
+                xj = alpha * xtj + (1.0 - alpha) * xj;
+                // box row j
+                const double zrb = alpha * xtj + (1.0 - alpha) * zb;
+                const double znb = tg_clamp(zrb + yb * rbi, lbb, ubb);
+                const double dyb = rb * (zrb - znb);
+                yb += dyb; zb = znb;
+                // rate row j
+                const double ztl = xtj - xtm;
+                const double zrr = alpha * ztl + (1.0 - alpha) * zr;
+                const double znr = tg_clamp(zrr + yr * rti, lrr, urr);
+                const double dyr = rt * (zrr - znr);
+                yr += dyr; zr = znr;
+                // rate row j+2 (redundant copy, same arithmetic as its owner)
+                double ztl2 = 0.0, dyr2 = 0.0;
+                if (has2) {
+                    ztl2 = xtp - xtj;
+                    const double zrr2 = alpha * ztl2 + (1.0 - alpha) * zr2;
+                    const double znr2 = tg_clamp(zrr2 + yr2 * rti2, lrr, urr);
+                    dyr2 = rt2 * (zrr2 - znr2);
+                    yr2 += dyr2; zr2 = znr2;
+                }
+                if (check) {   // residuals at (x~, z, y):  H x~ = rhs - sigma x~ - A'(rho .* z~)
+                    const double aty = yb + yr - yr2;
+                    const double atr = rb * xtj + rt * ztl - rt2 * ztl2;
+                    const double hx = rhs - sigma * xtj - atr;
+                    hx_last = hx;
+                    vals[0] = fmax(fabs(xtj - zb), fabs(ztl - zr));
+                    vals[1] = fmax(fabs(xtj), fabs(ztl));
+                    vals[2] = fmax(fabs(zb), fabs(zr));
+                    vals[3] = fabs(hx + qj + aty); vals[4] = fabs(hx); vals[5] = fabs(aty);
+                    vals[6] = fabs(dyb + dyr - dyr2);
+                    vals[7] = fmax(fabs(dyb), fabs(dyr));
+                    vals[8] = (isfinite(hx) && isfinite(aty)) ? 0.0 : 1.0;
+                    cert = ((dyb > 0.0) ? ubb * dyb : lbb * dyb) + ((dyr > 0.0) ? urr * dyr : lrr * dyr);
+                }
+                rhs = sigma * xj - qj + (rb * zb - yb) + (rt * zr - yr) - (rt2 * zr2 - yr2);
+                v[j] = rhs;
+            }
+            if (check) {
+                tg_block_reduce_max<9>(vals, red, tid, NT);
+                const double eps_p = c.eps_abs + c.eps_rel * fmax(vals[1], vals[2]);
+                const double eps_d = c.eps_abs + c.eps_rel * fmax(fmax(vals[4], vals[5]), nq);
+                if (vals[8] > 0.0 || !(vals[0] == vals[0]) || !(vals[3] == vals[3])) { status = TG_STATUS_NAN; break; }
+                if (vals[0] <= eps_p && vals[3] <= eps_d) { status = TG_STATUS_OPTIMAL; break; }
+                if (it == c.max_iter) {
+                    if (vals[0] <= 10.0 * eps_p && vals[3] <= 10.0 * eps_d) status = TG_STATUS_OPTIMAL_INACCURATE;
+                    break;
+                }
+                // primal infeasibility certificate (OSQP section 3.4); all bounds of these rows are finite
+                if (vals[7] > c.eps_pinf && vals[6] <= c.eps_pinf * vals[7]) {
+                    const double cert_sum = tg_block_reduce_sum(cert, red, tid, NT);
+                    if (cert_sum < -c.eps_pinf * vals[7]) { status = TG_STATUS_INFEASIBLE; break; }
+                }
+                // adaptive rho (OSQP section 5.2), iteration-triggered so runs are reproducible
+                if (c.adaptive_rho && Hws && it >= c.adaptive_rho_min_iter) {
+                    const double sp = fmax(vals[1], vals[2]), sd = fmax(fmax(vals[4], vals[5]), nq);
+                    const double ratio = sqrt((vals[0] / (sp + 1e-10)) / (vals[3] / (sd + 1e-10) + 1e-10));
+                    const double ns_ = fmin(fmax(rho_scale * ratio, 1e-6), 1e6);
+                    if (ns_ > rho_scale * c.adapt_tol || ns_ * c.adapt_tol < rho_scale) {
+                        const double f_ = ns_ / rho_scale;
+                        rho_scale = ns_;
+                        __syncthreads();
+                        for (int i = tid; i < m; i += NT) { rho[i] *= f_; rinv[i] = 1.0 / rho[i]; }
+                        if (row < n) {
+                            const double2 *h2 = reinterpret_cast<const double2 *>(Hws + row * NP + col0);
+#pragma unroll
+                            for (int jj = 0; jj < SEG; jj += 2) { const double2 hv = h2[jj >> 1]; a[jj] = hv.x; a[jj + 1] = hv.y; }
+                        }
+                        __syncthreads();
+                        tg_build_K<SEG>(c, L, sm, a, row, col0);
+                        tg_sweep_invert<SEG, S>(c, L, sm, a, row, col0);
+                        if (own) {
+                            rhs = sigma * xj - qj + (rho[j] * zb - yb) + (rho[n + j] * zr - yr) - (has2 ? (rho[n + j2] * zr2 - yr2) : 0.0);
+                            v[j] = rhs;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (own) { y[j] = yb; y[n + j] = yr; }
+        // objective at the returned point: c0 + q'x~ + 1/2 x~'H x~
+        if (status == TG_STATUS_OPTIMAL || status == TG_STATUS_OPTIMAL_INACCURATE)
+            obj = tg_block_reduce_sum(own ? xt[j] * (0.5 * hx_last + qj) : 0.0, red, tid, NT);
+    } else {
+        // ---- general path (state-bound rows present): vectors in shared memory, three barriers per iteration
+        if (!warm) {
+            for (int i = tid; i < n; i += NT) x[i] = 0.0;
+            for (int i = tid; i < m; i += NT) { z[i] = 0.0; y[i] = 0.0; }
+        } else {
+            for (int j = tid; j < n; j += NT) {
+                z[j] = tg_clamp(x[j], lb[j], ub[j]);
+                const double r_ = x[j] - ((j >= 2) ? x[j - 2] : 0.0);
+                z[n + j] = tg_clamp(r_, lb[n + j], ub[n + j]);
+            }
+            for (int i = tid; i < ms; i += NT) {
+                double acc = 0.0;
+                for (int j = 0; j < n; ++j) acc = fma(Gs[i * NP + j], x[j], acc);
+                z[2 * n + i] = tg_clamp(acc, lb[2 * n + i], ub[2 * n + i]);
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (it = 1; it <= c.max_iter; ++it) {
+            const bool check = (--until_check == 0) || (it == c.max_iter);
+            if (check) until_check = c.check_every;
+            // (a) rhs = sigma x - q + A'(rho z - y)
+            if (tid < n) {
+                const int j = tid;
+                double r_ = sigma * x[j] - q[j] + (rho[j] * z[j] - y[j]) + (rho[n + j] * z[n + j] - y[n + j]);
+                if (j + 2 < n) r_ -= (rho[n + j + 2] * z[n + j + 2] - y[n + j + 2]);
+                for (int i = 0; i < ms; ++i) r_ = fma(Gs[i * NP + j], rho[2 * n + i] * z[2 * n + i] - y[2 * n + i], r_);
+                v[j] = r_;
+            }
+            __syncthreads();
+            // (b) x~ = K^{-1} rhs
+            tg_matvec<SEG, S>(a, v, xt, row, seg, col0, n);
+            __syncthreads();
+            // (c) relaxation, projection, dual update
+            double rp = 0.0, nzt = 0.0, nz = 0.0;
+            if (tid < n) {
+                const int j = tid;
+                const double xtj = xt[j];
+                x[j] = alpha * xtj + (1.0 - alpha) * x[j];
+                {   // box row j
+                    const double zr = alpha * xtj + (1.0 - alpha) * z[j];
+                    const double zn = tg_clamp(zr + y[j] * rinv[j], lb[j], ub[j]);
+                    const double yn = y[j] + rho[j] * (zr - zn);
+                    dy[j] = yn - y[j]; zt[j] = xtj; rp = fabs(xtj - zn); nzt = fabs(xtj); nz = fabs(zn);
+                    y[j] = yn; z[j] = zn;
+                }
+                {   // rate row j
+                    const int i = n + j;
+                    const double ztl = xtj - ((j >= 2) ? xt[j - 2] : 0.0);
+                    const double zr = alpha * ztl + (1.0 - alpha) * z[i];
+                    const double zn = tg_clamp(zr + y[i] * rinv[i], lb[i], ub[i]);
+                    const double yn = y[i] + rho[i] * (zr - zn);
+                    dy[i] = yn - y[i]; zt[i] = ztl; rp = fmax(rp, fabs(ztl - zn)); nzt = fmax(nzt, fabs(ztl)); nz = fmax(nz, fabs(zn));
+                    y[i] = yn; z[i] = zn;
+                }
+            }
+            for (int r_ = tid; r_ < ms; r_ += NT) {
+                const int i = 2 * n + r_;
+                double ztl = 0.0;
+                for (int j = 0; j < n; ++j) ztl = fma(Gs[r_ * NP + j], xt[j], ztl);
+                const double zr = alpha * ztl + (1.0 - alpha) * z[i];
+                const double zn = tg_clamp(zr + y[i] * rinv[i], lb[i], ub[i]);
+                const double yn = y[i] + rho[i] * (zr - zn);
+                dy[i] = yn - y[i]; y[i] = yn; z[i] = zn; zt[i] = ztl;
+                rp = fmax(rp, fabs(ztl - zn)); nzt = fmax(nzt, fabs(ztl)); nz = fmax(nz, fabs(zn));
+            }
+            __syncthreads();
+            if (!check) continue;
+
+            // (d) residuals at (x~, z, y):  H x~ = rhs - sigma x~ - A'(rho .* z~)
+            double rd = 0.0, nh = 0.0, na = 0.0, natdy = 0.0, ndy = 0.0;
+            bool bad = false;
+            if (tid < n) {
+                const int j = tid;
+                double aty = y[j] + y[n + j], atr = rho[j] * zt[j] + rho[n + j] * zt[n + j], atd = dy[j] + dy[n + j];
+                if (j + 2 < n) { aty -= y[n + j + 2]; atr -= rho[n + j + 2] * zt[n + j + 2]; atd -= dy[n + j + 2]; }
+                for (int i = 0; i < ms; ++i) {
+                    const double gij = Gs[i * NP + j];
+                    aty = fma(gij, y[2 * n + i], aty);
+                    atr = fma(gij, rho[2 * n + i] * zt[2 * n + i], atr);
+                    atd = fma(gij, dy[2 * n + i], atd);
+                }
+                const double hx = v[j] - sigma * xt[j] - atr;
+                rd = fabs(hx + q[j] + aty); nh = fabs(hx); na = fabs(aty); natdy = fabs(atd);
+                bad = !(isfinite(hx) && isfinite(aty));
+            }
+            for (int i = tid; i < m; i += NT) ndy = fmax(ndy, fabs(dy[i]));
+            double vals[9] = {rp, nzt, nz, rd, nh, na, natdy, ndy, bad ? 1.0 : 0.0};
+            tg_block_reduce_max<9>(vals, red, tid, NT);
+            const double eps_p = c.eps_abs + c.eps_rel * fmax(vals[1], vals[2]);
+            const double eps_d = c.eps_abs + c.eps_rel * fmax(fmax(vals[4], vals[5]), nq);
+            if (vals[8] > 0.0 || !(vals[0] == vals[0]) || !(vals[3] == vals[3])) { status = TG_STATUS_NAN; break; }
+            if (vals[0] <= eps_p && vals[3] <= eps_d) { status = TG_STATUS_OPTIMAL; break; }
+            if (it == c.max_iter) {
+                if (vals[0] <= 10.0 * eps_p && vals[3] <= 10.0 * eps_d) status = TG_STATUS_OPTIMAL_INACCURATE;
+                break;
+            }
+            // primal infeasibility certificate (OSQP section 3.4): ||A'dy|| <= eps ||dy||, u'(dy)+ + l'(dy)- < -eps ||dy||,
+            // and no significant component of dy on an infinite side
+            if (vals[7] > c.eps_pinf && vals[6] <= c.eps_pinf * vals[7]) {
+                double cert = 0.0, infc = 0.0;
+                const double thr = c.eps_pinf * vals[7];
+                for (int i = tid; i < m; i += NT) {
+                    const double d_ = dy[i];
+                    if (d_ > 0.0) { if (ub[i] >= TG_INF) { if (d_ > thr) infc = 1.0; } else cert += ub[i] * d_; }
+                    else if (d_ < 0.0) { if (lb[i] <= -TG_INF) { if (d_ < -thr) infc = 1.0; } else cert += lb[i] * d_; }
+                }
+                const double cert_sum = tg_block_reduce_sum(cert, red, tid, NT);
+                double iv[1] = {infc};
+                tg_block_reduce_max<1>(iv, red, tid, NT);
+                if (iv[0] == 0.0 && cert_sum < -thr) { status = TG_STATUS_INFEASIBLE; break; }
+            }
+            if (c.adaptive_rho && Hws && it >= c.adaptive_rho_min_iter) {
+                const double sp = fmax(vals[1], vals[2]), sd = fmax(fmax(vals[4], vals[5]), nq);
+                const double ratio = sqrt((vals[0] / (sp + 1e-10)) / (vals[3] / (sd + 1e-10) + 1e-10));
+                const double ns_ = fmin(fmax(rho_scale * ratio, 1e-6), 1e6);
+                if (ns_ > rho_scale * c.adapt_tol || ns_ * c.adapt_tol < rho_scale) {
+                    const double f_ = ns_ / rho_scale;
+                    rho_scale = ns_;
+                    for (int i = tid; i < m; i += NT) { rho[i] *= f_; rinv[i] = 1.0 / rho[i]; }
+                    if (row < n) {
+#pragma unroll
+                        for (int jj = 0; jj < SEG; ++jj) a[jj] = Hws[row * NP + col0 + jj];
+                    }
+                    __syncthreads();
+                    tg_build_K<SEG>(c, L, sm, a, row, col0);
+                    tg_sweep_invert<SEG, S>(c, L, sm, a, row, col0);
+                }
+            }
+        }
+        if (status == TG_STATUS_OPTIMAL || status == TG_STATUS_OPTIMAL_INACCURATE) {
+            double objp = 0.0;
+            if (tid < n) {
+                const int j = tid;
+                double atr = rho[j] * zt[j] + rho[n + j] * zt[n + j];
+                if (j + 2 < n) atr -= rho[n + j + 2] * zt[n + j + 2];
+                for (int i = 0; i < ms; ++i) atr = fma(Gs[i * NP + j], rho[2 * n + i] * zt[2 * n + i], atr);
+                const double hx = v[j] - sigma * xt[j] - atr;
+                objp = xt[j] * (0.5 * hx + q[j]);
+            }
+            obj = tg_block_reduce_sum(objp, red, tid, NT);
+        }
     }
+    TG_TICK(5);
     if (it > c.max_iter) it = c.max_iter;
     res.status = status;
     res.iters = it;
     res.objective = obj + misc[M_C0];
     if (tid == 0) misc[M_RHOSCALE] = rho_scale;
     __syncthreads();
+    TG_TICK(6);
     return res;
 }

@@ -22,6 +22,19 @@
 #ifndef TG_MINB_20_2
 #define TG_MINB_20_2 7
 #endif
+// (20,2): 96 threads x 7 CTAs/SM -> 96 registers (ptxas picks 80 from the launch bound alone, which leaves no room
+// to keep shared-memory loads in flight ahead of the DFMAs that consume them)
+#ifndef TG_REGS_20_2
+#define TG_REGS_20_2 96
+#endif
+#ifndef TG_USE_MAXNREG
+#define TG_USE_MAXNREG 0
+#endif
+#if TG_USE_MAXNREG
+#define TG_KATTR(SEG, S) __maxnreg__(((S) == 2 && (SEG) == 20) ? TG_REGS_20_2 : (65536 / (TG_NT(SEG, S) * TG_MINB(SEG, S)) > 255 ? 255 : (65536 / (TG_NT(SEG, S) * TG_MINB(SEG, S))) / 8 * 8))
+#else
+#define TG_KATTR(SEG, S) __launch_bounds__(TG_NT(SEG, S), TG_MINB(SEG, S))
+#endif
 #define TG_MINB(SEG, S) ((S) == 2 ? ((SEG) <= 12 ? 8 : TG_MINB_20_2) : ((SEG) == 16 ? 2 : 1))
 
 static thread_local std::string g_err;
@@ -45,7 +58,7 @@ struct StepArgs {
 };
 
 template <int SEG, int S>
-__global__ void __launch_bounds__(TG_NT(SEG, S), TG_MINB(SEG, S))
+__global__ void TG_KATTR(SEG, S)
 tg_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, const __grid_constant__ StepArgs a)
 {
     extern __shared__ __align__(16) double sm[];
@@ -83,7 +96,7 @@ tg_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Sme
         tap.u = a.u ? a.u + (size_t)b * m : nullptr;
         tap.Gs = a.Gs ? a.Gs + (size_t)b * c.ms * n : nullptr;
         tap.stop = a.stop;
-        const StepResult r = tg_mpc_step_body<SEG, S>(c, L, sm, warm, Hws, tap);
+        const StepResult r = tg_mpc_step_body<SEG, S>(c, L, sm, warm, Hws, tap, nullptr);
         if (a.stop) continue;
         const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);  // :261
         const double ud = sm[L.uprev], udel = sm[L.uprev + 1];
@@ -142,7 +155,7 @@ __device__ __forceinline__ void tg_ref_window_dev(const DevCfg &c, const SmemLay
         double y, dy;
         tg_path_at(sp, brk, coef, sm[L.Xr + k], y, dy);
         sm[L.Yr + k] = y;
-        sm[L.Pr + k] = atan(dy);   // :66
+        sm[L.Pr + k] = tg_atan(dy);   // :66
     }
     __syncthreads();
 }
@@ -160,44 +173,48 @@ struct LoopArgs {
 };
 
 template <int SEG, int S>
-__global__ void __launch_bounds__(TG_NT(SEG, S), TG_MINB(SEG, S))
+__global__ void TG_KATTR(SEG, S)
 tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, const __grid_constant__ LoopArgs a)
 {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, NT = blockDim.x;
-    const int N = c.N, n = c.n, m = c.m, ms = c.ms, ns = c.ns, T = a.T;
+    const int n = c.n, ms = c.ms, ns = c.ns, T = a.T;
     double *Hws = a.Hws ? a.Hws + (size_t)blockIdx.x * n * c.NP : nullptr;
-    StepTaps tap = {};
+    const StepTaps tap = {};
+    int *cnt = reinterpret_cast<int *>(sm + L.misc + M_CNT);                 // 6 status counters
+    long long *itsum = reinterpret_cast<long long *>(sm + L.misc + M_CNT + 3);
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         __syncthreads();
-        const tg_ref_spec sp = a.spec[b];
-        const unsigned long long seed = c.seed_base + (unsigned long long)(a.traj_id0 + b);
-        double *clean = a.clean + (size_t)b * (T + 1) * 6, *noisy = a.noisy + (size_t)b * (T + 1) * 6;
-        double *U = a.U + (size_t)b * T * 2;
-        if (tid < 6) { const double v_ = a.x0[6 * (size_t)b + tid]; sm[L.x0 + tid] = v_; clean[tid] = v_; }
+        if (tid < 12) sm[L.spec + tid] = reinterpret_cast<const double *>(a.spec + b)[tid];   // scenario -> shared memory
+        if (tid < 6) { const double v_ = a.x0[6 * (size_t)b + tid]; sm[L.x0 + tid] = v_; a.clean[(size_t)b * (T + 1) * 6 + tid] = v_; }
         if (tid < 2) sm[L.uprev + tid] = a.u0[2 * (size_t)b + tid];
-        if (tid >= 32 && tid < 35) {   // row 0 noise
-            const int pr = tid - 32;
-            uint32_t r[4];
-            tg_philox4x32_10(0u, (uint32_t)(pr >> 1), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-            double n0, n1;
-            tg_box_muller(r[(pr & 1) * 2], r[(pr & 1) * 2 + 1], n0, n1);
-            noisy[2 * pr] = a.x0[6 * (size_t)b + 2 * pr] + c.noise_std[2 * pr] * n0;
-            noisy[2 * pr + 1] = a.x0[6 * (size_t)b + 2 * pr + 1] + c.noise_std[2 * pr + 1] * n1;
-        }
-        int cnt[TG_NUM_STATUS];
-#pragma unroll
-        for (int i = 0; i < TG_NUM_STATUS; ++i) cnt[i] = 0;
-        long long itsum = 0;
+        if (tid < TG_NUM_STATUS) cnt[tid] = 0;
+        if (tid == 0) *itsum = 0;
         bool warm = false;
         __syncthreads();
-        for (int t = 0; t < T; ++t) {
-            tg_ref_window_dev(c, L, sm, sp, a.brk, a.coef, t);
-            const StepResult r = tg_mpc_step_body<SEG, S>(c, L, sm, warm, Hws, tap);
+#pragma unroll 1
+        for (int t = 0; t <= T; ++t) {
+            FusedCtx fx;
+            fx.brk = a.brk; fx.coef = a.coef;
+            fx.noisy_row = a.noisy + ((size_t)b * (T + 1) + t) * 6;
+            fx.seed = c.seed_base + (unsigned long long)(a.traj_id0 + b);
+            fx.t_index = t;
+            if (t == T) {   // last row: only its noisy copy remains to be written
+                const int nbase = (NT >= 96) ? 64 : 32;
+                if (tid >= nbase && tid < nbase + 3) {
+                    const int pr = tid - nbase;
+                    uint32_t r4[4];
+                    tg_philox4x32_10((uint32_t)t, (uint32_t)(pr >> 1), 0u, 0u, (uint32_t)fx.seed, (uint32_t)(fx.seed >> 32), r4);
+                    double n0, n1;
+                    tg_box_muller(r4[(pr & 1) * 2], r4[(pr & 1) * 2 + 1], n0, n1);
+                    fx.noisy_row[2 * pr] = sm[L.x0 + 2 * pr] + c.noise_std[2 * pr] * n0;
+                    fx.noisy_row[2 * pr + 1] = sm[L.x0 + 2 * pr + 1] + c.noise_std[2 * pr + 1] * n1;
+                }
+                break;
+            }
+            const StepResult r = tg_mpc_step_body<SEG, S>(c, L, sm, warm, Hws, tap, &fx);
             const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);
-#pragma unroll
-            for (int i = 0; i < TG_NUM_STATUS; ++i) cnt[i] += (r.status == i) ? 1 : 0;
-            itsum += r.iters;
+            if (tid == 0) { cnt[r.status] += 1; *itsum += r.iters; }
             // shifted warm start for the next step, in the next step's dU coordinates
             double nx = 0.0, nyb = 0.0, nyr = 0.0;
             if (tid < n) {
@@ -213,42 +230,33 @@ tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
                 for (int i = 0; i < 6; ++i) xs[i] = sm[L.x0 + i];
                 tg_plant_step_lanes(c, xs, u0, u1, tid);
                 if (tid == 0) {
+                    double *clean = a.clean + ((size_t)b * (T + 1) + t + 1) * 6;
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) { sm[L.misc + 8 + i] = xs[i]; clean[6 * (size_t)(t + 1) + i] = xs[i]; }
-                    U[2 * (size_t)t] = u0; U[2 * (size_t)t + 1] = u1;
-                    sm[L.misc + 14] = u0; sm[L.misc + 15] = u1;
+                    for (int i = 0; i < 6; ++i) { sm[L.misc + M_XNEXT + i] = xs[i]; clean[i] = xs[i]; }
+                    a.U[((size_t)b * T + t) * 2] = u0; a.U[((size_t)b * T + t) * 2 + 1] = u1;
+                    sm[L.misc + M_UCMD] = u0; sm[L.misc + M_UCMD + 1] = u1;
                 }
+            }
+            double tmp[4];   // ms <= 6 N <= 4 NT for every supported shape
+            if (ms > 0) {
+#pragma unroll
+                for (int r_ = 0; r_ < 4; ++r_) { const int i = tid + r_ * NT; tmp[r_] = (i + ns < ms) ? sm[L.y + 2 * n + i + ns] : 0.0; }
             }
             __syncthreads();
             // commit the new state / warm start
-            if (tid < 6) sm[L.x0 + tid] = sm[L.misc + 8 + tid];
-            if (tid < 2) sm[L.uprev + tid] = sm[L.misc + 14 + tid];
+            if (tid < 6) sm[L.x0 + tid] = sm[L.misc + M_XNEXT + tid];
+            if (tid < 2) sm[L.uprev + tid] = sm[L.misc + M_UCMD + tid];
             if (tid < n) { sm[L.x + tid] = nx; sm[L.y + tid] = nyb; sm[L.y + n + tid] = nyr; }
             if (ms > 0) {
-                double tmp[4];   // ms <= 6 N <= 4 NT for every supported shape
-#pragma unroll
-                for (int r_ = 0; r_ < 4; ++r_) { const int i = tid + r_ * NT; tmp[r_] = (i + ns < ms) ? sm[L.y + 2 * n + i + ns] : 0.0; }
-                __syncthreads();
 #pragma unroll
                 for (int r_ = 0; r_ < 4; ++r_) { const int i = tid + r_ * NT; if (i < ms) sm[L.y + 2 * n + i] = tmp[r_]; }
-            }
-            if (tid >= 32 && tid < 35) {   // sensor noise of row t+1 (generation_type2.py:190-200), never fed back
-                const int pr = tid - 32;
-                uint32_t r4[4];
-                tg_philox4x32_10((uint32_t)(t + 1), (uint32_t)(pr >> 1), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r4);
-                double n0, n1;
-                tg_box_muller(r4[(pr & 1) * 2], r4[(pr & 1) * 2 + 1], n0, n1);
-                noisy[6 * (size_t)(t + 1) + 2 * pr] = sm[L.misc + 8 + 2 * pr] + c.noise_std[2 * pr] * n0;
-                noisy[6 * (size_t)(t + 1) + 2 * pr + 1] = sm[L.misc + 8 + 2 * pr + 1] + c.noise_std[2 * pr + 1] * n1;
             }
             warm = ok && c.warm_start;
             __syncthreads();
         }
-        if (tid == 0) {
-            if (a.status_counts)
-                for (int i = 0; i < TG_NUM_STATUS; ++i) a.status_counts[(size_t)b * TG_NUM_STATUS + i] = cnt[i];
-            if (a.iters_total) a.iters_total[b] = itsum;
-        }
+        __syncthreads();
+        if (tid < TG_NUM_STATUS && a.status_counts) a.status_counts[(size_t)b * TG_NUM_STATUS + tid] = cnt[tid];
+        if (tid == 0 && a.iters_total) a.iters_total[b] = *itsum;
     }
 }
 
@@ -386,7 +394,7 @@ void tg_default_config(tg_config *c)
     c->du_lo[0] = -0.5; c->du_hi[0] = 0.5; c->du_lo[1] = -0.3; c->du_hi[1] = 0.3;
     for (int i = 0; i < 6; ++i) { c->x_lo[i] = -TG_INF; c->x_hi[i] = TG_INF; }
     c->rho = 0.1; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-5; c->eps_rel = 1e-5; c->eps_prim_inf = 1e-4;
-    c->adaptive_rho_tol = 5.0; c->max_iter = 4000; c->check_every = 10; c->adaptive_rho = 1; c->adaptive_rho_min_iter = 20;
+    c->adaptive_rho_tol = 5.0; c->max_iter = 4000; c->check_every = 5; c->adaptive_rho = 1; c->adaptive_rho_min_iter = 20;
     c->warm_start = 0; c->vref_advance = 0;
     const double sd[6] = {0.05, 0.05, 0.003, 0.010, 0.003, 0.030};
     memcpy(c->noise_std, sd, sizeof(sd));
@@ -494,6 +502,14 @@ int tg_info(tg_handle *h, int32_t *ctas_per_sm, int32_t *threads_per_cta, int32_
     if (num_sms) *num_sms = h->num_sms;
     return TG_OK;
 }
+#ifdef TG_PHASE_TIMING
+int tg_debug_phases(long long *out16, int reset)
+{
+    if (out16) CK(cudaMemcpyFromSymbol(out16, g_tg_phase, sizeof(long long) * 16));
+    if (reset) { long long z[16] = {0}; CK(cudaMemcpyToSymbol(g_tg_phase, z, sizeof(z))); }
+    return TG_OK;
+}
+#endif
 int tg_kernel_launches(tg_handle *h, int64_t *count) { if (!h || !count) return fail(TG_ERR_INVALID, "null argument"); *count = h->launches; return TG_OK; }
 
 static int launch_step(tg_handle *h, StepArgs &a)
