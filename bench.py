@@ -193,8 +193,14 @@ def run_gpu(args, rank, world, local_rank):
     x0, u0, sc = make_workload(B, traj_id0)
     brk, coef = sc.tables()
     kw = dict(GEN_KW)
+    so = {}
     if args.check_every:
-        kw["solver_opts"] = {"check_every": args.check_every}
+        so["check_every"] = args.check_every
+    for kv in args.solver_opt:
+        k, v = kv.split("=")
+        so[k] = float(v)
+    if so:
+        kw["solver_opts"] = so
     gen = tg.ClosedLoopGenerator(device=local_rank, **kw)
     stream = torch.cuda.Stream(device=dev)
     gen.set_stream(stream.cuda_stream)
@@ -369,6 +375,7 @@ def main():
     ap.add_argument("--horizon-steps", type=int, default=1200, help="closed-loop steps T per trajectory")
     ap.add_argument("--check-every", type=int, default=0, help="override the ADMM termination-check interval (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (development runs)")
+    ap.add_argument("--solver-opt", action="append", default=[], help="development: key=value override of a tg_config solver field")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -85,6 +85,13 @@ class ClosedLoopGenerator(BatchedMPC):
     ``noise_std`` and ``noise_seed_base`` (generation_type2.py:31-43,191)."""
 
     def __init__(self, device=0, warm_start=True, **kwargs):
+        if warm_start:
+            # a shift-warm-started ADMM starts next to its fixed point, where OSQP's default over-relaxation (1.6)
+            # only adds oscillation: alpha = 1.2 converges at the first check (5.3 vs 15 iterations per step on the
+            # config-2 workload, profiles/r01_solver_sweep.txt).  Explicit solver_opts win.
+            so = dict(kwargs.get("solver_opts") or {})
+            so.setdefault("alpha", 1.2)
+            kwargs["solver_opts"] = so
         super().__init__(device=device, warm_start=warm_start, **kwargs)
 
     def generate(self, x0, u0, scenarios, T, traj_id0=0):
