@@ -21,7 +21,8 @@ struct DevCfg {
     int ns;           // number of state components with a finite bound
     int sidx[6];      // their indices
     int ms, m;        // ns*N state rows, 4N + ms rows in total
-    int NP;           // padded matrix width S*SEG
+    int NP;           // padded matrix width TG*BS
+    int NPP;          // length of a block-padded vector, TG*BSP
     int max_iter, check_every, adaptive_rho, adaptive_rho_min_iter, warm_start, vref_advance;
     double Ts;
     double p[TG_NPARAMS];

@@ -12,32 +12,18 @@
 //       inverted in registers by n symmetric sweep steps; every iteration is one register mat-vec plus
 //       O(n) vector work on register-resident (x, z, y) with two barriers; REDUX reductions for the
 //       residual norms; adaptive rho refactors from a copy of H kept in an L2-resident per-CTA workspace.
-// Thread layout: thread t -> matrix row t / S, column segment t % S of width SEG (n <= S*SEG = NP).
+// Thread layout: the CTA is a TG x TG grid of threads; thread t owns the BS x BS block (t / TG, t % TG) of the
+// n x n matrix (n <= TG*BS = NP) in registers.  Square blocks keep every diagonal entry at a static register
+// (a[i][i] of a diagonal-block thread) and make a rank-1 update cost BS + BS operand loads for BS*BS FMAs.
+// Vectors that feed the blocks are stored block-padded (BSP = BS rounded up to even doubles per block) so that
+// every operand load is an aligned 128-bit shared-memory load.
 #pragma once
 #include "tg_device.cuh"
 
 #ifndef TG_KB
 #define TG_KB 4   // horizon stages condensed per barrier in K2
 #endif
-// register-resident ADMM vectors: fewer barriers but it does not fit the 80-register budget of 8 CTAs/SM
-// (measured 7.1 M vs 8.6 M steps/s with the shared-memory path), so it is off
-#ifndef TG_FAST_ADMM
-#define TG_FAST_ADMM 0
-#endif
 
-// Scheduling fence: an empty asm that "modifies" the listed values.  NVVM otherwise sinks each shared-memory load
-// next to its first use, and ptxas keeps that order, so every DFMA waits a full LDS latency (ncu: short_scoreboard
-// on 60 of 60 FMAs per stage).  Routing all loaded values through one asm forces the loads to be issued as a batch.
-#define TG_FENCE2(a, b) asm volatile("" : "+d"((a).x), "+d"((a).y), "+d"((b).x), "+d"((b).y))
-#define TG_FENCE6(a, b, c_, d_, e, f) asm volatile("" : "+d"((a).x), "+d"((a).y), "+d"((b).x), "+d"((b).y), "+d"((c_).x), "+d"((c_).y), \
-                                                   "+d"((d_).x), "+d"((d_).y), "+d"((e).x), "+d"((e).y), "+d"((f).x), "+d"((f).y))
-template <int NV>
-__device__ __forceinline__ void tg_fence_all(double2 (&vv)[NV])
-{
-    static_assert(NV % 2 == 0, "even count");
-#pragma unroll
-    for (int i = 0; i < NV; i += 2) TG_FENCE2(vv[i], vv[i + 1]);
-}
 
 // optional phase timing (development): -DTG_PHASE_TIMING accumulates clock64 deltas of CTA 0 / thread 0 per phase
 #ifdef TG_PHASE_TIMING
@@ -55,7 +41,7 @@ struct SmemLayout {
     int total;
 };
 
-__host__ __device__ inline SmemLayout tg_make_layout(int N, int ms, int NP)
+__host__ __device__ inline SmemLayout tg_make_layout(int N, int ms, int NP, int NPP)
 {
     SmemLayout L;
     int o = 0;
@@ -65,7 +51,7 @@ __host__ __device__ inline SmemLayout tg_make_layout(int N, int ms, int NP)
     L.xbar = take(6 * (N + 1)); L.lin = take(TG_LIN * N);
     L.Xr = take(N + 1); L.Yr = take(N + 1); L.Pr = take(N + 1); L.sn = take(N + 1); L.cs = take(N + 1); L.vref = take(N + 1);
     L.rr = take(3 * (N + 1));
-    L.w = take(2 * TG_KB * 3 * NP); L.v = take(2 * NP + 4);
+    L.w = take(2 * TG_KB * 3 * NPP); L.v = take(2 * (NPP + 2));
     L.q = take(n); L.x = take(n); L.xt = take(NP + 2); L.dH = take(n);
     L.z = take(m); L.y = take(m); L.l = take(m); L.u = take(m); L.rho = take(m + 2); L.rinv = take(m + 2); L.zt = take(m); L.dy = take(m);
     L.Gs = take(ms * NP);
@@ -142,108 +128,124 @@ __device__ __forceinline__ double tg_block_reduce_sum(double v, double *red, int
     return v;
 }
 
+template <int BS> struct TgPad { static constexpr int BSP = (BS + 1) & ~1; };
+
+// BS consecutive doubles of a block-padded vector (16-byte aligned block start) -> registers, 128-bit loads
+template <int BS>
+__device__ __forceinline__ void tg_ld_block(const double *p, double (&o)[BS])
+{
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int i = 0; i < (BS + 1) / 2; ++i) {
+        const double2 t = p2[i];
+        o[2 * i] = t.x;
+        if (2 * i + 1 < BS) o[2 * i + 1] = t.y;
+    }
+}
+
 // K = H + sigma I + A' diag(rho) A on the register tile; rho vectors are in shared memory.
-template <int SEG>
-__device__ __forceinline__ void tg_build_K(const DevCfg &c, const SmemLayout &L, const double *sm, double (&a)[SEG],
-                                           int row, int col0)
+template <int BS>
+__device__ __forceinline__ void tg_build_K(const DevCfg &c, const SmemLayout &L, const double *sm, double (&a)[BS][BS],
+                                           int R0, int C0)
 {
     const int n = c.n;
-    if (row >= n) return;
     const double *rho_b = sm + L.rho, *rho_r = sm + L.rho + n, *rho_s = sm + L.rho + 2 * n;
-    const double dg = c.sigma + rho_b[row] + rho_r[row] + ((row + 2 < n) ? rho_r[row + 2] : 0.0);
-    const double lo = -rho_r[row];
-    const double hi = (row + 2 < n) ? -rho_r[row + 2] : 0.0;
 #pragma unroll
-    for (int jj = 0; jj < SEG; ++jj) {
-        const int col = col0 + jj;
-        double add = 0.0;
-        if (col == row) add = dg;
-        else if (col == row - 2) add = lo;
-        else if (col == row + 2) add = hi;
-        a[jj] += add;
+    for (int i = 0; i < BS; ++i) {
+        const int row = R0 + i;
+        if (row >= n) continue;
+#pragma unroll
+        for (int j = 0; j < BS; ++j) {
+            const int col = C0 + j;
+            double add = 0.0;
+            if (col == row) add = c.sigma + rho_b[row] + rho_r[row] + ((row + 2 < n) ? rho_r[row + 2] : 0.0);
+            else if (col == row - 2) add = -rho_r[row];
+            else if (col == row + 2 && col < n) add = -rho_r[col];
+            a[i][j] += add;
+        }
     }
     const double *Gs = sm + L.Gs;
-    for (int i = 0; i < c.ms; ++i) {
-        const double gi = Gs[i * c.NP + row] * rho_s[i];
+    for (int s_ = 0; s_ < c.ms; ++s_) {
+        const double rs = rho_s[s_];
 #pragma unroll
-        for (int jj = 0; jj < SEG; ++jj) a[jj] = fma(gi, Gs[i * c.NP + col0 + jj], a[jj]);
+        for (int i = 0; i < BS; ++i) {
+            const double gi = Gs[s_ * c.NP + R0 + i] * rs;
+#pragma unroll
+            for (int j = 0; j < BS; ++j) a[i][j] = fma(gi, Gs[s_ * c.NP + C0 + j], a[i][j]);
+        }
     }
 }
 
 // In-register inversion of the SPD tile by n symmetric sweeps (SWP_k: a_kk <- -1/a_kk, a_ik <- a_ik/a_kk,
 // a_ij <- a_ij - a_ik a_kj / a_kk); on return a = -K^{-1}.
-// Every thread of a row keeps the diagonal entry of its row in the scalar `diag`, so that no register of the
-// tile is ever indexed dynamically: the row-k threads publish their segment (row k = column k by symmetry),
-// patch v[k] = a_kk - 1 (which turns the generic update of column k into a_ik/a_kk) and v[NP] = 1/a_kk; every
-// thread then does one fused update with w = a_ik/a_kk (w = 1 - 1/a_kk on the pivot row, which turns the
-// generic update of row k into a_kj/a_kk).  The tile's own copy of the diagonal is repaired once at the end.
-template <int SEG, int S>
-__device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayout &L, double *sm, double (&a)[SEG],
-                                                int row, int col0)
+// Step k: the TG threads of block-row k/BS publish row k (= column k by symmetry) as a block-padded vector with
+// v[k] = a_kk - 1 (which turns the generic update of column k into a_ik/a_kk) and the reciprocal pivot beside
+// it; after the barrier every thread loads BS row operands + BS column operands and does one fused rank-1
+// update with w_i = a_ik/a_kk (w = 1 - 1/a_kk on the pivot row, which turns the generic update of row k into
+// a_kj/a_kk); the pivot itself is repaired in place (static register: square blocks).  The pivot-row index
+// inside a block is a compile-time constant because the k loop is unrolled by BS.
+template <int BS, int TG>
+__device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayout &L, double *sm, double (&a)[BS][BS],
+                                                int br, int bc)
 {
-    const int n = c.n, NP = c.NP;
+    constexpr int BSP = TgPad<BS>::BSP;
+    const int n = c.n, NPP = c.NPP;
     double *vb = sm + L.v;
-    double diag = 0.0;
-#pragma unroll
-    for (int jj = 0; jj < SEG; ++jj)
-        if (col0 + jj == row) diag = a[jj];
-#pragma unroll
-    for (int o = 1; o < S; o <<= 1) diag += __shfl_xor_sync(0xffffffffu, diag, o);   // the other segments hold 0
+    const int nblk = (n + BS - 1) / BS;
 #pragma unroll 1
-    for (int k = 0; k < n; ++k) {
-        double *v = vb + (k & 1) * (NP + 2);
-        if (row == k) {
-            double2 *v2 = reinterpret_cast<double2 *>(v + col0);
+    for (int kb = 0; kb < nblk; ++kb) {
 #pragma unroll
-            for (int jj = 0; jj < SEG; jj += 2) v2[jj >> 1] = make_double2(a[jj], a[jj + 1]);
-            if (k >= col0 && k < col0 + SEG) { v[k] = diag - 1.0; v[NP] = 1.0 / diag; }
-        }
-        __syncthreads();
-        if (row < n) {
-            const double2 *v2 = reinterpret_cast<const double2 *>(v + col0);
-            double2 vv[SEG / 2];
+        for (int kr = 0; kr < BS; ++kr) {
+            const int k = kb * BS + kr;
+            if (k < n) {   // uniform
+                double *v = vb + (k & 1) * (NPP + 2);
+                if (br == kb) {
 #pragma unroll
-            for (int jj = 0; jj < SEG / 2; ++jj) vv[jj] = v2[jj];
-            tg_fence_all(vv);
-            const double p = v[NP];
-            const double vi = v[row];
-            const bool piv = (row == k);
-            const double wi = piv ? (1.0 - p) : vi * p;
+                    for (int j = 0; j < BS; ++j) v[bc * BSP + j] = a[kr][j];
+                    if (bc == kb) { const double piv = a[kr][kr]; v[bc * BSP + kr] = piv - 1.0; v[NPP] = 1.0 / piv; }
+                }
+                __syncthreads();
+                double vr[BS], vc[BS];
+                tg_ld_block<BS>(v + br * BSP, vr);
+                tg_ld_block<BS>(v + bc * BSP, vc);
+                const double p = v[NPP];
 #pragma unroll
-            for (int jj = 0; jj < SEG; jj += 2) {
-                a[jj] = fma(-wi, vv[jj >> 1].x, a[jj]);
-                a[jj + 1] = fma(-wi, vv[jj >> 1].y, a[jj + 1]);
+                for (int i = 0; i < BS; ++i) vr[i] *= p;
+                if (br == kb) vr[kr] = 1.0 - p;
+#pragma unroll
+                for (int i = 0; i < BS; ++i)
+#pragma unroll
+                    for (int j = 0; j < BS; ++j) a[i][j] = fma(-vr[i], vc[j], a[i][j]);
+                if (br == kb && bc == kb) a[kr][kr] = -p;
             }
-            diag = piv ? -p : fma(-wi, vi, diag);
         }
     }
-#pragma unroll
-    for (int jj = 0; jj < SEG; ++jj)
-        if (col0 + jj == row) a[jj] = diag;
     __syncthreads();
 }
 
-// x~ = K^{-1} v for the register tile (a = -K^{-1}); result to xt[row]
-template <int SEG, int S>
-__device__ __forceinline__ void tg_matvec(const double (&a)[SEG], const double *v, double *xt, int row, int seg, int col0, int n)
+// x~ = K^{-1} v for the register tile (a = -K^{-1}); v is block-padded, the result goes to xt (dense)
+template <int BS, int TG>
+__device__ __forceinline__ void tg_matvec(const double (&a)[BS][BS], const double *v, double *xt, int br, int bc, int n)
 {
-    double p0 = 0.0, p1 = 0.0;
-    if (row < n) {
-        const double2 *v2 = reinterpret_cast<const double2 *>(v + col0);
-        double2 vv[SEG / 2];
+    constexpr int BSP = TgPad<BS>::BSP;
+    double vc[BS], part[BS];
+    tg_ld_block<BS>(v + bc * BSP, vc);
 #pragma unroll
-        for (int jj = 0; jj < SEG / 2; ++jj) vv[jj] = v2[jj];
-        tg_fence_all(vv);
+    for (int i = 0; i < BS; ++i) {
+        double acc = 0.0;
 #pragma unroll
-        for (int jj = 0; jj < SEG; jj += 2) {
-            p0 = fma(a[jj], vv[jj >> 1].x, p0);
-            p1 = fma(a[jj + 1], vv[jj >> 1].y, p1);
-        }
+        for (int j = 0; j < BS; ++j) acc = fma(a[i][j], vc[j], acc);
+        part[i] = acc;
     }
-    double part = p0 + p1;
 #pragma unroll
-    for (int o = 1; o < S; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (row < n && seg == 0) xt[row] = -part;
+    for (int o = 1; o < TG; o <<= 1)
+#pragma unroll
+        for (int i = 0; i < BS; ++i) part[i] += __shfl_xor_sync(0xffffffffu, part[i], o);
+    if (bc == 0) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+            if (br * BS + i < n) xt[br * BS + i] = -part[i];
+    }
 }
 
 // reference window by ONE warp (MPC/main.py:87-90): vref over the horizon, xs by sequential accumulation
@@ -275,13 +277,15 @@ __device__ __forceinline__ void tg_ref_window_warp(const DevCfg &c, const SmemLa
 // builds it from the scenario in sm[L.spec] -- the reference window (Xr, Yr, Pr, vref); if `warm`, the
 // warm-start dU in sm[L.x] and duals in sm[L.y].  On exit sm[L.xt] holds dU* (x-tilde of the last check),
 // sm[L.y] the duals, and the result is returned to every thread.
-template <int SEG, int S>
+template <int BS, int TG>
 __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, double *sm, bool warm, double *Hws,
                                        const StepTaps &tap, const FusedCtx *fx)
 {
     const int tid = threadIdx.x, NT = blockDim.x;
-    const int N = c.N, n = c.n, NP = c.NP, ms = c.ms, m = c.m, ns = c.ns;
-    const int row = tid / S, seg = tid % S, col0 = seg * SEG;
+    constexpr int BSP = TgPad<BS>::BSP;
+    const int N = c.N, n = c.n, NP = c.NP, NPP = c.NPP, ms = c.ms, m = c.m, ns = c.ns;
+    const int br = tid / TG, bc = tid % TG, R0 = br * BS, C0 = bc * BS;   // blockDim.x == TG*TG
+    const int jpad = (tid / BS) * BSP + tid % BS;                          // block-padded position of vector entry `tid`
     StepResult res;
     res.status = TG_STATUS_NAN; res.iters = 0; res.objective = 0.0;
 
@@ -331,8 +335,8 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         }
     }
     // zero the W staging buffers and the mat-vec pads (threads beyond warp 0 get here first)
-    for (int i = tid; i < 2 * TG_KB * 3 * NP; i += NT) wbuf[i] = 0.0;
-    for (int i = tid; i < 2 * NP + 4; i += NT) sm[L.v + i] = 0.0;
+    for (int i = tid; i < 2 * TG_KB * 3 * NPP; i += NT) wbuf[i] = 0.0;
+    for (int i = tid; i < 2 * (NPP + 2); i += NT) sm[L.v + i] = 0.0;
     for (int i = tid; i < NP + 2; i += NT) xt[i] = 0.0;
     for (int i = tid; i < ms * (NP - n); i += NT) Gs[(i / (NP - n)) * NP + n + i % (NP - n)] = 0.0;  // pad columns
     __syncthreads();
@@ -379,23 +383,25 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     TG_TICK(1);
 
     // ---------------- K2: condensing.  Thread j < n owns column j of G_k (6 registers).
-    double a[SEG];
+    double a[BS][BS];
 #pragma unroll
-    for (int jj = 0; jj < SEG; ++jj) a[jj] = 0.0;
+    for (int i = 0; i < BS; ++i)
+#pragma unroll
+        for (int j = 0; j < BS; ++j) a[i][j] = 0.0;
     {
         double G0 = 0, G1 = 0, G2 = 0, G3 = 0, G4 = 0, G5 = 0, qacc = 0.0;
         const double tqc = 2.0 * c.q_c, tqp = 2.0 * c.q_phi, tqv = 2.0 * c.q_vx;
 #pragma unroll 1
         for (int k0 = 0; k0 < N; k0 += TG_KB) {   // TG_KB stages per barrier
             const int kb = (N - k0 < TG_KB) ? N - k0 : TG_KB;
-            double *wblk = wbuf + ((k0 / TG_KB) & 1) * TG_KB * 3 * NP;
+            double *wblk = wbuf + ((k0 / TG_KB) & 1) * TG_KB * 3 * NPP;
             if (tid < n) {
                 const int j = tid;
 #pragma unroll 1
                 for (int s_i = 0; s_i < kb; ++s_i) {
                     const int k = k0 + s_i;
                     const double *r = lin + TG_LIN * k;
-                    double *wb = wblk + s_i * 3 * NP;
+                    double *wb = wblk + s_i * 3 * NPP;
                     if (j < 2 * k) {  // G_{k+1} = A_k G_k
                         const double n0 = G0 + r[0] * G2 + r[1] * G3 + r[2] * G4;
                         const double n1 = G1 + r[3] * G2 + r[4] * G3 + r[5] * G4;
@@ -411,7 +417,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                     }
                     const int kk = k + 1;
                     const double wc = sn[kk] * G0 - cs[kk] * G1;
-                    wb[j] = wc; wb[NP + j] = G2; wb[2 * NP + j] = G3;
+                    wb[jpad] = wc; wb[NPP + jpad] = G2; wb[2 * NPP + jpad] = G3;
                     qacc += tqc * rr[3 * kk] * wc + tqp * rr[3 * kk + 1] * G2 + tqv * rr[3 * kk + 2] * G3;
                     for (int si = 0; si < ns; ++si) {
                         const int sx = c.sidx[si];
@@ -421,27 +427,35 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 }
             }
             __syncthreads();
-            if (row < n) {
 #pragma unroll 1
-                for (int s_i = 0; s_i < kb; ++s_i) {
-                    const int k = k0 + s_i;
-                    if (row < 2 * k + 2 && col0 < 2 * k + 2) {
-                        const double *wb = wblk + s_i * 3 * NP;
-                        const double w0 = wb[row] * tqc, w1 = wb[NP + row] * tqp, w2 = wb[2 * NP + row] * tqv;
-                        const double2 *wa = reinterpret_cast<const double2 *>(wb + col0);
-                        const double2 *wp = reinterpret_cast<const double2 *>(wb + NP + col0);
-                        const double2 *wv = reinterpret_cast<const double2 *>(wb + 2 * NP + col0);
+            for (int s_i = 0; s_i < kb; ++s_i) {
+                const int k = k0 + s_i;
+                if (R0 < 2 * k + 2 && C0 < 2 * k + 2) {   // rank-3 update of the block: 3 x (BS + BS) operands, 3 BS^2 FMAs
+                    const double *wb = wblk + s_i * 3 * NPP;
+                    double rw[BS], cw[BS];
+                    tg_ld_block<BS>(wb + br * BSP, rw);
+                    tg_ld_block<BS>(wb + bc * BSP, cw);
 #pragma unroll
-                        for (int cc = 0; cc < SEG; cc += 4) {   // 6 x 128-bit loads in flight, then 12 FMAs
-                            double2 xa0 = wa[cc >> 1], xa1 = wa[(cc >> 1) + 1];
-                            double2 xp0 = wp[cc >> 1], xp1 = wp[(cc >> 1) + 1];
-                            double2 xv0 = wv[cc >> 1], xv1 = wv[(cc >> 1) + 1];
-                            TG_FENCE6(xa0, xa1, xp0, xp1, xv0, xv1);
-                            a[cc] = fma(w2, xv0.x, fma(w1, xp0.x, fma(w0, xa0.x, a[cc])));
-                            a[cc + 1] = fma(w2, xv0.y, fma(w1, xp0.y, fma(w0, xa0.y, a[cc + 1])));
-                            a[cc + 2] = fma(w2, xv1.x, fma(w1, xp1.x, fma(w0, xa1.x, a[cc + 2])));
-                            a[cc + 3] = fma(w2, xv1.y, fma(w1, xp1.y, fma(w0, xa1.y, a[cc + 3])));
-                        }
+                    for (int i = 0; i < BS; ++i) {
+                        const double wi = rw[i] * tqc;
+#pragma unroll
+                        for (int j = 0; j < BS; ++j) a[i][j] = fma(wi, cw[j], a[i][j]);
+                    }
+                    tg_ld_block<BS>(wb + NPP + br * BSP, rw);
+                    tg_ld_block<BS>(wb + NPP + bc * BSP, cw);
+#pragma unroll
+                    for (int i = 0; i < BS; ++i) {
+                        const double wi = rw[i] * tqp;
+#pragma unroll
+                        for (int j = 0; j < BS; ++j) a[i][j] = fma(wi, cw[j], a[i][j]);
+                    }
+                    tg_ld_block<BS>(wb + 2 * NPP + br * BSP, rw);
+                    tg_ld_block<BS>(wb + 2 * NPP + bc * BSP, cw);
+#pragma unroll
+                    for (int i = 0; i < BS; ++i) {
+                        const double wi = rw[i] * tqv;
+#pragma unroll
+                        for (int j = 0; j < BS; ++j) a[i][j] = fma(wi, cw[j], a[i][j]);
                     }
                 }
             }
@@ -453,20 +467,20 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     }
     TG_TICK(2);
     // input and input-rate penalties (mpc_6stati.py:238-245), expressed in dU
-    if (row < n) {
-        const int kr = row >> 1, cr = row & 1;
 #pragma unroll
-        for (int jj = 0; jj < SEG; ++jj) {
-            const int col = col0 + jj;
-            const int kc = col >> 1, cc = col & 1;
+    for (int i = 0; i < BS; ++i) {
+        const int row = R0 + i, kr = row >> 1, cr = row & 1;
+#pragma unroll
+        for (int j = 0; j < BS; ++j) {
+            const int col = C0 + j, kc = col >> 1, cc = col & 1;
             double add = 0.0;
-            if (col < n) {
+            if (row < n && col < n) {
                 if (kc == kr) add = 2.0 * c.Rs[cr * 2 + cc] + ((kr < N - 1) ? 4.0 : 2.0) * c.Rds[cr * 2 + cc];
                 else if (kc == kr + 1 || kc + 1 == kr) add = -2.0 * c.Rds[cr * 2 + cc];
             }
-            a[jj] += add;
-            if (col == row) dH[row] = a[jj];
+            a[i][j] += add;
         }
+        if (br == bc && row < n) dH[row] = a[i][i];
     }
     __syncthreads();
 
@@ -497,15 +511,18 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         const double rs = rho_scale * ((mx > 1e-30) ? 1.0 / mx : 1.0);
         rho[2 * n + i] = rs; rinv[2 * n + i] = 1.0 / rs;
     }
-    if (tap.H && row < n) {
+    if (tap.H) {
 #pragma unroll
-        for (int jj = 0; jj < SEG; ++jj)
-            if (col0 + jj < n) tap.H[row * n + col0 + jj] = a[jj];
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int j = 0; j < BS; ++j)
+                if (R0 + i < n && C0 + j < n) tap.H[(R0 + i) * n + C0 + j] = a[i][j];
     }
-    if (Hws && row < n) {
-        double2 *h2 = reinterpret_cast<double2 *>(Hws + row * NP + col0);
+    if (Hws) {
 #pragma unroll
-        for (int jj = 0; jj < SEG; jj += 2) h2[jj >> 1] = make_double2(a[jj], a[jj + 1]);
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int j = 0; j < BS; ++j) Hws[(i * BS + j) * NT + tid] = a[i][j];   // coalesced across the CTA
     }
     double nq = 0.0;
     for (int i = tid; i < n; i += NT) nq = fmax(nq, fabs(q[i]));
@@ -523,8 +540,8 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     TG_TICK(3);
 
     // ---------------- K3: factor
-    tg_build_K<SEG>(c, L, sm, a, row, col0);
-    tg_sweep_invert<SEG, S>(c, L, sm, a, row, col0);
+    tg_build_K<BS>(c, L, sm, a, R0, C0);
+    tg_sweep_invert<BS, TG>(c, L, sm, a, br, bc);
     TG_TICK(4);
 
     // ---------------- ADMM
@@ -536,127 +553,9 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
 
     if (x0_infeasible) {
         status = TG_STATUS_INFEASIBLE;
-    } else if (TG_FAST_ADMM && ms == 0) {
-        // ---- fast path (input and rate rows only): x, z, y of "my" rows live in registers.  Thread j < n owns
-        // variable j, box row j, rate row j, and a redundant bit-identical copy of rate row j+2 (needed for A'),
-        // so one iteration is: mat-vec | barrier | local vector update + next rhs | barrier.
-        const int j = tid;
-        const bool own = (j < n), has2 = (j + 2 < n);
-        const int jc = own ? j : 0, j2 = has2 ? j + 2 : jc;
-        double xj = 0.0, zb = 0.0, yb = 0.0, zr = 0.0, yr = 0.0, zr2 = 0.0, yr2 = 0.0;
-        const double lbb = lb[jc], ubb = ub[jc], lrr = lb[n + jc], urr = ub[n + jc];
-        if (warm && own) {
-            xj = x[j];
-            const double xm = (j >= 2) ? x[j - 2] : 0.0, xp = has2 ? x[j + 2] : 0.0;
-            zb = tg_clamp(xj, lbb, ubb); yb = y[j];
-            zr = tg_clamp(xj - xm, lrr, urr); yr = y[n + j];
-            if (has2) { zr2 = tg_clamp(xp - xj, lrr, urr); yr2 = y[n + j + 2]; }
-        }
-        const double qj = q[jc];
-        double rhs = 0.0, hx_last = 0.0;
-        if (own) {
-            rhs = sigma * xj - qj + (rho[jc] * zb - yb) + (rho[n + jc] * zr - yr) - (has2 ? (rho[n + j2] * zr2 - yr2) : 0.0);
-            v[j] = rhs;
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (it = 1; it <= c.max_iter; ++it) {
-            const bool check = (--until_check == 0) || (it == c.max_iter);
-            if (check) until_check = c.check_every;
-            tg_matvec<SEG, S>(a, v, xt, row, seg, col0, n);
-            __syncthreads();
-            double vals[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            double cert = 0.0;
-            if (own) {
-                const double rb = rho[j], rbi = rinv[j], rt = rho[n + j], rti = rinv[n + j];
-                const double rt2 = has2 ? rho[n + j2] : 0.0, rti2 = has2 ? rinv[n + j2] : 0.0;
-                const double xtj = xt[j], xtm = (j >= 2) ? xt[j - 2] : 0.0, xtp = xt[j + 2];   // xt is padded with zeros
-                xj = alpha * xtj + (1.0 - alpha) * xj;
-                // box row j
-                const double zrb = alpha * xtj + (1.0 - alpha) * zb;
-                const double znb = tg_clamp(zrb + yb * rbi, lbb, ubb);
-                const double dyb = rb * (zrb - znb);
-                yb += dyb; zb = znb;
-                // rate row j
-                const double ztl = xtj - xtm;
-                const double zrr = alpha * ztl + (1.0 - alpha) * zr;
-                const double znr = tg_clamp(zrr + yr * rti, lrr, urr);
-                const double dyr = rt * (zrr - znr);
-                yr += dyr; zr = znr;
-                // rate row j+2 (redundant copy, same arithmetic as its owner)
-                double ztl2 = 0.0, dyr2 = 0.0;
-                if (has2) {
-                    ztl2 = xtp - xtj;
-                    const double zrr2 = alpha * ztl2 + (1.0 - alpha) * zr2;
-                    const double znr2 = tg_clamp(zrr2 + yr2 * rti2, lrr, urr);
-                    dyr2 = rt2 * (zrr2 - znr2);
-                    yr2 += dyr2; zr2 = znr2;
-                }
-                if (check) {   // residuals at (x~, z, y):  H x~ = rhs - sigma x~ - A'(rho .* z~)
-                    const double aty = yb + yr - yr2;
-                    const double atr = rb * xtj + rt * ztl - rt2 * ztl2;
-                    const double hx = rhs - sigma * xtj - atr;
-                    hx_last = hx;
-                    vals[0] = fmax(fabs(xtj - zb), fabs(ztl - zr));
-                    vals[1] = fmax(fabs(xtj), fabs(ztl));
-                    vals[2] = fmax(fabs(zb), fabs(zr));
-                    vals[3] = fabs(hx + qj + aty); vals[4] = fabs(hx); vals[5] = fabs(aty);
-                    vals[6] = fabs(dyb + dyr - dyr2);
-                    vals[7] = fmax(fabs(dyb), fabs(dyr));
-                    vals[8] = (isfinite(hx) && isfinite(aty)) ? 0.0 : 1.0;
-                    cert = ((dyb > 0.0) ? ubb * dyb : lbb * dyb) + ((dyr > 0.0) ? urr * dyr : lrr * dyr);
-                }
-                rhs = sigma * xj - qj + (rb * zb - yb) + (rt * zr - yr) - (rt2 * zr2 - yr2);
-                v[j] = rhs;
-            }
-            if (check) {
-                tg_block_reduce_max<9>(vals, red, tid, NT);
-                const double eps_p = c.eps_abs + c.eps_rel * fmax(vals[1], vals[2]);
-                const double eps_d = c.eps_abs + c.eps_rel * fmax(fmax(vals[4], vals[5]), nq);
-                if (vals[8] > 0.0 || !(vals[0] == vals[0]) || !(vals[3] == vals[3])) { status = TG_STATUS_NAN; break; }
-                if (vals[0] <= eps_p && vals[3] <= eps_d) { status = TG_STATUS_OPTIMAL; break; }
-                if (it == c.max_iter) {
-                    if (vals[0] <= 10.0 * eps_p && vals[3] <= 10.0 * eps_d) status = TG_STATUS_OPTIMAL_INACCURATE;
-                    break;
-                }
-                // primal infeasibility certificate (OSQP section 3.4); all bounds of these rows are finite
-                if (vals[7] > c.eps_pinf && vals[6] <= c.eps_pinf * vals[7]) {
-                    const double cert_sum = tg_block_reduce_sum(cert, red, tid, NT);
-                    if (cert_sum < -c.eps_pinf * vals[7]) { status = TG_STATUS_INFEASIBLE; break; }
-                }
-                // adaptive rho (OSQP section 5.2), iteration-triggered so runs are reproducible
-                if (c.adaptive_rho && Hws && it >= c.adaptive_rho_min_iter) {
-                    const double sp = fmax(vals[1], vals[2]), sd = fmax(fmax(vals[4], vals[5]), nq);
-                    const double ratio = sqrt((vals[0] / (sp + 1e-10)) / (vals[3] / (sd + 1e-10) + 1e-10));
-                    const double ns_ = fmin(fmax(rho_scale * ratio, 1e-6), 1e6);
-                    if (ns_ > rho_scale * c.adapt_tol || ns_ * c.adapt_tol < rho_scale) {
-                        const double f_ = ns_ / rho_scale;
-                        rho_scale = ns_;
-                        __syncthreads();
-                        for (int i = tid; i < m; i += NT) { rho[i] *= f_; rinv[i] = 1.0 / rho[i]; }
-                        if (row < n) {
-                            const double2 *h2 = reinterpret_cast<const double2 *>(Hws + row * NP + col0);
-#pragma unroll
-                            for (int jj = 0; jj < SEG; jj += 2) { const double2 hv = h2[jj >> 1]; a[jj] = hv.x; a[jj + 1] = hv.y; }
-                        }
-                        __syncthreads();
-                        tg_build_K<SEG>(c, L, sm, a, row, col0);
-                        tg_sweep_invert<SEG, S>(c, L, sm, a, row, col0);
-                        if (own) {
-                            rhs = sigma * xj - qj + (rho[j] * zb - yb) + (rho[n + j] * zr - yr) - (has2 ? (rho[n + j2] * zr2 - yr2) : 0.0);
-                            v[j] = rhs;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        if (own) { y[j] = yb; y[n + j] = yr; }
-        // objective at the returned point: c0 + q'x~ + 1/2 x~'H x~
-        if (status == TG_STATUS_OPTIMAL || status == TG_STATUS_OPTIMAL_INACCURATE)
-            obj = tg_block_reduce_sum(own ? xt[j] * (0.5 * hx_last + qj) : 0.0, red, tid, NT);
     } else {
-        // ---- general path (state-bound rows present): vectors in shared memory, three barriers per iteration
+        // ---- vectors in shared memory, three barriers per iteration (a register-resident variant with two barriers
+        // was measured slower at the register budget that keeps 8 CTAs per SM resident)
         if (!warm) {
             for (int i = tid; i < n; i += NT) x[i] = 0.0;
             for (int i = tid; i < m; i += NT) { z[i] = 0.0; y[i] = 0.0; }
@@ -683,11 +582,11 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 double r_ = sigma * x[j] - q[j] + (rho[j] * z[j] - y[j]) + (rho[n + j] * z[n + j] - y[n + j]);
                 if (j + 2 < n) r_ -= (rho[n + j + 2] * z[n + j + 2] - y[n + j + 2]);
                 for (int i = 0; i < ms; ++i) r_ = fma(Gs[i * NP + j], rho[2 * n + i] * z[2 * n + i] - y[2 * n + i], r_);
-                v[j] = r_;
+                v[jpad] = r_;
             }
             __syncthreads();
             // (b) x~ = K^{-1} rhs
-            tg_matvec<SEG, S>(a, v, xt, row, seg, col0, n);
+            tg_matvec<BS, TG>(a, v, xt, br, bc, n);
             __syncthreads();
             // (c) relaxation, projection, dual update
             double rp = 0.0, nzt = 0.0, nz = 0.0;
@@ -738,7 +637,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                     atr = fma(gij, rho[2 * n + i] * zt[2 * n + i], atr);
                     atd = fma(gij, dy[2 * n + i], atd);
                 }
-                const double hx = v[j] - sigma * xt[j] - atr;
+                const double hx = v[jpad] - sigma * xt[j] - atr;
                 rd = fabs(hx + q[j] + aty); nh = fabs(hx); na = fabs(aty); natdy = fabs(atd);
                 bad = !(isfinite(hx) && isfinite(aty));
             }
@@ -776,13 +675,13 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                     const double f_ = ns_ / rho_scale;
                     rho_scale = ns_;
                     for (int i = tid; i < m; i += NT) { rho[i] *= f_; rinv[i] = 1.0 / rho[i]; }
-                    if (row < n) {
 #pragma unroll
-                        for (int jj = 0; jj < SEG; ++jj) a[jj] = Hws[row * NP + col0 + jj];
-                    }
+                    for (int i = 0; i < BS; ++i)
+#pragma unroll
+                        for (int j = 0; j < BS; ++j) a[i][j] = Hws[(i * BS + j) * NT + tid];
                     __syncthreads();
-                    tg_build_K<SEG>(c, L, sm, a, row, col0);
-                    tg_sweep_invert<SEG, S>(c, L, sm, a, row, col0);
+                    tg_build_K<BS>(c, L, sm, a, R0, C0);
+                    tg_sweep_invert<BS, TG>(c, L, sm, a, br, bc);
                 }
             }
         }
@@ -793,7 +692,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 double atr = rho[j] * zt[j] + rho[n + j] * zt[n + j];
                 if (j + 2 < n) atr -= rho[n + j + 2] * zt[n + j + 2];
                 for (int i = 0; i < ms; ++i) atr = fma(Gs[i * NP + j], rho[2 * n + i] * zt[2 * n + i], atr);
-                const double hx = v[j] - sigma * xt[j] - atr;
+                const double hx = v[jpad] - sigma * xt[j] - atr;
                 objp = xt[j] * (0.5 * hx + q[j]);
             }
             obj = tg_block_reduce_sum(objp, red, tid, NT);

@@ -17,26 +17,6 @@
 
 #include "tg_solver.cuh"
 
-// threads per CTA of a shape and the residency the register allocator must allow (<= 65536 / (NT * MINB) registers)
-#define TG_NT(SEG, S) ((((SEG) * (S) * (S) + 31) / 32) * 32 < 64 ? 64 : (((SEG) * (S) * (S) + 31) / 32) * 32)
-#ifndef TG_MINB_20_2
-#define TG_MINB_20_2 7
-#endif
-// (20,2): 96 threads x 7 CTAs/SM -> 96 registers (ptxas picks 80 from the launch bound alone, which leaves no room
-// to keep shared-memory loads in flight ahead of the DFMAs that consume them)
-#ifndef TG_REGS_20_2
-#define TG_REGS_20_2 96
-#endif
-#ifndef TG_USE_MAXNREG
-#define TG_USE_MAXNREG 0
-#endif
-#if TG_USE_MAXNREG
-#define TG_KATTR(SEG, S) __maxnreg__(((S) == 2 && (SEG) == 20) ? TG_REGS_20_2 : (65536 / (TG_NT(SEG, S) * TG_MINB(SEG, S)) > 255 ? 255 : (65536 / (TG_NT(SEG, S) * TG_MINB(SEG, S))) / 8 * 8))
-#else
-#define TG_KATTR(SEG, S) __launch_bounds__(TG_NT(SEG, S), TG_MINB(SEG, S))
-#endif
-#define TG_MINB(SEG, S) ((S) == 2 ? ((SEG) <= 12 ? 8 : TG_MINB_20_2) : ((SEG) == 16 ? 2 : 1))
-
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #define CK(call)                                                                                       \
@@ -44,6 +24,13 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
         cudaError_t e_ = (call);                                                                       \
         if (e_ != cudaSuccess) return fail(TG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
+
+// A shape is (BS, TG): TG x TG threads, each owning a BS x BS block of the n x n matrix (n <= BS*TG).
+// TG_MINB = resident CTAs per SM the register allocator must allow (65536 / (threads * MINB) registers/thread):
+// 64 threads x 8 CTAs -> 128 registers for N <= 20, which leaves room to keep operand loads in flight.
+#define TG_NT(BS, TG) ((TG) * (TG))
+#define TG_MINB(BS, TG) ((TG) == 8 ? 8 : ((BS) <= 5 ? 2 : 1))
+#define TG_KATTR(BS, TG) __launch_bounds__(TG_NT(BS, TG), TG_MINB(BS, TG))
 
 // ------------------------------------------------------------------------------------------------ kernels
 struct StepArgs {
@@ -57,14 +44,14 @@ struct StepArgs {
     double *Hws;                          // per-CTA H workspace, may be null
 };
 
-template <int SEG, int S>
-__global__ void TG_KATTR(SEG, S)
+template <int BS, int TG>
+__global__ void TG_KATTR(BS, TG)
 tg_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, const __grid_constant__ StepArgs a)
 {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, NT = blockDim.x;
     const int N = c.N, n = c.n, m = c.m;
-    double *Hws = a.Hws ? a.Hws + (size_t)blockIdx.x * n * c.NP : nullptr;
+    double *Hws = a.Hws ? a.Hws + (size_t)blockIdx.x * c.NP * c.NP : nullptr;
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         __syncthreads();
         if (tid < 6) sm[L.x0 + tid] = a.x0[6 * (size_t)b + tid];
@@ -96,7 +83,7 @@ tg_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Sme
         tap.u = a.u ? a.u + (size_t)b * m : nullptr;
         tap.Gs = a.Gs ? a.Gs + (size_t)b * c.ms * n : nullptr;
         tap.stop = a.stop;
-        const StepResult r = tg_mpc_step_body<SEG, S>(c, L, sm, warm, Hws, tap, nullptr);
+        const StepResult r = tg_mpc_step_body<BS, TG>(c, L, sm, warm, Hws, tap, nullptr);
         if (a.stop) continue;
         const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);  // :261
         const double ud = sm[L.uprev], udel = sm[L.uprev + 1];
@@ -172,14 +159,14 @@ struct LoopArgs {
     double *Hws;
 };
 
-template <int SEG, int S>
-__global__ void TG_KATTR(SEG, S)
+template <int BS, int TG>
+__global__ void TG_KATTR(BS, TG)
 tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, const __grid_constant__ LoopArgs a)
 {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, NT = blockDim.x;
     const int n = c.n, ms = c.ms, ns = c.ns, T = a.T;
-    double *Hws = a.Hws ? a.Hws + (size_t)blockIdx.x * n * c.NP : nullptr;
+    double *Hws = a.Hws ? a.Hws + (size_t)blockIdx.x * c.NP * c.NP : nullptr;
     const StepTaps tap = {};
     int *cnt = reinterpret_cast<int *>(sm + L.misc + M_CNT);                 // 6 status counters
     long long *itsum = reinterpret_cast<long long *>(sm + L.misc + M_CNT + 3);
@@ -212,7 +199,7 @@ tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
                 }
                 break;
             }
-            const StepResult r = tg_mpc_step_body<SEG, S>(c, L, sm, warm, Hws, tap, &fx);
+            const StepResult r = tg_mpc_step_body<BS, TG>(c, L, sm, warm, Hws, tap, &fx);
             const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);
             if (tid == 0) { cnt[r.status] += 1; *itsum += r.iters; }
             // shifted warm start for the next step, in the next step's dU coordinates
@@ -326,20 +313,20 @@ __global__ void tg_fma_peak_kernel(T *out, int iters)
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-struct Shape { int SEG, S, NP, NT; };
+struct Shape { int BS, TG, NP, NPP, NT; };
 
 static bool pick_shape(int N, Shape &s)
 {
     const int n = 2 * N;
-    if (n <= 24) { s.SEG = 12; s.S = 2; }
-    else if (n <= 40) { s.SEG = 20; s.S = 2; }
-    else if (n <= 64) { s.SEG = 16; s.S = 4; }
-    else if (n <= 80) { s.SEG = 20; s.S = 4; }
-    else if (n <= 112) { s.SEG = 28; s.S = 4; }
+    if (n <= 24) { s.BS = 3; s.TG = 8; }
+    else if (n <= 40) { s.BS = 5; s.TG = 8; }
+    else if (n <= 64) { s.BS = 4; s.TG = 16; }
+    else if (n <= 80) { s.BS = 5; s.TG = 16; }
+    else if (n <= 112) { s.BS = 7; s.TG = 16; }
     else return false;
-    s.NP = s.SEG * s.S;
-    s.NT = ((n * s.S + 31) / 32) * 32;
-    if (s.NT < 64) s.NT = 64;
+    s.NP = s.BS * s.TG;
+    s.NPP = ((s.BS + 1) & ~1) * s.TG;
+    s.NT = s.TG * s.TG;
     return true;
 }
 
@@ -363,14 +350,14 @@ struct tg_handle {
 template <typename F>
 static int dispatch_shape(const Shape &s, F &&f)
 {
-#ifndef TG_ONLY_SHAPE_20_2
-    if (s.SEG == 12 && s.S == 2) return f(std::integral_constant<int, 12>(), std::integral_constant<int, 2>());
+#ifndef TG_ONLY_SHAPE_5_8
+    if (s.BS == 3 && s.TG == 8) return f(std::integral_constant<int, 3>(), std::integral_constant<int, 8>());
 #endif
-    if (s.SEG == 20 && s.S == 2) return f(std::integral_constant<int, 20>(), std::integral_constant<int, 2>());
-#ifndef TG_ONLY_SHAPE_20_2
-    if (s.SEG == 16 && s.S == 4) return f(std::integral_constant<int, 16>(), std::integral_constant<int, 4>());
-    if (s.SEG == 20 && s.S == 4) return f(std::integral_constant<int, 20>(), std::integral_constant<int, 4>());
-    if (s.SEG == 28 && s.S == 4) return f(std::integral_constant<int, 28>(), std::integral_constant<int, 4>());
+    if (s.BS == 5 && s.TG == 8) return f(std::integral_constant<int, 5>(), std::integral_constant<int, 8>());
+#ifndef TG_ONLY_SHAPE_5_8
+    if (s.BS == 4 && s.TG == 16) return f(std::integral_constant<int, 4>(), std::integral_constant<int, 16>());
+    if (s.BS == 5 && s.TG == 16) return f(std::integral_constant<int, 5>(), std::integral_constant<int, 16>());
+    if (s.BS == 7 && s.TG == 16) return f(std::integral_constant<int, 7>(), std::integral_constant<int, 16>());
 #endif
     return fail(TG_ERR_UNSUPPORTED, "no kernel shape for this horizon");
 }
@@ -430,7 +417,7 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     d.ns = 0;
     for (int i = 0; i < 6; ++i)
         if (cfg->x_lo[i] > -TG_INF || cfg->x_hi[i] < TG_INF) d.sidx[d.ns++] = i;
-    d.ms = d.ns * d.N; d.m = 4 * d.N + d.ms; d.NP = sh.NP;
+    d.ms = d.ns * d.N; d.m = 4 * d.N + d.ms; d.NP = sh.NP; d.NPP = sh.NPP;
     d.max_iter = cfg->max_iter; d.check_every = cfg->check_every; d.adaptive_rho = cfg->adaptive_rho;
     d.adaptive_rho_min_iter = cfg->adaptive_rho_min_iter; d.warm_start = cfg->warm_start; d.vref_advance = cfg->vref_advance;
     d.Ts = cfg->Ts;
@@ -448,16 +435,16 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     memcpy(d.noise_std, cfg->noise_std, 48);
     d.seed_base = cfg->noise_seed_base;
 
-    h->L = tg_make_layout(d.N, d.ms, d.NP);
+    h->L = tg_make_layout(d.N, d.ms, d.NP, d.NPP);
     h->smem_bytes = (size_t)h->L.total * sizeof(double);
     if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
         delete h;
         return fail(TG_ERR_UNSUPPORTED, "state-bound rows x horizon exceed the 227 KB shared memory of one CTA");
     }
     int occ = 0;
-    int rc = dispatch_shape(sh, [&](auto SEG, auto S) -> int {
-        auto k1 = tg_mpc_step_kernel<decltype(SEG)::value, decltype(S)::value>;
-        auto k2 = tg_closed_loop_kernel<decltype(SEG)::value, decltype(S)::value>;
+    int rc = dispatch_shape(sh, [&](auto BS_, auto TG_) -> int {
+        auto k1 = tg_mpc_step_kernel<decltype(BS_)::value, decltype(TG_)::value>;
+        auto k2 = tg_closed_loop_kernel<decltype(BS_)::value, decltype(TG_)::value>;
         CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
         CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
         CK(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -473,7 +460,7 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     h->grid_cap = occ * h->num_sms;
     CK(cudaFuncSetAttribute(tg_ref_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     if (d.adaptive_rho) {
-        h->Hws_elems = (size_t)h->grid_cap * d.n * d.NP;
+        h->Hws_elems = (size_t)h->grid_cap * d.NP * d.NP;
         CK(cudaMalloc(&h->Hws, h->Hws_elems * sizeof(double)));
     }
     h->stream = 0;
@@ -518,8 +505,8 @@ static int launch_step(tg_handle *h, StepArgs &a)
     CK(cudaSetDevice(h->device));
     a.Hws = h->Hws;
     const int grid = a.B < h->grid_cap ? a.B : h->grid_cap;
-    int rc = dispatch_shape(h->shape, [&](auto SEG, auto S) -> int {
-        tg_mpc_step_kernel<decltype(SEG)::value, decltype(S)::value><<<grid, h->shape.NT, h->smem_bytes, h->stream>>>(h->dc, h->L, a);
+    int rc = dispatch_shape(h->shape, [&](auto BS_, auto TG_) -> int {
+        tg_mpc_step_kernel<decltype(BS_)::value, decltype(TG_)::value><<<grid, h->shape.NT, h->smem_bytes, h->stream>>>(h->dc, h->L, a);
         return TG_OK;
     });
     if (rc != TG_OK) return rc;
@@ -606,8 +593,8 @@ int tg_closed_loop(tg_handle *h, int B, int T, const double *x0, const double *u
     a.clean = clean; a.noisy = noisy; a.U = U; a.status_counts = status_counts; a.iters_total = (long long *)iters_total;
     a.Hws = h->Hws;
     const int grid = B < h->grid_cap ? B : h->grid_cap;
-    int rc = dispatch_shape(h->shape, [&](auto SEG, auto S) -> int {
-        tg_closed_loop_kernel<decltype(SEG)::value, decltype(S)::value><<<grid, h->shape.NT, h->smem_bytes, h->stream>>>(h->dc, h->L, a);
+    int rc = dispatch_shape(h->shape, [&](auto BS_, auto TG_) -> int {
+        tg_closed_loop_kernel<decltype(BS_)::value, decltype(TG_)::value><<<grid, h->shape.NT, h->smem_bytes, h->stream>>>(h->dc, h->L, a);
         return TG_OK;
     });
     if (rc != TG_OK) return rc;
