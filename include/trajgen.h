@@ -40,7 +40,7 @@ extern "C" {
 #define TG_STATUS_INFEASIBLE 2         /* "infeasible"  -> u_cmd = u_prev */
 #define TG_STATUS_UNBOUNDED 3          /* "unbounded"   (cannot occur: R > 0; kept for the mapping) */
 #define TG_STATUS_USER_LIMIT 4         /* "user_limit"  (max_iter reached) -> u_cmd = u_prev */
-#define TG_STATUS_NAN 5                /* "Solver Error: ..." (non-finite data) -> u_cmd = u_prev */
+#define TG_STATUS_NAN 5                /* "Solver Error: ..." (non-finite data or diverged iteration) -> u_cmd = u_prev */
 #define TG_NUM_STATUS 6
 
 /* dynamics variants */
@@ -85,6 +85,7 @@ typedef struct tg_config {
     double x_lo[6], x_hi[6];   /* :139-140; <= -TG_INF / >= TG_INF = absent */
     /* ADMM (OSQP-style) settings */
     double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, adaptive_rho_tol;
+    double alpha_warm;       /* relaxation of the first 4 check intervals of a WARM-started solve (then alpha); <= 0 = alpha */
     int32_t max_iter, check_every, adaptive_rho, adaptive_rho_min_iter;
     int32_t warm_start;      /* closed loop: shift-warm-start across steps; step API: keep per-problem state */
     int32_t vref_advance;    /* 0 = the reference's behaviour (window never advances, MPC/main.py:87) */
@@ -166,6 +167,14 @@ int tg_closed_loop_host(tg_handle *h, int B, int T, const double *x0, const doub
 int tg_plant_rollout(tg_handle *h, int B, int T, const double *x0, const double *U, double *X);
 int tg_sensor_noise(tg_handle *h, int64_t traj_id0, int n_traj, int n_rows, double *out);
 int tg_philox_u32(tg_handle *h, uint64_t seed, uint32_t first, uint32_t block, int n, uint32_t *out);
+
+/* host-side dataset writer -- replaces the DataFrame concat + to_csv of generation_type1.py:315-339 /
+ * generation_type2.py:202-218,309-322.  HOST pointers clean[B][T+1][6], noisy[B][T+1][6], U[B][T][2]; writes the
+ * clean file (with phi) and the noisy file (without), byte-identical to pandas' output for the same numbers
+ * (shortest-repr floats, empty d/delta on each trajectory's last row, ids traj_id0 + i).  append != 0 continues an
+ * existing file without a header (sharded / chunked generation).  Either path may be NULL.  n_threads <= 0 = all cores. */
+int tg_write_csv(const char *clean_path, const char *noisy_path, int B, int T, double Ts, int64_t traj_id0,
+                 const double *clean, const double *noisy, const double *U, int append, int n_threads);
 
 /* measured FMA peak of this GPU (roofline denominator): TFLOP/s for dtype 0 = fp64, 1 = fp32 */
 int tg_fma_peak(tg_handle *h, int dtype, double *tflops);

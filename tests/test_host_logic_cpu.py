@@ -26,9 +26,31 @@ def _reference_rows():
 def test_csv_writer_is_byte_identical_to_the_reference(tmp_path):
     """feeding the reference's own rows through the package's writer reproduces the reference's files."""
     res = _reference_rows()
-    tg.write_csv(res, 0.01, tmp_path / "c.csv", tmp_path / "n.csv")
-    assert open(tmp_path / "c.csv").read() == open(os.path.join(GOLDEN, "reference_gen2_clean.csv")).read()
-    assert open(tmp_path / "n.csv").read() == open(os.path.join(GOLDEN, "reference_gen2_noisy.csv")).read()
+    for engine in ("native", "pandas"):
+        tg.write_csv(res, 0.01, tmp_path / "c.csv", tmp_path / "n.csv", engine=engine)
+        assert open(tmp_path / "c.csv").read() == open(os.path.join(GOLDEN, "reference_gen2_clean.csv")).read()
+        assert open(tmp_path / "n.csv").read() == open(os.path.join(GOLDEN, "reference_gen2_noisy.csv")).read()
+    # appending shard by shard gives the same bytes as one call
+    first = {k: v[:2] for k, v in res.items()}
+    rest = {k: v[2:] for k, v in res.items()}
+    tg.write_csv(first, 0.01, tmp_path / "c2.csv", tmp_path / "n2.csv")
+    tg.write_csv(rest, 0.01, tmp_path / "c2.csv", tmp_path / "n2.csv", traj_id0=2, append=True)
+    assert open(tmp_path / "c2.csv").read() == open(os.path.join(GOLDEN, "reference_gen2_clean.csv")).read()
+
+
+def test_native_float_formatting_equals_python_repr(tmp_path):
+    """the native writer's float text is Python's repr for awkward values (exponent thresholds, subnormals, -0.0)."""
+    vals = np.array([0.0, -0.0, 1.0, -1.5, 0.1, 1e-4, 1e-5, 1.5e-7, 123456789.125, 1e15, 1e16, 1.2345678901234567e17, 5e-324,
+                     1.7976931348623157e308, 0.30000000000000004, 2.0 ** -20, 1 / 3, 12345678901234567.0, np.inf, -np.inf])
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([vals, rng.normal(size=200) * 10.0 ** rng.integers(-12, 12, 200)])
+    B = len(vals)
+    clean = np.zeros((B, 1, 6)); clean[:, 0, 0] = vals
+    res = {"clean": clean, "noisy": clean.copy(), "U": np.zeros((B, 0, 2))}
+    tg.write_csv(res, 0.5, tmp_path / "c.csv", tmp_path / "n.csv")
+    lines = open(tmp_path / "c.csv").read().splitlines()[1:]
+    for v, ln in zip(vals, lines):
+        assert ln.split(",")[1] == repr(float(v)), (v, ln)
     c, n = tg.to_frames(res, 0.01)
     assert list(c.columns) == tg.CLEAN_COLS and list(n.columns) == tg.NOISY_COLS
     last = c[c["trajectory_id"] == 2].iloc[-1]

@@ -19,7 +19,7 @@ TG_NUM_STATUS = 6
 PARAM_ORDER = ("Cm1", "Cm2", "Cr0", "Cr2", "Br", "Cr", "Dr", "Bf", "Cf", "Df", "m", "Iz", "lf", "lr", "g",
                "maxAlpha", "vx_zero")
 # mpc_step's status strings (MPC/mpc_6stati.py:257-262)
-STATUS_STRINGS = ("optimal", "optimal_inaccurate", "infeasible", "unbounded", "user_limit", "Solver Error: NonFinite")
+STATUS_STRINGS = ("optimal", "optimal_inaccurate", "infeasible", "unbounded", "user_limit", "Solver Error: NumericalFailure")
 ACCEPTED = (0, 1)
 
 d, i32, i64, u64, vp = ctypes.c_double, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_void_p
@@ -33,7 +33,7 @@ class TgConfig(ctypes.Structure):
         ("u_lo", d * 2), ("u_hi", d * 2), ("du_lo", d * 2), ("du_hi", d * 2),
         ("x_lo", d * 6), ("x_hi", d * 6),
         ("rho", d), ("sigma", d), ("alpha", d), ("eps_abs", d), ("eps_rel", d), ("eps_prim_inf", d),
-        ("adaptive_rho_tol", d),
+        ("adaptive_rho_tol", d), ("alpha_warm", d),
         ("max_iter", i32), ("check_every", i32), ("adaptive_rho", i32), ("adaptive_rho_min_iter", i32),
         ("warm_start", i32), ("vref_advance", i32),
         ("noise_std", d * 6), ("noise_seed_base", u64),
@@ -49,7 +49,7 @@ assert REF_SPEC_DTYPE.itemsize == 96
 EXPORTS = (
     "tg_last_error", "tg_version", "tg_default_config", "tg_create", "tg_destroy", "tg_set_stream", "tg_synchronize",
     "tg_kernel_launches", "tg_info", "tg_linearize", "tg_assemble", "tg_mpc_step", "tg_mpc_step_host", "tg_ref_window",
-    "tg_closed_loop", "tg_closed_loop_host", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
+    "tg_closed_loop", "tg_closed_loop_host", "tg_write_csv", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
     "tg_device_count", "tg_malloc", "tg_free", "tg_memcpy_h2d", "tg_memcpy_d2h", "tg_malloc_host", "tg_free_host",
 )
 
@@ -63,11 +63,12 @@ class TrajgenError(RuntimeError):
 def build(verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> libtrajgen.so (in-tree)."""
     src = os.path.join(CSRC, "trajgen.cu")
-    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    src_csv = os.path.join(CSRC, "tg_csv.cpp")
+    deps = [src, src_csv] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     deps.append(os.path.join(_HERE, "..", "include", "trajgen.h"))
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(p) for p in deps):
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, src]
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, src, src_csv]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
@@ -98,6 +99,7 @@ def load():
     L.tg_ref_window.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp, vp]
     L.tg_closed_loop.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     L.tg_closed_loop_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, vp]
+    L.tg_write_csv.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, d, i64, vp, vp, vp, ctypes.c_int, ctypes.c_int]
     L.tg_plant_rollout.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
     L.tg_sensor_noise.argtypes = [vp, i64, ctypes.c_int, ctypes.c_int, vp]
     L.tg_philox_u32.argtypes = [vp, u64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, vp]

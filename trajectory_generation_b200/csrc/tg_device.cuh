@@ -29,7 +29,7 @@ struct DevCfg {
     double q_c, q_phi, q_vx;
     double Rs[4], Rds[4];  // symmetric parts
     double u_lo[2], u_hi[2], du_lo[2], du_hi[2], x_lo[6], x_hi[6];
-    double rho, sigma, alpha, eps_abs, eps_rel, eps_pinf, adapt_tol;
+    double rho, sigma, alpha, alpha_warm, eps_abs, eps_rel, eps_pinf, adapt_tol;
     double noise_std[6];
     unsigned long long seed_base;
 };

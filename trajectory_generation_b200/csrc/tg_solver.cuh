@@ -23,6 +23,7 @@
 #ifndef TG_KB
 #define TG_KB 4   // horizon stages condensed per barrier in K2
 #endif
+#define TG_WARM_RESTART_ITER 300
 
 
 // optional phase timing (development): -DTG_PHASE_TIMING accumulates clock64 deltas of CTA 0 / thread 0 per phase
@@ -37,7 +38,7 @@ __device__ long long g_tg_phase[16];
 
 // shared-memory layout (offsets in doubles), identical on host and device
 struct SmemLayout {
-    int x0, uprev, misc, spec, xbar, lin, Xr, Yr, Pr, sn, cs, vref, rr, w, v, q, x, xt, dH, z, y, l, u, rho, rinv, zt, dy, Gs, red;
+    int x0, uprev, misc, spec, xbar, lin, Xr, Yr, Pr, sn, cs, vref, rr, w, v, dsc, q, x, xt, dH, z, y, l, u, rho, rinv, zt, dy, Gs, red;
     int total;
 };
 
@@ -51,7 +52,7 @@ __host__ __device__ inline SmemLayout tg_make_layout(int N, int ms, int NP, int 
     L.xbar = take(6 * (N + 1)); L.lin = take(TG_LIN * N);
     L.Xr = take(N + 1); L.Yr = take(N + 1); L.Pr = take(N + 1); L.sn = take(N + 1); L.cs = take(N + 1); L.vref = take(N + 1);
     L.rr = take(3 * (N + 1));
-    L.w = take(2 * TG_KB * 3 * NPP); L.v = take(2 * (NPP + 2));
+    L.w = take(2 * TG_KB * 3 * NPP); L.v = take(2 * (NPP + 2)); L.dsc = take(NPP);
     L.q = take(n); L.x = take(n); L.xt = take(NP + 2); L.dH = take(n);
     L.z = take(m); L.y = take(m); L.l = take(m); L.u = take(m); L.rho = take(m + 2); L.rinv = take(m + 2); L.zt = take(m); L.dy = take(m);
     L.Gs = take(ms * NP);
@@ -192,6 +193,24 @@ __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayou
     const int n = c.n, NPP = c.NPP;
     double *vb = sm + L.v;
     const int nblk = (n + BS - 1) / BS;
+    // Jacobi scaling K^ = D K D, D = diag(K)^-1/2: the unpivoted sweep is only as accurate as cond(K) allows, and K
+    // inherits the variable scaling of H (duty vs steering, growth of the Euler-discretised dynamics along the
+    // horizon: cond(K) up to 3e11 at N = 50, 1.6e3 after scaling -- without it the ADMM map diverged on hard cases).
+    double *dsc = sm + L.dsc;
+    if (br == bc) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i) dsc[br * BSP + i] = (br * BS + i < n) ? rsqrt(a[i][i]) : 0.0;
+    }
+    __syncthreads();
+    {
+        double dr[BS], dc[BS];
+        tg_ld_block<BS>(dsc + br * BSP, dr);
+        tg_ld_block<BS>(dsc + bc * BSP, dc);
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int j = 0; j < BS; ++j) a[i][j] *= dr[i] * dc[j];
+    }
 #pragma unroll 1
     for (int kb = 0; kb < nblk; ++kb) {
 #pragma unroll
@@ -219,6 +238,15 @@ __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayou
                 if (br == kb && bc == kb) a[kr][kr] = -p;
             }
         }
+    }
+    {   // K^{-1} = D K^^{-1} D
+        double dr[BS], dc[BS];
+        tg_ld_block<BS>(dsc + br * BSP, dr);
+        tg_ld_block<BS>(dsc + bc * BSP, dc);
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int j = 0; j < BS; ++j) a[i][j] *= dr[i] * dc[j];
     }
     __syncthreads();
 }
@@ -545,7 +573,11 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     TG_TICK(4);
 
     // ---------------- ADMM
-    const double alpha = c.alpha, sigma = c.sigma;
+    // a shift-warm-started solve starts next to its fixed point, where OSQP's over-relaxation (1.6) only adds
+    // oscillation: use alpha_warm for the first 4 check intervals, then fall back to alpha (hard problems want 1.6)
+    double alpha = warm ? c.alpha_warm : c.alpha;
+    const int alpha_switch = 4 * c.check_every;
+    const double sigma = c.sigma;
     double *v = sm + L.v;  // mat-vec input (first NP entries)
     int status = TG_STATUS_USER_LIMIT, it = 0;
     int until_check = c.check_every;
@@ -576,6 +608,14 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         for (it = 1; it <= c.max_iter; ++it) {
             const bool check = (--until_check == 0) || (it == c.max_iter);
             if (check) until_check = c.check_every;
+            if (it == alpha_switch + 1) alpha = c.alpha;
+            if (warm && it == TG_WARM_RESTART_ITER) {
+                // a warm start that has not converged by now is a bad start (e.g. the active set changed: cold solves of
+                // such steps take ~1e3 iterations where the shifted start ran into max_iter): restart from zero
+                for (int i = tid; i < n; i += NT) x[i] = 0.0;
+                for (int i = tid; i < m; i += NT) { z[i] = 0.0; y[i] = 0.0; }
+                __syncthreads();
+            }
             // (a) rhs = sigma x - q + A'(rho z - y)
             if (tid < n) {
                 const int j = tid;
@@ -652,20 +692,26 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 if (vals[0] <= 10.0 * eps_p && vals[3] <= 10.0 * eps_d) status = TG_STATUS_OPTIMAL_INACCURATE;
                 break;
             }
-            // primal infeasibility certificate (OSQP section 3.4): ||A'dy|| <= eps ||dy||, u'(dy)+ + l'(dy)- < -eps ||dy||,
-            // and no significant component of dy on an infinite side
-            if (vals[7] > c.eps_pinf && vals[6] <= c.eps_pinf * vals[7]) {
-                double cert = 0.0, infc = 0.0;
-                const double thr = c.eps_pinf * vals[7];
+            // numerical failure guard: a convergent iteration stays near the input box; with relative tolerances a
+            // diverging one would otherwise "converge" (eps_rel * 1e58 > any residual)
+            if (vals[1] > 1e8) { status = TG_STATUS_NAN; break; }
+            // primal infeasibility certificate.  OSQP (section 3.4) asks ||A'dy|| <= eps ||dy|| and u'(dy)+ + l'(dy)- < 0;
+            // on this problem family ||A'dy|| / ||dy|| plateaus near 5e-3 for thousands of iterations.  Every dU_j is
+            // boxed by its input row (|dU_j| <= r_j = max(|l_j|, |u_j|)), which gives a RIGOROUS, scale-free test:
+            // for any feasible dU, -sum_j |A'dy|_j r_j <= dy'A dU <= u'(dy)+ + l'(dy)-, so
+            //      u'(dy)+ + l'(dy)- + sum_j |(A'dy)_j| r_j < 0   proves infeasibility
+            // (it fired after 40-200 iterations where the OSQP form had not after 20000).
+            {
+                double part = 0.0;
+                const double thr = 1e-9 * vals[7];
                 for (int i = tid; i < m; i += NT) {
                     const double d_ = dy[i];
-                    if (d_ > 0.0) { if (ub[i] >= TG_INF) { if (d_ > thr) infc = 1.0; } else cert += ub[i] * d_; }
-                    else if (d_ < 0.0) { if (lb[i] <= -TG_INF) { if (d_ < -thr) infc = 1.0; } else cert += lb[i] * d_; }
+                    if (d_ > thr) part += (ub[i] >= TG_INF) ? 1e300 : ub[i] * d_;
+                    else if (d_ < -thr) part += (lb[i] <= -TG_INF) ? 1e300 : lb[i] * d_;
                 }
-                const double cert_sum = tg_block_reduce_sum(cert, red, tid, NT);
-                double iv[1] = {infc};
-                tg_block_reduce_max<1>(iv, red, tid, NT);
-                if (iv[0] == 0.0 && cert_sum < -thr) { status = TG_STATUS_INFEASIBLE; break; }
+                if (tid < n) part += natdy * fmax(fabs(lb[tid]), fabs(ub[tid]));
+                const double cert_sum = tg_block_reduce_sum(part, red, tid, NT);
+                if (vals[7] > 1e-30 && cert_sum < -1e-9 * vals[7]) { status = TG_STATUS_INFEASIBLE; break; }
             }
             if (c.adaptive_rho && Hws && it >= c.adaptive_rho_min_iter) {
                 const double sp = fmax(vals[1], vals[2]), sd = fmax(fmax(vals[4], vals[5]), nq);

@@ -381,7 +381,7 @@ void tg_default_config(tg_config *c)
     c->du_lo[0] = -0.5; c->du_hi[0] = 0.5; c->du_lo[1] = -0.3; c->du_hi[1] = 0.3;
     for (int i = 0; i < 6; ++i) { c->x_lo[i] = -TG_INF; c->x_hi[i] = TG_INF; }
     c->rho = 0.1; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-5; c->eps_rel = 1e-5; c->eps_prim_inf = 1e-4;
-    c->adaptive_rho_tol = 5.0; c->max_iter = 4000; c->check_every = 5; c->adaptive_rho = 1; c->adaptive_rho_min_iter = 20;
+    c->adaptive_rho_tol = 5.0; c->alpha_warm = 1.2; c->max_iter = 10000; c->check_every = 5; c->adaptive_rho = 1; c->adaptive_rho_min_iter = 20;
     c->warm_start = 0; c->vref_advance = 0;
     const double sd[6] = {0.05, 0.05, 0.003, 0.010, 0.003, 0.030};
     memcpy(c->noise_std, sd, sizeof(sd));
@@ -430,7 +430,8 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
         }
     memcpy(d.u_lo, cfg->u_lo, 16); memcpy(d.u_hi, cfg->u_hi, 16); memcpy(d.du_lo, cfg->du_lo, 16); memcpy(d.du_hi, cfg->du_hi, 16);
     memcpy(d.x_lo, cfg->x_lo, 48); memcpy(d.x_hi, cfg->x_hi, 48);
-    d.rho = cfg->rho; d.sigma = cfg->sigma; d.alpha = cfg->alpha; d.eps_abs = cfg->eps_abs; d.eps_rel = cfg->eps_rel;
+    d.rho = cfg->rho; d.sigma = cfg->sigma; d.alpha = cfg->alpha;
+    d.alpha_warm = (cfg->alpha_warm > 0.0 && cfg->alpha_warm < 2.0) ? cfg->alpha_warm : cfg->alpha; d.eps_abs = cfg->eps_abs; d.eps_rel = cfg->eps_rel;
     d.eps_pinf = cfg->eps_prim_inf; d.adapt_tol = cfg->adaptive_rho_tol > 1.0 ? cfg->adaptive_rho_tol : 5.0;
     memcpy(d.noise_std, cfg->noise_std, 48);
     d.seed_base = cfg->noise_seed_base;

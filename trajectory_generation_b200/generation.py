@@ -85,13 +85,6 @@ class ClosedLoopGenerator(BatchedMPC):
     ``noise_std`` and ``noise_seed_base`` (generation_type2.py:31-43,191)."""
 
     def __init__(self, device=0, warm_start=True, **kwargs):
-        if warm_start:
-            # a shift-warm-started ADMM starts next to its fixed point, where OSQP's default over-relaxation (1.6)
-            # only adds oscillation: alpha = 1.2 converges at the first check (5.3 vs 15 iterations per step on the
-            # config-2 workload, profiles/r01_solver_sweep.txt).  Explicit solver_opts win.
-            so = dict(kwargs.get("solver_opts") or {})
-            so.setdefault("alpha", 1.2)
-            kwargs["solver_opts"] = so
         super().__init__(device=device, warm_start=warm_start, **kwargs)
 
     def generate(self, x0, u0, scenarios, T, traj_id0=0):
@@ -182,11 +175,22 @@ def to_frames(result, Ts, traj_id0=0):
     return frames[0][CLEAN_COLS], frames[1][NOISY_COLS]
 
 
-def write_csv(result, Ts, clean_path, noisy_path, traj_id0=0):
-    """clean/noisy CSV files exactly as generation_type2.py:319-322 writes them (pandas to_csv, index=False)."""
-    c, n = to_frames(result, Ts, traj_id0)
-    c.to_csv(clean_path, index=False)
-    n.to_csv(noisy_path, index=False)
+def write_csv(result, Ts, clean_path, noisy_path, traj_id0=0, append=False, engine="native", n_threads=0):
+    """clean/noisy CSV files exactly as generation_type2.py:319-322 writes them.  engine="native": the library's
+    multi-threaded writer (tg_write_csv, byte-identical to pandas for the same numbers); engine="pandas":
+    DataFrame.to_csv(index=False) as the reference does."""
+    if engine == "pandas":
+        c, n = to_frames(result, Ts, traj_id0)
+        c.to_csv(clean_path, index=False, mode="a" if append else "w", header=not append)
+        n.to_csv(noisy_path, index=False, mode="a" if append else "w", header=not append)
+        return
+    clean = np.ascontiguousarray(result["clean"], dtype=np.float64)
+    noisy = np.ascontiguousarray(result["noisy"], dtype=np.float64)
+    U = np.ascontiguousarray(result["U"], dtype=np.float64)
+    B, T1, _ = clean.shape
+    _lib.check(_lib.load().tg_write_csv(str(clean_path).encode(), str(noisy_path).encode(), B, T1 - 1, float(Ts), int(traj_id0),
+                                        _lib.ptr(clean), _lib.ptr(noisy), _lib.ptr(U) if U.size else None, int(bool(append)),
+                                        int(n_threads)))
 
 
 def to_loader_tensors(result, T_steps):
