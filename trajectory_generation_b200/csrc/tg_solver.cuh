@@ -151,6 +151,8 @@ __device__ __forceinline__ void tg_build_K(const DevCfg &c, const SmemLayout &L,
 {
     const int n = c.n;
     const double *rho_b = sm + L.rho, *rho_r = sm + L.rho + n, *rho_s = sm + L.rho + 2 * n;
+    const int dblk = R0 - C0;
+    if (dblk <= BS && dblk >= -BS)   // sigma I + box + rate terms live within two entries of the diagonal
 #pragma unroll
     for (int i = 0; i < BS; ++i) {
         const int row = R0 + i;
@@ -211,6 +213,10 @@ __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayou
 #pragma unroll
             for (int j = 0; j < BS; ++j) a[i][j] *= dr[i] * dc[j];
     }
+    // the reciprocal of pivot k+1 is started as soon as that entry has been updated in step k, so its latency
+    // (MUFU.RCP64H + Newton steps, ~100 cycles) overlaps the rest of the rank-1 update instead of sitting in
+    // front of every barrier
+    double rp_next = (br == 0 && bc == 0) ? 1.0 / a[0][0] : 0.0;
 #pragma unroll 1
     for (int kb = 0; kb < nblk; ++kb) {
 #pragma unroll
@@ -221,7 +227,7 @@ __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayou
                 if (br == kb) {
 #pragma unroll
                     for (int j = 0; j < BS; ++j) v[bc * BSP + j] = a[kr][j];
-                    if (bc == kb) { const double piv = a[kr][kr]; v[bc * BSP + kr] = piv - 1.0; v[NPP] = 1.0 / piv; }
+                    if (bc == kb) { v[bc * BSP + kr] = a[kr][kr] - 1.0; v[NPP] = rp_next; }
                 }
                 __syncthreads();
                 double vr[BS], vc[BS];
@@ -231,6 +237,11 @@ __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayou
 #pragma unroll
                 for (int i = 0; i < BS; ++i) vr[i] *= p;
                 if (br == kb) vr[kr] = 1.0 - p;
+                {   // next pivot first
+                    const int nx = (kr + 1 < BS) ? kr + 1 : 0;   // static after unrolling
+                    const int nb = (kr + 1 < BS) ? kb : kb + 1;
+                    if (br == nb && bc == nb) rp_next = 1.0 / fma(-vr[nx], vc[nx], a[nx][nx]);
+                }
 #pragma unroll
                 for (int i = 0; i < BS; ++i)
 #pragma unroll
@@ -428,7 +439,12 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
 #pragma unroll 1
                 for (int s_i = 0; s_i < kb; ++s_i) {
                     const int k = k0 + s_i;
-                    const double *r = lin + TG_LIN * k;
+                    double r[22];   // stage record: all 128-bit loads issued before the FMAs that use them
+                    {
+                        const double2 *r2 = reinterpret_cast<const double2 *>(lin + TG_LIN * k);
+#pragma unroll
+                        for (int i = 0; i < 11; ++i) { const double2 t = r2[i]; r[2 * i] = t.x; r[2 * i + 1] = t.y; }
+                    }
                     double *wb = wblk + s_i * 3 * NPP;
                     if (j < 2 * k) {  // G_{k+1} = A_k G_k
                         const double n0 = G0 + r[0] * G2 + r[1] * G3 + r[2] * G4;
@@ -439,9 +455,9 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                         const double n5 = r[13] * G3 + r[14] * G4 + r[15] * G5;
                         G0 = n0; G1 = n1; G2 = n2; G3 = n3; G4 = n4; G5 = n5;
                     } else if (j < 2 * k + 2) {  // new block column: B_k
-                        const int cc = j - 2 * k;
+                        const bool c1 = (j - 2 * k) != 0;
                         G0 = 0.0; G1 = 0.0; G2 = 0.0;
-                        G3 = r[16 + cc]; G4 = r[18 + cc]; G5 = r[20 + cc];
+                        G3 = c1 ? r[17] : r[16]; G4 = c1 ? r[19] : r[18]; G5 = c1 ? r[21] : r[20];
                     }
                     const int kk = k + 1;
                     const double wc = sn[kk] * G0 - cs[kk] * G1;
@@ -494,7 +510,9 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         }
     }
     TG_TICK(2);
-    // input and input-rate penalties (mpc_6stati.py:238-245), expressed in dU
+    // input and input-rate penalties (mpc_6stati.py:238-245), expressed in dU: block-tridiagonal in 2x2 blocks,
+    // so only tile blocks within one block of the diagonal are touched (BS >= 3)
+    const bool near_diag = (br - bc <= 1) && (bc - br <= 1);
 #pragma unroll
     for (int i = 0; i < BS; ++i) {
         const int row = R0 + i, kr = row >> 1, cr = row & 1;
@@ -502,7 +520,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         for (int j = 0; j < BS; ++j) {
             const int col = C0 + j, kc = col >> 1, cc = col & 1;
             double add = 0.0;
-            if (row < n && col < n) {
+            if (row < n && col < n && near_diag) {
                 if (kc == kr) add = 2.0 * c.Rs[cr * 2 + cc] + ((kr < N - 1) ? 4.0 : 2.0) * c.Rds[cr * 2 + cc];
                 else if (kc == kr + 1 || kc + 1 == kr) add = -2.0 * c.Rds[cr * 2 + cc];
             }
@@ -604,6 +622,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
             }
         }
         __syncthreads();
+        TG_TICK(7);
 #pragma unroll 1
         for (it = 1; it <= c.max_iter; ++it) {
             const bool check = (--until_check == 0) || (it == c.max_iter);
@@ -662,6 +681,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 rp = fmax(rp, fabs(ztl - zn)); nzt = fmax(nzt, fabs(ztl)); nz = fmax(nz, fabs(zn));
             }
             __syncthreads();
+            TG_TICK(8);
             if (!check) continue;
 
             // (d) residuals at (x~, z, y):  H x~ = rhs - sigma x~ - A'(rho .* z~)
@@ -687,6 +707,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
             const double eps_p = c.eps_abs + c.eps_rel * fmax(vals[1], vals[2]);
             const double eps_d = c.eps_abs + c.eps_rel * fmax(fmax(vals[4], vals[5]), nq);
             if (vals[8] > 0.0 || !(vals[0] == vals[0]) || !(vals[3] == vals[3])) { status = TG_STATUS_NAN; break; }
+            TG_TICK(9);
             if (vals[0] <= eps_p && vals[3] <= eps_d) { status = TG_STATUS_OPTIMAL; break; }
             if (it == c.max_iter) {
                 if (vals[0] <= 10.0 * eps_p && vals[3] <= 10.0 * eps_d) status = TG_STATUS_OPTIMAL_INACCURATE;
