@@ -1,0 +1,63 @@
+"""BASELINE.json configs 1, 3, 4, 5 at full size on one B200 (config 2 is bench.py): timing + sanity numbers.
+Writes a short report to stdout; used to fill profiles/rNN_configs.txt."""
+import sys, time
+import numpy as np
+sys.path.insert(0, ".")
+import bench
+import trajectory_generation_b200 as tg
+
+def timed(gen, x0, u0, sc, T, reps=2):
+    gen.generate(x0[:8], u0[:8], sc.slice(0, 8), 3)
+    best = 1e9
+    for _ in range(reps):
+        t = time.perf_counter(); res = gen.generate(x0, u0, sc, T); best = min(best, time.perf_counter() - t)
+    return res, best
+
+# ---- config 1: MPC/main.py verbatim (B = 1, N = 40, Ts = 0.02, 600 steps)
+gen = tg.ClosedLoopGenerator(N=40, Ts=0.02)
+x0 = np.array([[0, 0.5, 0, 1.0, 0, 0.0]]); u0 = np.array([[tg.d_steady_state(1.0), 0.0]])
+res, dt = timed(gen, x0, u0, tg.Scenarios(1), 600, reps=3)
+d, de = res["U"][0, :, 0], res["U"][0, :, 1]
+print(f"config 1  B=1 N=40 T=600: {dt*1e3:.1f} ms end to end = {dt/600*1e6:.0f} us per closed-loop step; statuses {res['status_counts'][0]}; "
+      f"d mean {d.mean():.4f} std {d.std():.4f}, delta mean {de.mean():.4f} std {de.std():.4f} (generation_type1.py:250: 0.2161/0.1314, 0.0035/0.0338)")
+ctl = tg.BatchedMPC(N=40, Ts=0.02)
+from oracle import refgen as R
+v = R.vref_profile(R.VREF_RAMP, (0.8, 2.0, 2.0), 40, 0.02); pr = R.ref_window(0.0, 40, 0.02, v)
+ctl.step(x0, u0, pr[None], v[None])
+ts = []
+for _ in range(50):
+    t = time.perf_counter(); ctl.step(x0, u0, pr[None], v[None]); ts.append(time.perf_counter() - t)
+print(f"          one mpc_step call through the host API (B=1, cold start): p50 {np.median(ts)*1e6:.0f} us")
+
+# ---- config 3: 65536 trajectories, parabola + mixed references, generator plant, clean+noisy CSV (first 5000 ids)
+B, T = 65536, 1200
+t = time.perf_counter(); x0, u0, sc = bench.make_workload(B); t_setup = time.perf_counter() - t
+rng = np.random.default_rng(3)
+par = np.arange(0, B, 3)
+sc.set_parabola(par, rng.uniform(-0.2, 0.2, len(par)))          # every third trajectory: y = c x^2 (MPC/main.py:64 has c = 0.1)
+x0[par, 1] = sc.spec["path"][par, 0] * x0[par, 0] ** 2 + rng.uniform(-0.2, 0.2, len(par)); x0[par, 2] = np.arctan(2 * sc.spec["path"][par, 0] * x0[par, 0])
+gen = tg.ClosedLoopGenerator(N=20, Ts=0.01, plant=tg.PLANT_GEN2, vref_advance=True)
+res, dt = timed(gen, x0, u0, sc, T, reps=1)
+st = res["status_counts"].sum(0)
+print(f"config 3  B={B} N=20 T={T}: {dt:.2f} s end to end (host buffers, {res['clean'].nbytes*2/1e9 + res['U'].nbytes/1e9:.1f} GB out) = {B*T/dt:.3e} MPC steps/s; "
+      f"statuses {dict(zip(tg.STATUS_STRINGS, st.tolist()))}; mean ADMM iterations/step {res['iters_total'].sum()/(B*T):.2f}; scenario setup on host {t_setup:.1f} s")
+sub = {k: v[:5000] for k, v in res.items()}
+t = time.perf_counter(); tg.write_csv(sub, 0.01, "/tmp/c3_clean.csv", "/tmp/c3_noisy.csv"); t_csv = time.perf_counter() - t
+import os
+print(f"          native CSV writer, first 5000 ids (6.0 M rows x 2 files, {os.path.getsize('/tmp/c3_clean.csv')/1e9 + os.path.getsize('/tmp/c3_noisy.csv')/1e9:.2f} GB): {t_csv:.1f} s")
+del res, sub
+
+# ---- config 4: horizon sweep with active rate / state boxes, B = 16384, T = 200
+HARD = dict(du_bounds=((-0.1, 0.1), (-0.04, 0.04)), x_lo=[-1e20] * 4 + [-0.15, -2.0], x_hi=[1e20] * 4 + [0.15, 2.0])
+B, T = 16384, 200
+rng = np.random.default_rng(4)
+x0 = np.zeros((B, 6)); x0[:, 1] = rng.uniform(-1.5, 1.5, B); x0[:, 3] = rng.uniform(0.8, 1.2, B)
+u0 = np.stack([tg.d_steady_state(x0[:, 3]), np.zeros(B)], 1)
+sc = tg.Scenarios(B); sc.set_sine(slice(0, B), 0.5, 0.5, 0.0, 0.0)
+for N in (10, 20, 50):
+    gen = tg.ClosedLoopGenerator(N=N, Ts=0.02, **HARD)
+    res, dt = timed(gen, x0, u0, sc, T, reps=1)
+    st = res["status_counts"].sum(0)
+    its = res["iters_total"] / T
+    print(f"config 4  B={B} N={N} T={T}: {dt:.2f} s = {B*T/dt:.3e} MPC steps/s; statuses {dict(zip(tg.STATUS_STRINGS, st.tolist()))}; "
+          f"ADMM iterations/step mean {its.mean():.0f} p50 {np.median(its):.0f} p90 {np.percentile(its, 90):.0f} max {its.max():.0f}; launch geometry {gen.info()}")
