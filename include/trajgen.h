@@ -92,7 +92,7 @@ typedef struct tg_config {
     /* sensor noise (generation_type1.py:25-32,255) */
     double noise_std[6];
     uint64_t noise_seed_base;
-    int32_t threads_per_problem; /* 0 = choose from N */
+    int32_t threads_per_problem; /* reserved, must be 0: the launch geometry follows from N (tg_info reports it) */
     int32_t reserved;
 } tg_config;
 

@@ -9,6 +9,7 @@ import pytest
 
 import trajectory_generation_b200 as tg
 from oracle import dynamics as dyn, mpc as ompc, philox as oph, qp as oqp, refgen as R
+from oracle import refgen as R_
 from conftest import HARD
 
 pytestmark = pytest.mark.gpu
@@ -318,3 +319,32 @@ def test_generated_csv_loads_through_the_reference_schema(tmp_path):
     assert c["d"].isna().sum() == B and not c[["X", "Y", "phi", "vx", "vy", "omega"]].isna().any().any()
     y, u, x = tg.to_loader_tensors(res, T)
     assert y.shape == (B, 5, T) and not np.isnan(u).any()
+
+
+def test_random_controller_settings_vs_oracle():
+    """non-default keyword arguments of mpc_step (params override, weights, full R / Rd matrices, bounds, Ts, N):
+    the CUDA path and the oracle must agree on the optimum, the objective and the predicted states."""
+    rng = np.random.default_rng(11)
+    worst = 0.0
+    for case in range(10):
+        N = int(rng.choice([8, 12, 20, 25, 33]))
+        Ts = float(rng.choice([0.01, 0.02]))
+        a, b = rng.uniform(0.01, 0.05), rng.uniform(1.0, 3.0)
+        R = np.array([[a, 0.02 * rng.uniform(-1, 1)], [0.0, b]]); R[1, 0] = R[0, 1] + 0.01          # not symmetric: quad_form uses the symmetric part
+        Rd = np.array([[rng.uniform(0.005, 0.02), 0.0], [0.0, rng.uniform(2.0, 8.0)]])
+        kw = dict(Ts=Ts, N=N, params={"m": 0.041 * rng.uniform(0.9, 1.1), "Df": 0.192 * rng.uniform(0.9, 1.1)},
+                  q_c=rng.uniform(2, 10), q_phi=rng.uniform(0.1, 1.0), q_vx=rng.uniform(0.1, 1.0), R=R, Rd=Rd,
+                  u_bounds=((-0.8, 0.9), (-0.5, 0.45)), du_bounds=((-0.3, 0.4), (-0.2, 0.15)))
+        vx = rng.uniform(0.6, 1.5)
+        x = np.array([rng.uniform(-1, 1), rng.uniform(-0.4, 0.4), rng.uniform(-0.3, 0.3), vx, rng.uniform(-0.05, 0.05), rng.uniform(-1, 1)])
+        up = np.array([tg.d_steady_state(vx), rng.uniform(-0.1, 0.1)])
+        v = R_.vref_profile(R_.VREF_TRAPEZOID, (0.8, 2.0, 0.1, 0.1, 0.1), N, Ts)
+        pr = R_.ref_window(x[0], N, Ts, v, R_.PATH_SINE, (rng.uniform(0.2, 0.8), rng.uniform(0.3, 1.0), rng.uniform(0, 6), 0.0))
+        ug, sg, ig = tg.mpc_step(x, up, pr, vref=v, solver_opts=TIGHT, **kw)
+        uo, so, io = ompc.mpc_step(x, up, pr, vref=v, solver="ipm", **kw)
+        assert sg == so == "optimal"
+        err = np.abs(ig["U_opt"] - io["U_opt"]).max()
+        worst = max(worst, err)
+        assert err < TOL_U and np.abs(ig["X_opt"] - io["X_opt"]).max() < 5e-3
+        assert abs(ig["objective"] - io["objective"]) < 1e-5 * (1 + abs(io["objective"]))
+    print("worst |U - U*| over random settings:", worst)
