@@ -411,6 +411,7 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     tg_handle *h = new (std::nothrow) tg_handle();
     if (!h) return fail(TG_ERR_NOMEM, "out of host memory");
     memset(h, 0, sizeof(*h));
+    struct Guard { tg_handle *p; ~Guard() { if (p) { cudaFree(p->Hws); delete p; } } } guard{h};   // released on success
     h->cfg = *cfg; h->shape = sh; h->device = device; h->num_sms = prop.multiProcessorCount;
     DevCfg &d = h->dc;
     d.N = cfg->N; d.n = 2 * cfg->N; d.model = cfg->model; d.plant = cfg->plant; d.jacobian = cfg->jacobian;
@@ -439,7 +440,6 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     h->L = tg_make_layout(d.N, d.ms, d.NP, d.NPP);
     h->smem_bytes = (size_t)h->L.total * sizeof(double);
     if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
-        delete h;
         return fail(TG_ERR_UNSUPPORTED, "state-bound rows x horizon exceed the 227 KB shared memory of one CTA");
     }
     int occ = 0;
@@ -456,8 +456,8 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
         occ = o1 < o2 ? o1 : o2;
         return TG_OK;
     });
-    if (rc != TG_OK) { delete h; return rc; }
-    if (occ < 1) { delete h; return fail(TG_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration"); }
+    if (rc != TG_OK) return rc;
+    if (occ < 1) return fail(TG_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration");
     h->grid_cap = occ * h->num_sms;
     CK(cudaFuncSetAttribute(tg_ref_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     if (d.adaptive_rho) {
@@ -465,6 +465,7 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
         CK(cudaMalloc(&h->Hws, h->Hws_elems * sizeof(double)));
     }
     h->stream = 0;
+    guard.p = nullptr;
     *out = h;
     return TG_OK;
 }

@@ -218,6 +218,8 @@ def mpc_step(x0, u_prev, path_ref, Ts=0.02, N=20, params=None, q_c=6.0, q_phi=0.
            _freeze(du_bounds), _freeze(x_lo), _freeze(x_hi), _freeze(solver_opts), device)
     ctl = _SHIM_CACHE.get(key)
     if ctl is None:
+        if len(_SHIM_CACHE) >= 16:                          # a caller that varies the settings every call must not leak handles
+            _SHIM_CACHE.pop(next(iter(_SHIM_CACHE))).close()
         ctl = BatchedMPC(device=device, Ts=Ts, N=N, params=params, q_c=q_c, q_phi=q_phi, q_vx=q_vx, R=R, Rd=Rd,
                          u_bounds=u_bounds, du_bounds=du_bounds, x_lo=x_lo, x_hi=x_hi, solver_opts=solver_opts)
         _SHIM_CACHE[key] = ctl
