@@ -26,6 +26,7 @@ struct DevCfg {
     int max_iter, check_every, adaptive_rho, adaptive_rho_min_iter, warm_start, vref_advance;
     double Ts;
     double p[TG_NPARAMS];
+    double inv_m, inv_Iz;   // 1.0/m, 1.0/Iz (the MPC variant multiplies by them, MPC/mpc_6stati.py:67-69)
     double q_c, q_phi, q_vx;
     double Rs[4], Rds[4];  // symmetric parts
     double u_lo[2], u_hi[2], du_lo[2], du_hi[2], x_lo[6], x_hi[6];
@@ -113,8 +114,9 @@ __device__ __forceinline__ void tg_plant_step(const DevCfg &c, double x[6], doub
 // role 1 = rear tyre chain, roles 2/3 = tg_sin(phi) / tg_sin(phi + pi/2) = cos(phi) sharing the final sin with the
 // tyre lanes; three transcendental latencies instead of eight on the sequential rollout / plant path.  Must be
 // called by all 32 lanes of a warp; every lane returns the full f.
-__device__ __forceinline__ void tg_f_cont_lanes(const double *__restrict__ p, int variant, const double x[6], double d,
-                                                double delta, double sd, double cd, int lane, double f[6])
+__device__ __forceinline__ void tg_f_cont_lanes(const double *__restrict__ p, double inv_m, double inv_Iz, int variant,
+                                                const double x[6], double d, double delta, double sd, double cd, int lane,
+                                                double f[6])
 {
     const int role = lane & 3, base = lane & ~3;
     const double phi = x[2], vx = x[3], vy = x[4], om = x[5];
@@ -139,9 +141,9 @@ __device__ __forceinline__ void tg_f_cont_lanes(const double *__restrict__ p, in
     f[1] = vx * sp + vy * cp;
     f[2] = om;
     if (variant == TG_MODEL_MPC) {
-        f[3] = (1.0 / m) * (Frx - Fyf * sd + m * vy * om);
-        f[4] = (1.0 / m) * (Fyr + Fyf * cd - m * vx * om);
-        f[5] = (1.0 / Iz) * (Fyf * p[P_lf] * cd - Fyr * p[P_lr]);
+        f[3] = inv_m * (Frx - Fyf * sd + m * vy * om);       // (1.0/m) * (...), MPC/mpc_6stati.py:67
+        f[4] = inv_m * (Fyr + Fyf * cd - m * vx * om);
+        f[5] = inv_Iz * (Fyf * p[P_lf] * cd - Fyr * p[P_lr]);
     } else {
         f[3] = (Frx - Fyf * sd + m * vy * om) / m;
         f[4] = (Fyr + Fyf * cd - m * vx * om) / m;
@@ -154,7 +156,7 @@ __device__ __forceinline__ void tg_plant_step_lanes(const DevCfg &c, double x[6]
 {
     double sd, cd, f[6];
     TG_SINCOS(delta, sd, cd);
-    tg_f_cont_lanes(c.p, c.plant, x, d, delta, sd, cd, lane, f);
+    tg_f_cont_lanes(c.p, c.inv_m, c.inv_Iz, c.plant, x, d, delta, sd, cd, lane, f);
 #pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = x[i] + c.Ts * f[i];
     if (c.plant != TG_PLANT_MPC) {
@@ -196,7 +198,8 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
     const double *p = c.p;
     const int variant = c.model;
     const double phi = x[2], vx = x[3], vy = x[4], om = x[5];
-    const double lf = p[P_lf], lr = p[P_lr], m = p[P_m], Iz = p[P_Iz], ma = p[P_maxAlpha];
+    const double lf = p[P_lf], lr = p[P_lr], m = p[P_m], ma = p[P_maxAlpha];
+    const double im = c.inv_m, iI = c.inv_Iz;
     const double avx = fabs(vx);
     const double vmag = fmax(avx, p[P_vx_zero]);
     const double sgn = (double)((vx > 0.0) - (vx < 0.0));
@@ -233,17 +236,17 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
     f[0] = vx * cp - vy * sp;
     f[1] = vx * sp + vy * cp;
     f[2] = om;
-    f[3] = (Frx - Fyf * sd + m * vy * om) / m;
-    f[4] = (Fyr + Fyf * cd - m * vx * om) / m;
-    f[5] = (Fyf * lf * cd - Fyr * lr) / Iz;
+    f[3] = (Frx - Fyf * sd + m * vy * om) * im;
+    f[4] = (Fyr + Fyf * cd - m * vx * om) * im;
+    f[5] = (Fyf * lf * cd - Fyr * lr) * iI;
     // continuous Jacobian entries (rows 3..5)
-    const double j33 = (Frx_vx - Ff_vx * sd) / m, j34 = (-Ff_vy * sd + m * om) / m, j35 = (-Ff_om * sd + m * vy) / m;
-    const double j43 = (Fr_vx + Ff_vx * cd - m * om) / m, j44 = (Fr_vy + Ff_vy * cd) / m, j45 = (Fr_om + Ff_om * cd - m * vx) / m;
-    const double j53 = (Ff_vx * lf * cd - Fr_vx * lr) / Iz, j54 = (Ff_vy * lf * cd - Fr_vy * lr) / Iz,
-                 j55 = (Ff_om * lf * cd - Fr_om * lr) / Iz;
-    const double b30 = Frx_d / m, b31 = (-Ff_de * sd - Fyf * cd) / m;
-    const double b41 = (Ff_de * cd - Fyf * sd) / m;
-    const double b51 = (Ff_de * lf * cd - Fyf * lf * sd) / Iz;
+    const double j33 = (Frx_vx - Ff_vx * sd) * im, j34 = (-Ff_vy * sd + m * om) * im, j35 = (-Ff_om * sd + m * vy) * im;
+    const double j43 = (Fr_vx + Ff_vx * cd - m * om) * im, j44 = (Fr_vy + Ff_vy * cd) * im, j45 = (Fr_om + Ff_om * cd - m * vx) * im;
+    const double j53 = (Ff_vx * lf * cd - Fr_vx * lr) * iI, j54 = (Ff_vy * lf * cd - Fr_vy * lr) * iI,
+                 j55 = (Ff_om * lf * cd - Fr_om * lr) * iI;
+    const double b30 = Frx_d * im, b31 = (-Ff_de * sd - Fyf * cd) * im;
+    const double b41 = (Ff_de * cd - Fyf * sd) * im;
+    const double b51 = (Ff_de * lf * cd - Fyf * lf * sd) * iI;
     const double Ts = c.Ts;
     rec[0] = -Ts * f[1]; rec[1] = Ts * cp; rec[2] = -Ts * sp;
     rec[3] = Ts * f[0];  rec[4] = Ts * sp; rec[5] = Ts * cp;

@@ -345,7 +345,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         if (tid < 6) xbar[tid] = sm[L.x0 + tid];
 #pragma unroll 1
         for (int k = 0; k < N; ++k) {
-            tg_f_cont_lanes(c.p, c.model, xs, ud, udel, sd, cd, tid, f);
+            tg_f_cont_lanes(c.p, c.inv_m, c.inv_Iz, c.model, xs, ud, udel, sd, cd, tid, f);
 #pragma unroll
             for (int i = 0; i < 6; ++i) xs[i] = xs[i] + c.Ts * f[i];
             if (tid == 0) {
@@ -405,10 +405,12 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
             rr[3 * k] = rc; rr[3 * k + 1] = rp; rr[3 * k + 2] = rv;
             c0_part += c.q_c * rc * rc + c.q_phi * rp * rp + c.q_vx * rv * rv;
         }
-        // constant term: stage costs at xbar + N u_prev' R u_prev
-        double c0 = tg_block_reduce_sum(c0_part, red, tid, NT);
-        c0 += (double)N * (ud * (c.Rs[0] * ud + c.Rs[1] * udel) + udel * (c.Rs[2] * ud + c.Rs[3] * udel));
-        if (tid == 0) misc[M_C0] = c0;
+        // constant term: stage costs at xbar + N u_prev' R u_prev (only the step API reports the objective)
+        if (!fx) {
+            double c0 = tg_block_reduce_sum(c0_part, red, tid, NT);
+            c0 += (double)N * (ud * (c.Rs[0] * ud + c.Rs[1] * udel) + udel * (c.Rs[2] * ud + c.Rs[3] * udel));
+            if (tid == 0) misc[M_C0] = c0;
+        }
     }
     __syncthreads();
     if (tap.A || tap.Bm || tap.g || tap.xbar) {
@@ -752,7 +754,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 }
             }
         }
-        if (status == TG_STATUS_OPTIMAL || status == TG_STATUS_OPTIMAL_INACCURATE) {
+        if (!fx && (status == TG_STATUS_OPTIMAL || status == TG_STATUS_OPTIMAL_INACCURATE)) {
             double objp = 0.0;
             if (tid < n) {
                 const int j = tid;

@@ -423,6 +423,7 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     d.adaptive_rho_min_iter = cfg->adaptive_rho_min_iter; d.warm_start = cfg->warm_start; d.vref_advance = cfg->vref_advance;
     d.Ts = cfg->Ts;
     memcpy(d.p, cfg->params, sizeof(d.p));
+    d.inv_m = 1.0 / d.p[P_m]; d.inv_Iz = 1.0 / d.p[P_Iz];
     d.q_c = cfg->q_c; d.q_phi = cfg->q_phi; d.q_vx = cfg->q_vx;
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 2; ++j) {
