@@ -144,6 +144,53 @@ __device__ __forceinline__ void tg_ld_block(const double *p, double (&o)[BS])
     }
 }
 
+// Band terms of the tile.  R-bar + D'Rd-bar D and sigma I + A'diag(rho)A (input + rate rows) live within three entries
+// of the diagonal, i.e. in tile blocks with R0 - C0 in {-BS, 0, BS}.  With the block offset D and the parity of R0 as
+// template parameters every (i, j) knows at compile time which 2x2 coefficient it takes, so the code is a handful of
+// predicated adds instead of 25 data-dependent branches (which cost 8 k cycles per step in the first version).
+template <int BS, int D, int PAR>
+__device__ __forceinline__ void tg_add_R_terms(const DevCfg &c, double (&a)[BS][BS], int R0, int n)
+{
+#pragma unroll
+    for (int i = 0; i < BS; ++i)
+#pragma unroll
+        for (int j = 0; j < BS; ++j) {
+            const int dd = D + i - j;                          // row - col
+            const int cr = (PAR + i) & 1;                      // row & 1
+            const int cc = (PAR + (D & 1) + j) & 1;            // col & 1   (col = R0 - D + j)
+            const int e = dd - (cr - cc);                      // 2 (row/2 - col/2)
+            if (e == 0 || e == 2 || e == -2) {
+                const int row = R0 + i, col = R0 - D + j;
+                double add;
+                if (e == 0) add = 2.0 * c.Rs[cr * 2 + cc] + ((row < n - 2) ? 4.0 : 2.0) * c.Rds[cr * 2 + cc];
+                else add = -2.0 * c.Rds[cr * 2 + cc];
+                if (row < n && col < n && col >= 0) a[i][j] += add;
+            }
+        }
+}
+
+template <int BS, int D>
+__device__ __forceinline__ void tg_add_K_band(const DevCfg &c, const double *rho_b, const double *rho_r, double (&a)[BS][BS],
+                                              int R0, int n)
+{
+#pragma unroll
+    for (int i = 0; i < BS; ++i)
+#pragma unroll
+        for (int j = 0; j < BS; ++j) {
+            const int dd = D + i - j;
+            if (dd == 0 || dd == 2 || dd == -2) {
+                const int row = R0 + i, col = R0 - D + j;
+                if (row < n && col < n && col >= 0) {
+                    double add;
+                    if (dd == 0) add = c.sigma + rho_b[row] + rho_r[row] + ((row + 2 < n) ? rho_r[row + 2] : 0.0);
+                    else if (dd == 2) add = -rho_r[row];
+                    else add = -rho_r[col];
+                    a[i][j] += add;
+                }
+            }
+        }
+}
+
 // K = H + sigma I + A' diag(rho) A on the register tile; rho vectors are in shared memory.
 template <int BS>
 __device__ __forceinline__ void tg_build_K(const DevCfg &c, const SmemLayout &L, const double *sm, double (&a)[BS][BS],
@@ -152,21 +199,9 @@ __device__ __forceinline__ void tg_build_K(const DevCfg &c, const SmemLayout &L,
     const int n = c.n;
     const double *rho_b = sm + L.rho, *rho_r = sm + L.rho + n, *rho_s = sm + L.rho + 2 * n;
     const int dblk = R0 - C0;
-    if (dblk <= BS && dblk >= -BS)   // sigma I + box + rate terms live within two entries of the diagonal
-#pragma unroll
-    for (int i = 0; i < BS; ++i) {
-        const int row = R0 + i;
-        if (row >= n) continue;
-#pragma unroll
-        for (int j = 0; j < BS; ++j) {
-            const int col = C0 + j;
-            double add = 0.0;
-            if (col == row) add = c.sigma + rho_b[row] + rho_r[row] + ((row + 2 < n) ? rho_r[row + 2] : 0.0);
-            else if (col == row - 2) add = -rho_r[row];
-            else if (col == row + 2 && col < n) add = -rho_r[col];
-            a[i][j] += add;
-        }
-    }
+    if (dblk == 0) tg_add_K_band<BS, 0>(c, rho_b, rho_r, a, R0, n);
+    else if (dblk == BS) tg_add_K_band<BS, BS>(c, rho_b, rho_r, a, R0, n);
+    else if (dblk == -BS) tg_add_K_band<BS, -BS>(c, rho_b, rho_r, a, R0, n);
     const double *Gs = sm + L.Gs;
     for (int s_ = 0; s_ < c.ms; ++s_) {
         const double rs = rho_s[s_];
@@ -514,23 +549,19 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     TG_TICK(2);
     // input and input-rate penalties (mpc_6stati.py:238-245), expressed in dU: block-tridiagonal in 2x2 blocks,
     // so only tile blocks within one block of the diagonal are touched (BS >= 3)
-    const bool near_diag = (br - bc <= 1) && (bc - br <= 1);
+    {
+        const int dblk = R0 - C0, par = R0 & 1;
+        if (dblk == 0) { if (par) tg_add_R_terms<BS, 0, 1>(c, a, R0, n); else tg_add_R_terms<BS, 0, 0>(c, a, R0, n); }
+        else if (dblk == BS) { if (par) tg_add_R_terms<BS, BS, 1>(c, a, R0, n); else tg_add_R_terms<BS, BS, 0>(c, a, R0, n); }
+        else if (dblk == -BS) { if (par) tg_add_R_terms<BS, -BS, 1>(c, a, R0, n); else tg_add_R_terms<BS, -BS, 0>(c, a, R0, n); }
+        if (br == bc) {
 #pragma unroll
-    for (int i = 0; i < BS; ++i) {
-        const int row = R0 + i, kr = row >> 1, cr = row & 1;
-#pragma unroll
-        for (int j = 0; j < BS; ++j) {
-            const int col = C0 + j, kc = col >> 1, cc = col & 1;
-            double add = 0.0;
-            if (row < n && col < n && near_diag) {
-                if (kc == kr) add = 2.0 * c.Rs[cr * 2 + cc] + ((kr < N - 1) ? 4.0 : 2.0) * c.Rds[cr * 2 + cc];
-                else if (kc == kr + 1 || kc + 1 == kr) add = -2.0 * c.Rds[cr * 2 + cc];
-            }
-            a[i][j] += add;
+            for (int i = 0; i < BS; ++i)
+                if (R0 + i < n) dH[R0 + i] = a[i][i];
         }
-        if (br == bc && row < n) dH[row] = a[i][i];
     }
     __syncthreads();
+    TG_TICK(10);
 
     // ---------------- bounds (mpc_6stati.py:198-221) and per-row rho = rho0 / max_j(a_ij^2 / H_jj)
     bool x0_infeasible = false;
@@ -559,6 +590,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         const double rs = rho_scale * ((mx > 1e-30) ? 1.0 / mx : 1.0);
         rho[2 * n + i] = rs; rinv[2 * n + i] = 1.0 / rs;
     }
+    TG_TICK(11);
     if (tap.H) {
 #pragma unroll
         for (int i = 0; i < BS; ++i)
@@ -572,6 +604,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
 #pragma unroll
             for (int j = 0; j < BS; ++j) Hws[(i * BS + j) * NT + tid] = a[i][j];   // coalesced across the CTA
     }
+    TG_TICK(12);
     double nq = 0.0;
     for (int i = tid; i < n; i += NT) nq = fmax(nq, fabs(q[i]));
     {
