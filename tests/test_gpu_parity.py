@@ -348,3 +348,29 @@ def test_random_controller_settings_vs_oracle():
         assert err < TOL_U and np.abs(ig["X_opt"] - io["X_opt"]).max() < 5e-3
         assert abs(ig["objective"] - io["objective"]) < 1e-5 * (1 + abs(io["objective"]))
     print("worst |U - U*| over random settings:", worst)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 7, 13, 21, 32, 33, 41, 56])
+def test_small_odd_and_boundary_horizons(N):
+    """every tile shape and its edges (n = 2N just below / at / above a shape boundary, partial last K2 block)."""
+    rng = np.random.default_rng(100 + N)
+    Ts = 0.02 if N <= 33 else 0.01
+    vx = rng.uniform(0.8, 1.4)
+    x = np.array([0.3, 0.2, 0.05, vx, 0.01, 0.2]); up = np.array([tg.d_steady_state(vx), 0.02])
+    v = R_.vref_profile(R_.VREF_RAMP, (0.8, 2.0, 2.0), N, Ts)
+    pr = R_.ref_window(x[0], N, Ts, v, R_.PATH_SINE, (0.5, 0.5, 0.3, 0.0))
+    ug, sg, ig = tg.mpc_step(x, up, pr, Ts=Ts, N=N, vref=v, solver_opts=TIGHT)
+    uo, so, io = ompc.mpc_step(x, up, pr, Ts=Ts, N=N, vref=v, solver="ipm")
+    assert sg == so == "optimal"
+    assert np.abs(ig["U_opt"] - io["U_opt"]).max() < TOL_U and np.abs(ig["X_opt"] - io["X_opt"]).max() < 5e-3
+    assert abs(ig["objective"] - io["objective"]) < 1e-5 * (1 + abs(io["objective"]))
+    gen = tg.ClosedLoopGenerator(N=N, Ts=Ts, solver_opts=TIGHT)
+    sc = tg.Scenarios(1); sc.set_sine(0, 0.5, 0.5, 0.3, 0.0)
+    res = gen.generate(x[None], up[None], sc, 6)
+    Xo, Uo, st, _ = ompc.closed_loop(x, up, 6, Ts, N, path_kind=R_.PATH_SINE, path_prm=(0.5, 0.5, 0.3, 0.0))
+    assert np.abs(res["clean"][0] - Xo).max() < TOL_LOOP and np.abs(res["U"][0] - Uo).max() < TOL_LOOP
+
+
+def test_unsupported_horizon_is_a_loud_error():
+    with pytest.raises(tg.TrajgenError):
+        tg.BatchedMPC(N=57)
