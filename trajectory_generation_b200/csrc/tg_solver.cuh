@@ -466,7 +466,8 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         for (int j = 0; j < BS; ++j) a[i][j] = 0.0;
     {
         double G0 = 0, G1 = 0, G2 = 0, G3 = 0, G4 = 0, G5 = 0, qacc = 0.0;
-        const double tqc = 2.0 * c.q_c, tqp = 2.0 * c.q_phi, tqv = 2.0 * c.q_vx;
+        // the staged rows carry sqrt(2 q) so that the rank-3 update is a plain outer product (no scaling in the inner loop)
+        const double sqc = sqrt(2.0 * c.q_c), sqp = sqrt(2.0 * c.q_phi), sqv = sqrt(2.0 * c.q_vx);
 #pragma unroll 1
         for (int k0 = 0; k0 < N; k0 += TG_KB) {   // TG_KB stages per barrier
             const int kb = (N - k0 < TG_KB) ? N - k0 : TG_KB;
@@ -497,9 +498,9 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                         G3 = c1 ? r[17] : r[16]; G4 = c1 ? r[19] : r[18]; G5 = c1 ? r[21] : r[20];
                     }
                     const int kk = k + 1;
-                    const double wc = sn[kk] * G0 - cs[kk] * G1;
-                    wb[jpad] = wc; wb[NPP + jpad] = G2; wb[2 * NPP + jpad] = G3;
-                    qacc += tqc * rr[3 * kk] * wc + tqp * rr[3 * kk + 1] * G2 + tqv * rr[3 * kk + 2] * G3;
+                    const double wc = sqc * (sn[kk] * G0 - cs[kk] * G1), wp = sqp * G2, wv = sqv * G3;
+                    wb[jpad] = wc; wb[NPP + jpad] = wp; wb[2 * NPP + jpad] = wv;
+                    qacc += sqc * rr[3 * kk] * wc + sqp * rr[3 * kk + 1] * wp + sqv * rr[3 * kk + 2] * wv;
                     for (int si = 0; si < ns; ++si) {
                         const int sx = c.sidx[si];
                         const double gv = (sx == 0) ? G0 : (sx == 1) ? G1 : (sx == 2) ? G2 : (sx == 3) ? G3 : (sx == 4) ? G4 : G5;
@@ -517,27 +518,21 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                     tg_ld_block<BS>(wb + br * BSP, rw);
                     tg_ld_block<BS>(wb + bc * BSP, cw);
 #pragma unroll
-                    for (int i = 0; i < BS; ++i) {
-                        const double wi = rw[i] * tqc;
+                    for (int i = 0; i < BS; ++i)
 #pragma unroll
-                        for (int j = 0; j < BS; ++j) a[i][j] = fma(wi, cw[j], a[i][j]);
-                    }
+                        for (int j = 0; j < BS; ++j) a[i][j] = fma(rw[i], cw[j], a[i][j]);
                     tg_ld_block<BS>(wb + NPP + br * BSP, rw);
                     tg_ld_block<BS>(wb + NPP + bc * BSP, cw);
 #pragma unroll
-                    for (int i = 0; i < BS; ++i) {
-                        const double wi = rw[i] * tqp;
+                    for (int i = 0; i < BS; ++i)
 #pragma unroll
-                        for (int j = 0; j < BS; ++j) a[i][j] = fma(wi, cw[j], a[i][j]);
-                    }
+                        for (int j = 0; j < BS; ++j) a[i][j] = fma(rw[i], cw[j], a[i][j]);
                     tg_ld_block<BS>(wb + 2 * NPP + br * BSP, rw);
                     tg_ld_block<BS>(wb + 2 * NPP + bc * BSP, cw);
 #pragma unroll
-                    for (int i = 0; i < BS; ++i) {
-                        const double wi = rw[i] * tqv;
+                    for (int i = 0; i < BS; ++i)
 #pragma unroll
-                        for (int j = 0; j < BS; ++j) a[i][j] = fma(wi, cw[j], a[i][j]);
-                    }
+                        for (int j = 0; j < BS; ++j) a[i][j] = fma(rw[i], cw[j], a[i][j]);
                 }
             }
         }
