@@ -116,7 +116,7 @@ __device__ __forceinline__ void tg_plant_step(const DevCfg &c, double x[6], doub
 // called by all 32 lanes of a warp; every lane returns the full f.
 __device__ __forceinline__ void tg_f_cont_lanes(const double *__restrict__ p, double inv_m, double inv_Iz, int variant,
                                                 const double x[6], double d, double delta, double sd, double cd, int lane,
-                                                double f[6])
+                                                double f[6], double *aux = nullptr)
 {
     const int role = lane & 3, base = lane & ~3;
     const double phi = x[2], vx = x[3], vy = x[4], om = x[5];
@@ -127,10 +127,17 @@ __device__ __forceinline__ void tg_f_cont_lanes(const double *__restrict__ p, do
     const double nl = front ? (om * Lt + vy) : (om * Lt - vy);
     const double at = tg_atan2(nl, vx_eff);
     double alpha = front ? (-at + delta) : at;
+    const double alpha_raw = alpha;
     if (front || variant != TG_MODEL_GEN1) alpha = tg_clamp(alpha, -p[P_maxAlpha], p[P_maxAlpha]);
     const double th = (front ? p[P_Cf] : p[P_Cr]) * tg_atan((front ? p[P_Bf] : p[P_Br]) * alpha);
     const double arg = (role < 2) ? th : ((role == 2) ? phi : phi + 1.5707963267948966);
     const double sv = tg_sin(arg);
+    if (aux && lane < 4) {   // hand the transcendental intermediates of this stage to the linearisation (one predicate,
+        // no divergence): tyre lanes store (slip angle before the clamp, C atan(B alpha)), lanes 2/3 sin(phi) / cos(phi)
+        const bool tyre = role < 2;
+        aux[tyre ? 2 * role : 2 + role] = tyre ? alpha_raw : sv;
+        aux[tyre ? 2 * role + 1 : 2 + role] = tyre ? th : sv;
+    }
     const double F = (front ? p[P_Df] : p[P_Dr]) * sv;
     const double Fyf = __shfl_sync(0xffffffffu, F, base), Fyr = __shfl_sync(0xffffffffu, F, base + 1);
     const double sp = __shfl_sync(0xffffffffu, sv, base + 2), cp = __shfl_sync(0xffffffffu, sv, base + 3);
@@ -192,8 +199,11 @@ __device__ __forceinline__ void tg_lin_expand(const double *__restrict__ r, doub
 }
 
 // Analytic linearisation at (x, u): Ad = I + Ts df/dx, Bd = Ts df/du, g = Ts (f - Jx x - Ju u).
+// `aux` (optional) = {alpha_f before the clamp, Cf atan(Bf alpha_f), alpha_r before the clamp, Cr atan(Br alpha_r),
+// sin(phi), cos(phi)} as the nominal rollout left them for this stage: the rollout has just evaluated f at exactly
+// this point, so the two atan2, two atan and one sincos of the linearisation are not recomputed.
 __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double d, double delta, double sd,
-                                      double cd, double *__restrict__ rec)
+                                      double cd, double *__restrict__ rec, const double *__restrict__ aux = nullptr)
 {
     const double *p = c.p;
     const int variant = c.model;
@@ -209,8 +219,8 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
     else                         { vx_eff = vmag;       dveff = free_v ? sgn : 0.0; }
     const double nf = om * lf + vy, nr = om * lr - vy;
     const double denf = nf * nf + vx_eff * vx_eff, denr = nr * nr + vx_eff * vx_eff;
-    double af = -tg_atan2(nf, vx_eff) + delta;
-    double ar = tg_atan2(nr, vx_eff);
+    double af = aux ? aux[0] : -tg_atan2(nf, vx_eff) + delta;
+    double ar = aux ? aux[2] : tg_atan2(nr, vx_eff);
     // partials of the slip angles (zero where the clamp is active)
     double af_vx = (nf / denf) * dveff, af_vy = -vx_eff / denf, af_om = -lf * vx_eff / denf, af_de = 1.0;
     double ar_vx = -(nr / denr) * dveff, ar_vy = -vx_eff / denr, ar_om = lr * vx_eff / denr;
@@ -218,8 +228,8 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
     if (variant != TG_MODEL_GEN1 && (ar > ma || ar < -ma)) { ar = tg_clamp(ar, -ma, ma); ar_vx = ar_vy = ar_om = 0.0; }
     double s1, c1, s2, c2;
     const double Bf = p[P_Bf], Br = p[P_Br];
-    TG_SINCOS(p[P_Cf] * tg_atan(Bf * af), s1, c1);
-    TG_SINCOS(p[P_Cr] * tg_atan(Br * ar), s2, c2);
+    TG_SINCOS(aux ? aux[1] : p[P_Cf] * tg_atan(Bf * af), s1, c1);
+    TG_SINCOS(aux ? aux[3] : p[P_Cr] * tg_atan(Br * ar), s2, c2);
     const double Fyf = p[P_Df] * s1, Fyr = p[P_Dr] * s2;
     const double dFf = p[P_Df] * c1 * p[P_Cf] * Bf / (1.0 + (Bf * af) * (Bf * af));  // dFyf / d alpha_f
     const double dFr = p[P_Dr] * c2 * p[P_Cr] * Br / (1.0 + (Br * ar) * (Br * ar));
@@ -231,7 +241,7 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
     const double Frx_vx = (-p[P_Cm2] * d - 2.0 * p[P_Cr2] * vl) * dvl;
     const double Frx_d = p[P_Cm1] - p[P_Cm2] * vl;
     double sp, cp;
-    TG_SINCOS(phi, sp, cp);
+    if (aux) { sp = aux[4]; cp = aux[5]; } else TG_SINCOS(phi, sp, cp);
     double f[6];
     f[0] = vx * cp - vy * sp;
     f[1] = vx * sp + vy * cp;

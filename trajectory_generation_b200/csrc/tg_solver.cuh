@@ -38,7 +38,7 @@ __device__ long long g_tg_phase[16];
 
 // shared-memory layout (offsets in doubles), identical on host and device
 struct SmemLayout {
-    int x0, uprev, misc, spec, xbar, lin, Xr, Yr, Pr, sn, cs, vref, rr, w, v, dsc, q, x, xt, dH, z, y, l, u, rho, rinv, zt, dy, Gs, red;
+    int x0, uprev, misc, spec, xbar, lin, aux, Xr, Yr, Pr, sn, cs, vref, rr, w, v, dsc, q, x, xt, dH, z, y, l, u, rho, rinv, zt, dy, Gs, red;
     int total;
 };
 
@@ -49,7 +49,7 @@ __host__ __device__ inline SmemLayout tg_make_layout(int N, int ms, int NP, int 
     const int n = 2 * N, m = 4 * N + ms;
     auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };  // keep 16-byte alignment
     L.x0 = take(6); L.uprev = take(2); L.misc = take(24); L.spec = take(12);
-    L.xbar = take(6 * (N + 1)); L.lin = take(TG_LIN * N);
+    L.xbar = take(6 * (N + 1)); L.lin = take(TG_LIN * N); L.aux = take(6 * N);
     L.Xr = take(N + 1); L.Yr = take(N + 1); L.Pr = take(N + 1); L.sn = take(N + 1); L.cs = take(N + 1); L.vref = take(N + 1);
     L.rr = take(3 * (N + 1));
     L.w = take(2 * TG_KB * 3 * NPP); L.v = take(2 * (NPP + 2)); L.dsc = take(NPP);
@@ -380,7 +380,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         if (tid < 6) xbar[tid] = sm[L.x0 + tid];
 #pragma unroll 1
         for (int k = 0; k < N; ++k) {
-            tg_f_cont_lanes(c.p, c.inv_m, c.inv_Iz, c.model, xs, ud, udel, sd, cd, tid, f);
+            tg_f_cont_lanes(c.p, c.inv_m, c.inv_Iz, c.model, xs, ud, udel, sd, cd, tid, f, sm + L.aux + 6 * k);
 #pragma unroll
             for (int i = 0; i < 6; ++i) xs[i] = xs[i] + c.Ts * f[i];
             if (tid == 0) {
@@ -428,7 +428,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
             } else {
                 double sd, cd;
                 TG_SINCOS(udel, sd, cd);
-                tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k);
+                tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k, sm + L.aux + 6 * k);
             }
         }
         // stage costs at xbar: threads of the LAST warp, so that they overlap the linearisation in warp 0
