@@ -48,7 +48,7 @@ assert REF_SPEC_DTYPE.itemsize == 96
 # every symbol include/trajgen.h declares
 EXPORTS = (
     "tg_last_error", "tg_version", "tg_default_config", "tg_create", "tg_destroy", "tg_set_stream", "tg_synchronize",
-    "tg_kernel_launches", "tg_info", "tg_linearize", "tg_assemble", "tg_mpc_step", "tg_mpc_step_host", "tg_ref_window",
+    "tg_kernel_launches", "tg_info", "tg_tyre_table_info", "tg_linearize", "tg_assemble", "tg_mpc_step", "tg_mpc_step_host", "tg_ref_window",
     "tg_closed_loop", "tg_closed_loop_host", "tg_write_csv", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
     "tg_device_count", "tg_malloc", "tg_free", "tg_memcpy_h2d", "tg_memcpy_d2h", "tg_malloc_host", "tg_free_host",
 )
@@ -92,6 +92,7 @@ def load():
     L.tg_synchronize.argtypes = [vp]
     L.tg_kernel_launches.argtypes = [vp, ctypes.POINTER(i64)]
     L.tg_info.argtypes = [vp] + [ctypes.POINTER(i32)] * 4
+    L.tg_tyre_table_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(d), ctypes.POINTER(d)]
     L.tg_linearize.argtypes = [vp, ctypes.c_int] + [vp] * 6
     L.tg_assemble.argtypes = [vp, ctypes.c_int] + [vp] * 10
     L.tg_mpc_step.argtypes = [vp, ctypes.c_int] + [vp] * 11

@@ -14,6 +14,8 @@
 #include "../../include/trajgen.h"
 
 #define TG_LIN 28  // compact per-stage linearisation record (see lin_store)
+#define TG_TAB_NI 64   // intervals of the tyre-curve table
+#define TG_TAB_NC 10   // coefficients per interval (degree 9 in the local variable s in [-1, 1])
 
 struct DevCfg {
     int N, n;         // horizon, 2N
@@ -27,6 +29,8 @@ struct DevCfg {
     double Ts;
     double p[TG_NPARAMS];
     double inv_m, inv_Iz;   // 1.0/m, 1.0/Iz (the MPC variant multiplies by them, MPC/mpc_6stati.py:67-69)
+    const double *tyre_tab; // [2][TG_TAB_NI][TG_TAB_NC] piecewise polynomials of sin(C atan(B alpha)) on [-maxAlpha, maxAlpha], or null
+    double tab_scale;       // TG_TAB_NI / (2 maxAlpha)
     double q_c, q_phi, q_vx;
     double Rs[4], Rds[4];  // symmetric parts
     double u_lo[2], u_hi[2], du_lo[2], du_hi[2], x_lo[6], x_hi[6];
@@ -158,12 +162,104 @@ __device__ __forceinline__ void tg_f_cont_lanes(const double *__restrict__ p, do
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tyre curve from a table.  The Pacejka term g(alpha) = sin(C atan(B alpha)) is only ever evaluated on the clamped
+// slip angle |alpha| <= maxAlpha (MPC/mpc_6stati.py:42-47), a compact interval on which g is analytic (nearest
+// singularity at alpha = +-i/B), so a piecewise degree-9 polynomial on 64 intervals reproduces it to ~1e-16
+// (built in long double at tg_create, verified there against libm; the handle falls back to atan/sin if the fit is
+// not at rounding level for the caller's B, C).  It replaces two of the three dependent fp64 transcendentals of
+// every stage of the sequential nominal rollout -- the longest dependent chain of an MPC step -- by an index
+// computation and nine FMAs, and gives the linearisation dg/dalpha for free.
+__device__ __forceinline__ void tg_tyre_tab(const double *__restrict__ tab, double alpha, double ma, double scale,
+                                            double &g, double &dg)
+{
+    const double u = (alpha + ma) * scale;
+    int i = (int)u;
+    i = i < 0 ? 0 : (i > TG_TAB_NI - 1 ? TG_TAB_NI - 1 : i);
+    const double s_ = 2.0 * (u - (double)i) - 1.0;
+    const double2 *c2 = reinterpret_cast<const double2 *>(tab + i * TG_TAB_NC);
+    const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3), c89 = __ldg(c2 + 4);
+    double v = c89.y, d_ = 0.0;   // Horner for the value and its derivative together
+    d_ = fma(d_, s_, v); v = fma(v, s_, c89.x);
+    d_ = fma(d_, s_, v); v = fma(v, s_, c67.y);
+    d_ = fma(d_, s_, v); v = fma(v, s_, c67.x);
+    d_ = fma(d_, s_, v); v = fma(v, s_, c45.y);
+    d_ = fma(d_, s_, v); v = fma(v, s_, c45.x);
+    d_ = fma(d_, s_, v); v = fma(v, s_, c23.y);
+    d_ = fma(d_, s_, v); v = fma(v, s_, c23.x);
+    d_ = fma(d_, s_, v); v = fma(v, s_, c01.y);
+    d_ = fma(d_, s_, v); v = fma(v, s_, c01.x);
+    g = v;
+    dg = d_ * (2.0 * scale);
+}
+
+// sin / cos of phi + dphi from sin / cos of phi, |dphi| <= 0.25 (Taylor to x^13 / x^12: < 3e-18)
+__device__ __forceinline__ void tg_rotate_small(double &sp, double &cp, double dphi)
+{
+    const double x2 = dphi * dphi;
+    double ps = -1.0 / 6227020800.0;
+    ps = fma(ps, x2, 1.0 / 39916800.0); ps = fma(ps, x2, -1.0 / 362880.0); ps = fma(ps, x2, 1.0 / 5040.0);
+    ps = fma(ps, x2, -1.0 / 120.0); ps = fma(ps, x2, 1.0 / 6.0);
+    const double sn = fma(-dphi * x2, ps, dphi);                        // dphi - dphi^3 (1/6 - ...)
+    double pc = 1.0 / 479001600.0;
+    pc = fma(pc, x2, -1.0 / 3628800.0); pc = fma(pc, x2, 1.0 / 40320.0); pc = fma(pc, x2, -1.0 / 720.0);
+    pc = fma(pc, x2, 1.0 / 24.0); pc = fma(pc, x2, -0.5);
+    const double cm1 = pc * x2;                                          // cos(dphi) - 1
+    const double ns = fma(sp, cm1, fma(cp, sn, sp));
+    const double nc = fma(cp, cm1, fma(-sp, sn, cp));
+    sp = ns; cp = nc;
+}
+
+// f_cont by a lane pair (lane & 1: 0 = front tyre, 1 = rear tyre) with the tyre table and sin/cos(phi) supplied by
+// the caller.  Variants MPC / GEN2 only (GEN1 leaves the rear slip angle unclamped -> callers use tg_f_cont_lanes).
+// aux (optional, shared memory) receives {alpha_f raw, alpha_r raw, sin phi, cos phi} for the linearisation.
+__device__ __forceinline__ void tg_f_cont_tab(const DevCfg &c, int variant, const double x[6], double d, double delta,
+                                              double sd, double cd, double sp, double cp, int lane, double f[6],
+                                              double *aux = nullptr)
+{
+    const double *__restrict__ p = c.p;
+    const int rear = lane & 1, base = lane & ~1;
+    const double vx = x[3], vy = x[4], om = x[5];
+    const double vmag = fmax(fabs(vx), p[P_vx_zero]);
+    const double vx_eff = (variant == TG_MODEL_MPC) ? (double)((vx > 0.0) - (vx < 0.0)) * vmag : vmag;
+    const double nl = rear ? (om * p[P_lr] - vy) : (om * p[P_lf] + vy);
+    const double at = tg_atan2(nl, vx_eff);
+    const double alpha_raw = rear ? at : (-at + delta);
+    const double alpha = tg_clamp(alpha_raw, -p[P_maxAlpha], p[P_maxAlpha]);
+    double g, dg;
+    tg_tyre_tab(c.tyre_tab + rear * (TG_TAB_NI * TG_TAB_NC), alpha, p[P_maxAlpha], c.tab_scale, g, dg);
+    const double F = (rear ? p[P_Dr] : p[P_Df]) * g;
+    if (aux && lane < 2) { aux[rear] = alpha_raw; aux[2 + rear] = rear ? cp : sp; }
+    const double Fyf = __shfl_sync(0xffffffffu, F, base), Fyr = __shfl_sync(0xffffffffu, F, base + 1);
+    const double vl = (variant == TG_MODEL_MPC) ? vx : vx_eff;
+    const double Frx = (p[P_Cm1] - p[P_Cm2] * vl) * d - p[P_Cr0] - p[P_Cr2] * (vl * vl);
+    const double m = p[P_m];
+    f[0] = vx * cp - vy * sp;
+    f[1] = vx * sp + vy * cp;
+    f[2] = om;
+    if (variant == TG_MODEL_MPC) {
+        f[3] = c.inv_m * (Frx - Fyf * sd + m * vy * om);       // (1.0/m) * (...), MPC/mpc_6stati.py:67
+        f[4] = c.inv_m * (Fyr + Fyf * cd - m * vx * om);
+        f[5] = c.inv_Iz * (Fyf * p[P_lf] * cd - Fyr * p[P_lr]);
+    } else {
+        f[3] = (Frx - Fyf * sd + m * vy * om) / m;
+        f[4] = (Fyr + Fyf * cd - m * vx * om) / m;
+        f[5] = (Fyf * p[P_lf] * cd - Fyr * p[P_lr]) / p[P_Iz];
+    }
+}
+
 // plant step by a whole warp (see tg_f_cont_lanes)
 __device__ __forceinline__ void tg_plant_step_lanes(const DevCfg &c, double x[6], double d, double delta, int lane)
 {
     double sd, cd, f[6];
     TG_SINCOS(delta, sd, cd);
-    tg_f_cont_lanes(c.p, c.inv_m, c.inv_Iz, c.plant, x, d, delta, sd, cd, lane, f);
+    if (c.tyre_tab && c.plant != TG_PLANT_GEN1) {
+        double sp, cp;
+        TG_SINCOS(x[2], sp, cp);
+        tg_f_cont_tab(c, c.plant, x, d, delta, sd, cd, sp, cp, lane, f);
+    } else {
+        tg_f_cont_lanes(c.p, c.inv_m, c.inv_Iz, c.plant, x, d, delta, sd, cd, lane, f);
+    }
 #pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = x[i] + c.Ts * f[i];
     if (c.plant != TG_PLANT_MPC) {
@@ -202,8 +298,11 @@ __device__ __forceinline__ void tg_lin_expand(const double *__restrict__ r, doub
 // `aux` (optional) = {alpha_f before the clamp, Cf atan(Bf alpha_f), alpha_r before the clamp, Cr atan(Br alpha_r),
 // sin(phi), cos(phi)} as the nominal rollout left them for this stage: the rollout has just evaluated f at exactly
 // this point, so the two atan2, two atan and one sincos of the linearisation are not recomputed.
+// With `tab_aux` = {alpha_f, alpha_r before the clamp, sin(phi), cos(phi)} (table path) the tyre force and its slope
+// come from the table and no transcendental is evaluated at all.
 __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double d, double delta, double sd,
-                                      double cd, double *__restrict__ rec, const double *__restrict__ aux = nullptr)
+                                      double cd, double *__restrict__ rec, const double *__restrict__ aux = nullptr,
+                                      const double *__restrict__ tab_aux = nullptr)
 {
     const double *p = c.p;
     const int variant = c.model;
@@ -219,20 +318,29 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
     else                         { vx_eff = vmag;       dveff = free_v ? sgn : 0.0; }
     const double nf = om * lf + vy, nr = om * lr - vy;
     const double denf = nf * nf + vx_eff * vx_eff, denr = nr * nr + vx_eff * vx_eff;
-    double af = aux ? aux[0] : -tg_atan2(nf, vx_eff) + delta;
-    double ar = aux ? aux[2] : tg_atan2(nr, vx_eff);
+    double af = tab_aux ? tab_aux[0] : (aux ? aux[0] : -tg_atan2(nf, vx_eff) + delta);
+    double ar = tab_aux ? tab_aux[1] : (aux ? aux[2] : tg_atan2(nr, vx_eff));
     // partials of the slip angles (zero where the clamp is active)
     double af_vx = (nf / denf) * dveff, af_vy = -vx_eff / denf, af_om = -lf * vx_eff / denf, af_de = 1.0;
     double ar_vx = -(nr / denr) * dveff, ar_vy = -vx_eff / denr, ar_om = lr * vx_eff / denr;
     if (af > ma || af < -ma) { af = tg_clamp(af, -ma, ma); af_vx = af_vy = af_om = af_de = 0.0; }
     if (variant != TG_MODEL_GEN1 && (ar > ma || ar < -ma)) { ar = tg_clamp(ar, -ma, ma); ar_vx = ar_vy = ar_om = 0.0; }
-    double s1, c1, s2, c2;
-    const double Bf = p[P_Bf], Br = p[P_Br];
-    TG_SINCOS(aux ? aux[1] : p[P_Cf] * tg_atan(Bf * af), s1, c1);
-    TG_SINCOS(aux ? aux[3] : p[P_Cr] * tg_atan(Br * ar), s2, c2);
-    const double Fyf = p[P_Df] * s1, Fyr = p[P_Dr] * s2;
-    const double dFf = p[P_Df] * c1 * p[P_Cf] * Bf / (1.0 + (Bf * af) * (Bf * af));  // dFyf / d alpha_f
-    const double dFr = p[P_Dr] * c2 * p[P_Cr] * Br / (1.0 + (Br * ar) * (Br * ar));
+    double Fyf, Fyr, dFf, dFr;   // forces and dF / d alpha
+    if (tab_aux) {
+        double g, dg;
+        tg_tyre_tab(c.tyre_tab, af, ma, c.tab_scale, g, dg);
+        Fyf = p[P_Df] * g; dFf = p[P_Df] * dg;
+        tg_tyre_tab(c.tyre_tab + TG_TAB_NI * TG_TAB_NC, ar, ma, c.tab_scale, g, dg);
+        Fyr = p[P_Dr] * g; dFr = p[P_Dr] * dg;
+    } else {
+        double s1, c1, s2, c2;
+        const double Bf = p[P_Bf], Br = p[P_Br];
+        TG_SINCOS(aux ? aux[1] : p[P_Cf] * tg_atan(Bf * af), s1, c1);
+        TG_SINCOS(aux ? aux[3] : p[P_Cr] * tg_atan(Br * ar), s2, c2);
+        Fyf = p[P_Df] * s1; Fyr = p[P_Dr] * s2;
+        dFf = p[P_Df] * c1 * p[P_Cf] * Bf / (1.0 + (Bf * af) * (Bf * af));
+        dFr = p[P_Dr] * c2 * p[P_Cr] * Br / (1.0 + (Br * ar) * (Br * ar));
+    }
     const double Ff_vx = dFf * af_vx, Ff_vy = dFf * af_vy, Ff_om = dFf * af_om, Ff_de = dFf * af_de;
     const double Fr_vx = dFr * ar_vx, Fr_vy = dFr * ar_vy, Fr_om = dFr * ar_om;
     double vl, dvl;
@@ -241,7 +349,7 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
     const double Frx_vx = (-p[P_Cm2] * d - 2.0 * p[P_Cr2] * vl) * dvl;
     const double Frx_d = p[P_Cm1] - p[P_Cm2] * vl;
     double sp, cp;
-    if (aux) { sp = aux[4]; cp = aux[5]; } else TG_SINCOS(phi, sp, cp);
+    if (tab_aux) { sp = tab_aux[2]; cp = tab_aux[3]; } else if (aux) { sp = aux[4]; cp = aux[5]; } else TG_SINCOS(phi, sp, cp);
     double f[6];
     f[0] = vx * cp - vy * sp;
     f[1] = vx * sp + vy * cp;

@@ -378,11 +378,19 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
 #pragma unroll
         for (int i = 0; i < 6; ++i) xs[i] = sm[L.x0 + i];
         if (tid < 6) xbar[tid] = sm[L.x0 + tid];
+        const bool use_tab = c.tyre_tab && c.model != TG_MODEL_GEN1;
+        double sp = 0.0, cp = 1.0;
+        if (use_tab) TG_SINCOS(xs[2], sp, cp);
 #pragma unroll 1
         for (int k = 0; k < N; ++k) {
-            tg_f_cont_lanes(c.p, c.inv_m, c.inv_Iz, c.model, xs, ud, udel, sd, cd, tid, f, sm + L.aux + 6 * k);
+            if (use_tab) tg_f_cont_tab(c, c.model, xs, ud, udel, sd, cd, sp, cp, tid, f, sm + L.aux + 6 * k);
+            else tg_f_cont_lanes(c.p, c.inv_m, c.inv_Iz, c.model, xs, ud, udel, sd, cd, tid, f, sm + L.aux + 6 * k);
 #pragma unroll
             for (int i = 0; i < 6; ++i) xs[i] = xs[i] + c.Ts * f[i];
+            if (use_tab) {   // sin / cos of the new heading by a small rotation (phi advances by Ts * omega)
+                const double dphi = c.Ts * f[2];
+                if (fabs(dphi) <= 0.25) tg_rotate_small(sp, cp, dphi); else TG_SINCOS(xs[2], sp, cp);
+            }
             if (tid == 0) {
 #pragma unroll
                 for (int i = 0; i < 6; ++i) xbar[6 * (k + 1) + i] = xs[i];
@@ -428,7 +436,8 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
             } else {
                 double sd, cd;
                 TG_SINCOS(udel, sd, cd);
-                tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k, sm + L.aux + 6 * k);
+                if (c.tyre_tab && c.model != TG_MODEL_GEN1) tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k, nullptr, sm + L.aux + 6 * k);
+                else tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k, sm + L.aux + 6 * k);
             }
         }
         // stage costs at xbar: threads of the LAST warp, so that they overlap the linearisation in warp 0

@@ -330,6 +330,53 @@ static bool pick_shape(int N, Shape &s)
     return true;
 }
 
+// Tyre-curve table (tg_device.cuh: tg_tyre_tab): per interval the degree-(NC-1) Chebyshev interpolant of
+// g(alpha) = sin(C atan(B alpha)) in long double, converted to monomials of s in [-1, 1].  Returns the largest
+// deviation from libm on a dense check grid (value and slope) so the caller can refuse a table that is not at
+// rounding level for unusual B, C.
+static double build_tyre_table(double B, double C, double ma, double *tab /*[NI][NC]*/, double *slope_err)
+{
+    const int NI = TG_TAB_NI, NC = TG_TAB_NC;
+    const long double PI = 3.141592653589793238462643383279502884L;
+    long double T[TG_TAB_NC][TG_TAB_NC] = {};   // T[k][i] = coefficient of s^i in T_k(s)
+    T[0][0] = 1.0L;
+    if (NC > 1) T[1][1] = 1.0L;
+    for (int k = 2; k < NC; ++k)
+        for (int i = 0; i < NC; ++i) T[k][i] = (i > 0 ? 2.0L * T[k - 1][i - 1] : 0.0L) - T[k - 2][i];
+    const long double hw = (long double)ma / NI;
+    double worst = 0.0, worst_d = 0.0;
+    for (int it = 0; it < NI; ++it) {
+        const long double ctr = -(long double)ma + (2 * it + 1) * hw;
+        long double fv[TG_TAB_NC], a[TG_TAB_NC];
+        for (int j = 0; j < NC; ++j) {
+            const long double sj = cosl(PI * (j + 0.5L) / NC);
+            fv[j] = sinl((long double)C * atanl((long double)B * (ctr + hw * sj)));
+        }
+        for (int k = 0; k < NC; ++k) {
+            long double acc = 0.0L;
+            for (int j = 0; j < NC; ++j) acc += fv[j] * cosl(PI * k * (j + 0.5L) / NC);
+            a[k] = acc * (k == 0 ? 1.0L : 2.0L) / NC;
+        }
+        for (int i = 0; i < NC; ++i) {
+            long double m = 0.0L;
+            for (int k = 0; k < NC; ++k) m += a[k] * T[k][i];
+            tab[it * NC + i] = (double)m;
+        }
+        for (int q = 0; q <= 16; ++q) {   // check grid incl. the interval ends
+            const double sq = -1.0 + q / 8.0;
+            double v = tab[it * NC + NC - 1], dv = 0.0;
+            for (int i = NC - 2; i >= 0; --i) { dv = dv * sq + v; v = v * sq + tab[it * NC + i]; }
+            const long double al = ctr + hw * sq, ba = (long double)B * al;
+            const long double ref = sinl((long double)C * atanl(ba));
+            const long double dref = cosl((long double)C * atanl(ba)) * C * B / (1.0L + ba * ba);
+            worst = fmax(worst, fabs((double)(v - ref)));
+            worst_d = fmax(worst_d, fabs((double)(dv / (double)hw - dref)));
+        }
+    }
+    if (slope_err) *slope_err = worst_d;
+    return worst;
+}
+
 struct tg_handle {
     tg_config cfg;
     DevCfg dc;
@@ -340,6 +387,8 @@ struct tg_handle {
     cudaStream_t stream;
     long long launches;
     double *Hws; size_t Hws_elems;
+    double *tyre_tab;   // device copy of the tyre-curve table, or null (fit not at rounding level -> atan/sin path)
+    double tab_err[2];  // max |table - libm| of value and slope on the check grid
     // warm-start state for the step API
     double *ws_x, *ws_y; int *ws_valid; int ws_B;
     // staging for *_host entry points
@@ -411,7 +460,7 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     tg_handle *h = new (std::nothrow) tg_handle();
     if (!h) return fail(TG_ERR_NOMEM, "out of host memory");
     memset(h, 0, sizeof(*h));
-    struct Guard { tg_handle *p; ~Guard() { if (p) { cudaFree(p->Hws); delete p; } } } guard{h};   // released on success
+    struct Guard { tg_handle *p; ~Guard() { if (p) { cudaFree(p->Hws); cudaFree(p->tyre_tab); delete p; } } } guard{h};   // released on success
     h->cfg = *cfg; h->shape = sh; h->device = device; h->num_sms = prop.multiProcessorCount;
     DevCfg &d = h->dc;
     d.N = cfg->N; d.n = 2 * cfg->N; d.model = cfg->model; d.plant = cfg->plant; d.jacobian = cfg->jacobian;
@@ -424,6 +473,20 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     d.Ts = cfg->Ts;
     memcpy(d.p, cfg->params, sizeof(d.p));
     d.inv_m = 1.0 / d.p[P_m]; d.inv_Iz = 1.0 / d.p[P_Iz];
+    d.tyre_tab = nullptr; d.tab_scale = 0.0;
+    if (d.p[P_maxAlpha] > 0.0 && !getenv("TRAJGEN_NO_TYRE_TABLE")) {
+        std::vector<double> tab(2 * TG_TAB_NI * TG_TAB_NC);
+        double se_f = 0.0, se_r = 0.0;
+        const double e_f = build_tyre_table(d.p[P_Bf], d.p[P_Cf], d.p[P_maxAlpha], tab.data(), &se_f);
+        const double e_r = build_tyre_table(d.p[P_Br], d.p[P_Cr], d.p[P_maxAlpha], tab.data() + TG_TAB_NI * TG_TAB_NC, &se_r);
+        h->tab_err[0] = fmax(e_f, e_r); h->tab_err[1] = fmax(se_f, se_r);
+        if (h->tab_err[0] <= 4e-16 && h->tab_err[1] <= 1e-12) {
+            CK(cudaMalloc(&h->tyre_tab, tab.size() * sizeof(double)));
+            CK(cudaMemcpy(h->tyre_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+            d.tyre_tab = h->tyre_tab;
+            d.tab_scale = TG_TAB_NI / (2.0 * d.p[P_maxAlpha]);
+        }
+    }
     d.q_c = cfg->q_c; d.q_phi = cfg->q_phi; d.q_vx = cfg->q_vx;
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 2; ++j) {
@@ -475,7 +538,7 @@ int tg_destroy(tg_handle *h)
 {
     if (!h) return TG_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->Hws); cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_valid); cudaFree(h->dstage);
+    cudaFree(h->Hws); cudaFree(h->tyre_tab); cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_valid); cudaFree(h->dstage);
     if (h->hstage) cudaFreeHost(h->hstage);
     delete h;
     return TG_OK;
@@ -500,6 +563,14 @@ int tg_debug_phases(long long *out16, int reset)
     return TG_OK;
 }
 #endif
+int tg_tyre_table_info(tg_handle *h, int32_t *in_use, double *max_value_err, double *max_slope_err)
+{
+    if (!h) return fail(TG_ERR_INVALID, "null handle");
+    if (in_use) *in_use = h->tyre_tab != nullptr;
+    if (max_value_err) *max_value_err = h->tab_err[0];
+    if (max_slope_err) *max_slope_err = h->tab_err[1];
+    return TG_OK;
+}
 int tg_kernel_launches(tg_handle *h, int64_t *count) { if (!h || !count) return fail(TG_ERR_INVALID, "null argument"); *count = h->launches; return TG_OK; }
 
 static int launch_step(tg_handle *h, StepArgs &a)

@@ -108,6 +108,12 @@ class BatchedMPC:
         _lib.check(_lib.load().tg_info(self._h, *[ctypes.byref(x) for x in v]))
         return dict(zip(("ctas_per_sm", "threads_per_cta", "smem_bytes", "num_sms"), [x.value for x in v]))
 
+    def tyre_table_info(self):
+        """dict(in_use, max_value_err, max_slope_err) of the tyre-curve table built for this handle's B, C, maxAlpha."""
+        u, a, b = ctypes.c_int32(), ctypes.c_double(), ctypes.c_double()
+        _lib.check(_lib.load().tg_tyre_table_info(self._h, ctypes.byref(u), ctypes.byref(a), ctypes.byref(b)))
+        return {"in_use": bool(u.value), "max_value_err": a.value, "max_slope_err": b.value}
+
     # -- host-array API
     @staticmethod
     def _arr(a, shape):
