@@ -374,3 +374,27 @@ def test_small_odd_and_boundary_horizons(N):
 def test_unsupported_horizon_is_a_loud_error():
     with pytest.raises(tg.TrajgenError):
         tg.BatchedMPC(N=57)
+
+
+def test_tyre_table_is_verified_and_optional(golden_physics, monkeypatch):
+    """the table path is used only when it reproduces sin(C atan(B alpha)) to rounding level, and it changes the
+    linearisation by no more than rounding; a handle with an unusual B silently keeps atan/sin and stays correct."""
+    g = golden_physics
+    ctl = tg.BatchedMPC(N=20, Ts=0.02)
+    info = ctl.tyre_table_info()
+    assert info["in_use"] and info["max_value_err"] < 4e-16 and info["max_slope_err"] < 1e-12
+    A1, B1, g1, x1 = ctl.linearize(g["XL"][:4], g["UL"][:4])
+    monkeypatch.setenv("TRAJGEN_NO_TYRE_TABLE", "1")
+    ctl2 = tg.BatchedMPC(N=20, Ts=0.02)
+    assert not ctl2.tyre_table_info()["in_use"]
+    A2, B2, g2, x2 = ctl2.linearize(g["XL"][:4], g["UL"][:4])
+    monkeypatch.delenv("TRAJGEN_NO_TYRE_TABLE")
+    assert np.abs(x1 - x2).max() < 1e-13 and np.abs(A1 - A2).max() < 1e-11 and np.abs(B1 - B2).max() < 1e-11 and np.abs(g1 - g2).max() < 1e-11
+    stiff = {"Bf": 10.0, "Br": 12.0}
+    ctl3 = tg.BatchedMPC(N=20, Ts=0.02, params=stiff)
+    assert not ctl3.tyre_table_info()["in_use"]
+    x = np.array([0.0, 0.3, 0.05, 1.0, 0.0, 0.1]); up = np.array([tg.d_steady_state(1.0), 0.0])
+    v = R_.vref_profile(R_.VREF_RAMP, (0.8, 2.0, 2.0), 20, 0.02); pr = R_.ref_window(0.0, 20, 0.02, v)
+    ug, sg, ig = tg.mpc_step(x, up, pr, vref=v, params=stiff, solver_opts=TIGHT)
+    uo, so, io = ompc.mpc_step(x, up, pr, vref=v, params=stiff, solver="ipm")
+    assert sg == so == "optimal" and np.abs(ig["U_opt"] - io["U_opt"]).max() < TOL_U
