@@ -29,7 +29,10 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 // TG_MINB = resident CTAs per SM the register allocator must allow (65536 / (threads * MINB) registers/thread):
 // 64 threads x 8 CTAs -> 128 registers for N <= 20, which leaves room to keep operand loads in flight.
 #define TG_NT(BS, TG) ((TG) * (TG))
-#define TG_MINB(BS, TG) ((TG) == 8 ? 8 : ((BS) <= 5 ? 2 : 1))
+#ifndef TG_MINB8
+#define TG_MINB8 8
+#endif
+#define TG_MINB(BS, TG) ((TG) == 8 ? TG_MINB8 : ((BS) <= 5 ? 2 : 1))
 #define TG_KATTR(BS, TG) __launch_bounds__(TG_NT(BS, TG), TG_MINB(BS, TG))
 
 // ------------------------------------------------------------------------------------------------ kernels
