@@ -31,32 +31,42 @@ METRIC = "closed-loop MPC steps/sec (batched QP solves/sec)"
 
 def make_workload(B, traj_id0=0, seed=2025):
     """BASELINE config 2: per trajectory id i (seed 2025 + i): even ids a natural cubic
-    spline y(x) through knots every U(1,3) m with N(0, 0.3^2) m ordinates, odd ids y = A sin(kx + psi) with
+    spline y(x) through 27 knots every U(1,3) m (from x = -6 m) with N(0, 0.3^2) m ordinates, odd ids y = A sin(kx + psi) with
     A~U(0.2,1), k~U(0.3,1), psi~U(0,2pi); vref ramp-cruise 0.8 -> U(0.8,2.0) m/s over 2 s, advancing in time;
     x0 from generation_type1.py:260-265's ranges with heading / lateral offset relative to the path."""
     import trajectory_generation_b200 as tg
     sc = tg.Scenarios(B)
     x0 = np.zeros((B, 6))
+    K = 27                                                   # knots per spline: -6 m ... >= 20 m at 1-3 m spacing
+    kxs, kys, sidx = [], [], []
+    ys, dys = np.zeros(B), np.zeros(B)
+    draws = np.zeros((B, 8))
     for b in range(B):
         i = traj_id0 + b
         rng = np.random.default_rng(seed + i)
         X = rng.uniform(-2.0, 2.0)
         if i % 2 == 0:
-            kx = [-6.0]
-            while kx[-1] < 45.0:
-                kx.append(kx[-1] + rng.uniform(1.0, 3.0))
-            ky = rng.normal(0.0, 0.3, len(kx))
-            sc.set_spline(b, kx, ky)
-            from scipy.interpolate import CubicSpline
-            cs = CubicSpline(kx, ky, bc_type="natural")
-            y, dy = float(cs(X)), float(cs(X, 1))
+            kx = -6.0 + np.concatenate([[0.0], np.cumsum(rng.uniform(1.0, 3.0, K - 1))])
+            ky = rng.normal(0.0, 0.3, K)
+            kxs.append(kx); kys.append(ky); sidx.append(b)
         else:
             A, k, psi = rng.uniform(0.2, 1.0), rng.uniform(0.3, 1.0), rng.uniform(0.0, 2 * np.pi)
             sc.set_sine(b, A, k, psi, 0.0)
-            y, dy = A * np.sin(k * X + psi), A * k * np.cos(k * X + psi)
+            ys[b], dys[b] = A * np.sin(k * X + psi), A * k * np.cos(k * X + psi)
         sc.set_vref(b, tg.VREF_RAMP, 0.8, rng.uniform(0.8, 2.0), 2.0)
-        x0[b] = [X, y + rng.uniform(-0.2, 0.2), np.arctan(dy) + rng.uniform(-0.2, 0.2), rng.uniform(0.4, 1.5),
-                 rng.uniform(-0.05, 0.05), rng.uniform(-1.0, 1.0)]
+        draws[b] = [X, rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2), rng.uniform(0.4, 1.5), rng.uniform(-0.05, 0.05),
+                    rng.uniform(-1.0, 1.0), 0.0, 0.0]
+    if sidx:                                                 # all splines in one batched fit
+        sidx = np.array(sidx); kxs = np.array(kxs); kys = np.array(kys)
+        coef = sc.set_splines(sidx, kxs, kys)
+        Xs = draws[sidx, 0]
+        piece = np.clip((kxs[:, :-1] <= Xs[:, None]).sum(1) - 1, 0, K - 2)
+        dx = Xs - kxs[np.arange(len(sidx)), piece]
+        c = coef[np.arange(len(sidx)), piece]
+        ys[sidx] = ((c[:, 0] * dx + c[:, 1]) * dx + c[:, 2]) * dx + c[:, 3]
+        dys[sidx] = (3.0 * c[:, 0] * dx + 2.0 * c[:, 1]) * dx + c[:, 2]
+    x0[:, 0] = draws[:, 0]; x0[:, 1] = ys + draws[:, 1]; x0[:, 2] = np.arctan(dys) + draws[:, 2]
+    x0[:, 3] = draws[:, 3]; x0[:, 4] = draws[:, 4]; x0[:, 5] = draws[:, 5]
     u0 = np.stack([tg.d_steady_state(x0[:, 3]), np.zeros(B)], axis=1)
     return x0, u0, sc
 

@@ -102,3 +102,21 @@ def test_shard_ranges_partition_the_ids():
         assert r[0][0] == 0 and r[-1][1] == B
         assert all(r[k][1] == r[k + 1][0] for k in range(W - 1))
         assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+
+
+def test_batched_natural_splines_equal_scipy():
+    from scipy.interpolate import CubicSpline
+    rng = np.random.default_rng(5)
+    M, K = 7, 12
+    X = np.cumsum(rng.uniform(1.0, 3.0, (M, K)), axis=1) - 6.0
+    Y = rng.normal(0, 0.3, (M, K))
+    sc = tg.Scenarios(10)
+    sc.set_spline(0, X[0], Y[0])                        # a single one first: the batch appends after it
+    coef = sc.set_splines(np.arange(2, 2 + M), X, Y)
+    brk, cf = sc.tables()
+    for i in range(M):
+        cs = CubicSpline(X[i], Y[i], bc_type="natural")
+        np.testing.assert_allclose(coef[i], cs.c.T, rtol=1e-10, atol=1e-12)
+        f, n_ = sc.spec["spline_first"][2 + i], sc.spec["spline_count"][2 + i]
+        assert n_ == K - 1 and np.array_equal(brk[f:f + n_], X[i, :-1]) and np.array_equal(cf[f:f + n_], coef[i])
+    assert sc.spec["spline_first"][0] == 0 and sc.spec["spline_first"][2] == K - 1

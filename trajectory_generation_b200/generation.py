@@ -62,6 +62,43 @@ class Scenarios:
         self.spec["spline_first"][i] = first
         self.spec["spline_count"][i] = K
 
+    def set_splines(self, idx, knots_x, knots_y):
+        """natural cubic splines for many trajectories at once: idx[M] trajectory indices, knots_x[M,K] (increasing along
+        axis 1), knots_y[M,K].  Same result as M calls of set_spline (scipy's CubicSpline(bc_type='natural') coefficients to
+        rounding), but the tridiagonal systems are solved for the whole batch with array operations."""
+        idx = np.asarray(idx)
+        X = np.asarray(knots_x, float); Y = np.asarray(knots_y, float)
+        M, K = X.shape
+        h = np.diff(X, axis=1)                                  # [M, K-1]
+        d = np.diff(Y, axis=1) / h
+        # second derivatives m_0 = m_{K-1} = 0;  h_{i-1} m_{i-1} + 2 (h_{i-1} + h_i) m_i + h_i m_{i+1} = 6 (d_i - d_{i-1})
+        n = K - 2
+        m = np.zeros((M, K))
+        if n > 0:
+            a = h[:, :-1].copy(); b = 2.0 * (h[:, :-1] + h[:, 1:]); c = h[:, 1:].copy(); r = 6.0 * (d[:, 1:] - d[:, :-1])
+            for i in range(1, n):                               # Thomas algorithm, vectorised over the batch
+                w = a[:, i] / b[:, i - 1]
+                b[:, i] -= w * c[:, i - 1]
+                r[:, i] -= w * r[:, i - 1]
+            sol = np.zeros((M, n))
+            sol[:, -1] = r[:, -1] / b[:, -1]
+            for i in range(n - 2, -1, -1):
+                sol[:, i] = (r[:, i] - c[:, i] * sol[:, i + 1]) / b[:, i]
+            m[:, 1:-1] = sol
+        # piece i on [x_i, x_{i+1}]: y = c0 dx^3 + c1 dx^2 + c2 dx + c3 (scipy PPoly order)
+        c0 = (m[:, 1:] - m[:, :-1]) / (6.0 * h)
+        c1 = m[:, :-1] / 2.0
+        c2 = d - h * (2.0 * m[:, :-1] + m[:, 1:]) / 6.0
+        c3 = Y[:, :-1]
+        coef = np.stack([c0, c1, c2, c3], axis=-1)              # [M, K-1, 4]
+        first = sum(len(b_) for b_ in self._breaks)
+        self._breaks.append(X[:, :-1].reshape(-1))
+        self._coef.append(coef.reshape(-1, 4))
+        self.spec["path_kind"][idx] = PATH_SPLINE
+        self.spec["spline_first"][idx] = first + np.arange(M) * (K - 1)
+        self.spec["spline_count"][idx] = K - 1
+        return coef
+
     def set_vref(self, i, kind, *prm):
         self.spec["vref_kind"][i] = kind
         cols = list(prm) + [0.0] * (6 - len(prm))
