@@ -31,6 +31,7 @@ def lib():
         L.tgo_noise_block.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p]
         L.tgo_philox_stream.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
         L.tgo_box_muller.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        L.tgo_box_muller_vec.argtypes = [ctypes.c_uint32] + [ctypes.c_void_p] * 4
         _LIB = L
     return _LIB
 
@@ -51,6 +52,21 @@ def philox_stream(seed, first, block, n):
     out = np.zeros((n, 4), dtype=np.uint32)
     lib().tgo_philox_stream(int(seed), int(first), int(block), int(n), out.ctypes.data)
     return out
+
+
+def uniform01(r):
+    """u = (r + 0.5) 2^-32 of raw 32-bit words (exact in fp64) -- the stream's uniform convention."""
+    return (np.asarray(r, dtype=np.float64) + 0.5) * 2.0 ** -32
+
+
+def box_muller(r0, r1):
+    """Vectorised tgo_box_muller: (r0[i], r1[i]) -> (n0[i], n1[i])."""
+    r0 = np.ascontiguousarray(r0, dtype=np.uint32).ravel()
+    r1 = np.ascontiguousarray(r1, dtype=np.uint32).ravel()
+    n0 = np.zeros(r0.size)
+    n1 = np.zeros(r0.size)
+    lib().tgo_box_muller_vec(r0.size, r0.ctypes.data, r1.ctypes.data, n0.ctypes.data, n1.ctypes.data)
+    return n0, n1
 
 
 def standard_normals(seed, n_rows):

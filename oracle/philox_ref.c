@@ -151,3 +151,9 @@ void tgo_philox_stream(uint64_t seed, uint32_t first, uint32_t block, uint32_t n
         tgo_philox4x32_10(c, key, out + 4 * (uint64_t)i);
     }
 }
+
+/* Box-Muller over arrays (open-loop control draws, oracle/openloop.py): pair i = (r0[i], r1[i]) */
+void tgo_box_muller_vec(uint32_t n, const uint32_t *r0, const uint32_t *r1, double *n0, double *n1)
+{
+    for (uint32_t i = 0; i < n; ++i) tgo_box_muller(r0[i], r1[i], &n0[i], &n1[i]);
+}

@@ -28,6 +28,11 @@ def golden_qp():
 
 
 @pytest.fixture(scope="session")
+def golden_openloop():
+    return np.load(os.path.join(GOLDEN, "reference_openloop.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_loop():
     return np.load(os.path.join(GOLDEN, "oracle_closed_loop.npz"))
 

@@ -103,6 +103,56 @@ def reference_fixtures():
     print("reference fixtures written")
 
 
+def reference_openloop_fixtures():
+    """Outputs of the reference's own open-loop generators -> reference_openloop.npz.
+    type 2: generate_dataset (generation_type2.py:162-220) as is; type 1: the per-trajectory body of its __main__
+    loop (generation_type1.py:267-292; the loop is not in a function, so its statements are replayed here on the
+    module's own functions and constants, with the legacy global RNG seeded like :17)."""
+    g1 = refload.load_gen1()
+    g2 = refload.load_gen2()
+    out = {}
+    # ---- type 2
+    cases2 = ((3, 12.0, 0.01, 42), (3, 6.0, 0.02, 7))
+    for c, (n, dur, Ts, seed) in enumerate(cases2):
+        old = sys.stdout; sys.stdout = io.StringIO()
+        try:
+            df = g2.generate_dataset(num_traj=n, T=dur, Ts=Ts, seed=seed)
+        finally:
+            sys.stdout = old
+        cl = df[df["noise_type"] == "clean"]
+        T1 = len(cl) // n
+        names = {"accelerate": 0, "cruise": 1, "turn_left": 2, "turn_right": 3, "": -1}
+        out[f"t2_{c}_meta"] = np.array([n, T1 - 1, Ts, seed])
+        out[f"t2_{c}_X"] = cl[["X", "Y", "phi", "vx", "vy", "omega"]].to_numpy().reshape(n, T1, 6)
+        out[f"t2_{c}_U"] = cl[["d", "delta"]].to_numpy().reshape(n, T1, 2)[:, :-1]
+        out[f"t2_{c}_modes"] = np.array([names[m] for m in cl["mode"]], dtype=np.int8).reshape(n, T1)[:, :-1]
+    # ---- type 1
+    stats = {'d_mean': 0.2161, 'd_std': 0.1314, 'delta_mean': 0.0035, 'delta_std': 0.0338}     # :250
+    du_bounds = ((-0.1, 0.1), (-0.04, 0.04))                                                    # :251
+    ranges = ((-2.0, 2.0), (-2.0, 2.0), (-np.pi, np.pi), (0.4, 1.5), (-0.05, 0.05), (-1.0, 1.0))  # :260-265
+    cases1 = ((6, 1200, 0.01, 42), (4, 400, 0.02, 11))
+    for c, (n, T, Ts, seed) in enumerate(cases1):
+        np.random.seed(seed)
+        X0 = np.zeros((n, 6)); U = np.zeros((n, T, 2)); X = np.zeros((n, T + 1, 6)); modes = np.zeros(n, dtype=np.int8)
+        DC = np.zeros((n, T, 2))
+        for i in range(n):
+            x0 = np.array([np.random.uniform(*r) for r in ranges])
+            d_clean, delta_clean, mode = g1.generate_smooth_profiles(T, Ts, stats)
+            noise_d = np.random.normal(0, stats['d_std'] * 0.1, T)
+            noise_delta = np.random.normal(0, stats['delta_std'] * 0.1, T)
+            d_true = np.clip(g1.apply_du_bounds(d_clean + noise_d, *du_bounds[0]), -1.0, 1.0)
+            delta_true = np.clip(g1.apply_du_bounds(delta_clean + noise_delta, *du_bounds[1]), -0.6, 0.6)
+            Ui = np.stack([d_true, delta_true], axis=1)
+            X0[i], U[i], X[i] = x0, Ui, g1.simulate_trajectory(x0, Ui, Ts, g1.Params)
+            DC[i] = np.stack([d_clean, delta_clean], axis=1)
+            modes[i] = {"straight": 0, "sinusoid": 1}[mode]
+        out[f"t1_{c}_meta"] = np.array([n, T, Ts, seed])
+        out[f"t1_{c}_x0"], out[f"t1_{c}_U"], out[f"t1_{c}_X"], out[f"t1_{c}_modes"], out[f"t1_{c}_clean_profiles"] = X0, U, X, modes, DC
+    out["n_t1"], out["n_t2"] = len(cases1), len(cases2)
+    np.savez_compressed(os.path.join(HERE, "reference_openloop.npz"), **out)
+    print("reference open-loop fixtures written")
+
+
 def oracle_qp_fixtures():
     rng = np.random.default_rng(7)
     cases = []
@@ -154,5 +204,6 @@ if __name__ == "__main__":
     if not refload.available():
         raise SystemExit("the reference tree is not mounted; fixtures can only be regenerated in the build container")
     reference_fixtures()
+    reference_openloop_fixtures()
     oracle_qp_fixtures()
     oracle_closed_loop_fixtures()

@@ -190,3 +190,73 @@ def test_closed_loop_golden_prefix(golden_loop):
     np.testing.assert_allclose(X, g["X40"][:6], atol=1e-7)
     d = g["U40"][:, 0]
     assert abs(d.mean() - 0.2161) < 5e-3        # soft anchor: generation_type1.py:250 (statistics of an MPC run)
+
+
+# ------------------------------------------------------------------ open-loop generators
+def test_type2_state_machine_reproduces_reference(golden_openloop):
+    """oracle/openloop.py with the reference's own PCG64 streams == generation_type2.generate_dataset."""
+    from oracle import openloop as ol
+    g = golden_openloop
+    for c in range(int(g["n_t2"])):
+        n, T, Ts, seed = g[f"t2_{c}_meta"]
+        n, T, seed = int(n), int(T), int(seed)
+        X0 = ods.sample_x0_type2(n, seed)
+        for i in range(n):
+            U, X, modes = ol.type2_trajectory(ol.GeneratorSource(np.random.default_rng(seed + i)), X0[i], T, float(Ts))
+            np.testing.assert_array_equal(U, g[f"t2_{c}_U"][i])
+            np.testing.assert_array_equal(modes, g[f"t2_{c}_modes"][i])
+            np.testing.assert_allclose(X, g[f"t2_{c}_X"][i], rtol=1e-10, atol=1e-10)
+    assert len(np.unique(g["t2_0_modes"])) == 4          # every mode of the machine occurs in the fixture
+
+
+def test_type1_profiles_reproduce_reference(golden_openloop):
+    """oracle/openloop.py with the legacy MT19937 stream == the per-trajectory body of generation_type1's main loop."""
+    from oracle import openloop as ol
+    g = golden_openloop
+    seen = set()
+    for c in range(int(g["n_t1"])):
+        n, T, Ts, seed = g[f"t1_{c}_meta"]
+        n, T, seed = int(n), int(T), int(seed)
+        rs = np.random.RandomState(seed)
+        for i in range(n):
+            x0 = np.array([rs.uniform(lo, hi) for lo, hi in ods.X0_RANGES_TYPE1])
+            np.testing.assert_array_equal(x0, g[f"t1_{c}_x0"][i])
+            U, X, mode = ol.type1_trajectory(ol.LegacyNumpySource(rs), x0, T, float(Ts))
+            np.testing.assert_array_equal(U, g[f"t1_{c}_U"][i])
+            assert mode == g[f"t1_{c}_modes"][i]
+            np.testing.assert_allclose(X, g[f"t1_{c}_X"][i], rtol=1e-10, atol=1e-10)
+            seen.add(int(mode))
+    assert seen == {0, 1}
+
+
+def test_philox_sources_keep_the_generators_contract():
+    """The B200 path's Philox streams: same distributions / ranges as the reference's draws."""
+    from oracle import openloop as ol
+    r1, r2 = ol.Type1Rules(), ol.Type2Rules()
+    modes, Us = [], []
+    for i in range(24):
+        U, mode = ol.type1_controls(ol.PhiloxType1Source(42 + i), 1200, 0.01, r1)
+        modes.append(mode)
+        Us.append(U)
+        assert np.all(np.abs(np.diff(U[:, 0])) <= 0.1 + 1e-15) and np.all(np.abs(np.diff(U[:, 1])) <= 0.04 + 1e-15)
+    U = np.concatenate(Us)
+    assert 4 <= sum(modes) <= 20                                               # p(sinusoid) = 0.5
+    assert abs(U[:, 0].mean() - r1.d_mean) < 0.02 and abs(U[:, 1].mean() - r1.delta_mean) < 0.01
+    # independent streams per trajectory and reproducibility
+    a = ol.type1_controls(ol.PhiloxType1Source(42), 300, 0.01, r1)[0]
+    b = ol.type1_controls(ol.PhiloxType1Source(42), 300, 0.01, r1)[0]
+    c = ol.type1_controls(ol.PhiloxType1Source(43), 300, 0.01, r1)[0]
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    # type 2: bounds of the machine hold, every mode is reachable, turns are followed by straights
+    counts = np.zeros(4, dtype=int)
+    for i in range(6):
+        x0 = ods.sample_x0_type2(6, 42)[i]
+        U, X, m = ol.type2_trajectory(ol.PhiloxType2Source(42 + i), x0, 1200, 0.01, r2)
+        counts += np.bincount(m, minlength=4)
+        assert U[:, 0].min() >= r2.d_range[0] and U[:, 0].max() <= r2.d_range[1]
+        assert np.all(np.abs(np.diff(np.concatenate([[0.0], U[:, 1]]))) <= r2.delta_rate_max * 0.01 + 1e-15)
+        assert X[:, 3].min() >= 0.0 and np.abs(X[:, 5]).max() <= 6.0
+        change = np.flatnonzero(np.diff(m) != 0)
+        for k in change:
+            assert not (m[k] >= 2 and m[k + 1] >= 2)                          # generation_type2.py:107-109
+    assert (counts > 0).all()
