@@ -171,6 +171,58 @@ int tg_plant_rollout(tg_handle *h, int B, int T, const double *x0, const double 
 int tg_sensor_noise(tg_handle *h, int64_t traj_id0, int n_traj, int n_rows, double *out);
 int tg_philox_u32(tg_handle *h, uint64_t seed, uint32_t first, uint32_t block, int n, uint32_t *out);
 
+/* ---- open-loop generators: the control synthesis of the two generator scripts, fused
+ * with the plant integration and the sensor noise.  The handle supplies Ts, the plant (TG_PLANT_GEN1 / TG_PLANT_GEN2),
+ * params, noise_std and noise_seed_base; N and the MPC settings are ignored.  Random numbers: Philox4x32-10 keyed by
+ * ctrl_seed_base + traj_id0 + i (controls) and noise_seed_base + traj_id0 + i (sensor noise) -- the reference's
+ * distributions and seeding contract with a counter-based stream (layout: oracle/openloop.py). */
+typedef struct tg_type1_rules {          /* generation_type1.py */
+    double d_mean, d_std, delta_mean, delta_std; /* mpc_stats :250 */
+    double du_lo[2], du_hi[2];           /* slew per step (d, delta) :251 */
+    double u_lo[2], u_hi[2];             /* final clip :288-289 */
+    double transient_s[2];               /* duration of the spline transient, uniform :110 */
+    double checkpoint_s[2];              /* knot spacing of the transient spline, uniform :90 */
+    double period_s[2], amp_frac[2];     /* steering sinusoid: period, amplitude / delta_std :122 */
+    double p_straight;                   /* P(mode = straight) :108 */
+    double tr_d_frac, tr_delta_frac;     /* knot sigma / (d_std, delta_std) :115 */
+    double st_d_frac;                    /* steady d sigma / d_std :118 */
+    double sin_noise_frac, straight_frac;/* steady delta sigma / delta_std, sinusoid :124 and straight :128 */
+    double ctrl_noise_frac;              /* high-frequency control noise sigma / std :283-284 */
+    int32_t mode;                        /* -1 = 'random', 0 = 'straight', 1 = 'sinusoid' (:105) */
+    int32_t reserved;
+} tg_type1_rules;
+
+typedef struct tg_type2_rules {          /* generation_type2.py: ControlRules :21-30 + the literals of :97-149 */
+    double v_turn_max, v_high;
+    double d_range[2], delta_turn_range[2];
+    double delta_straight_noise;
+    double delta_rate_max;               /* rad/s :97 */
+    double v_floor, d_boost_min;         /* :100 */
+    double seg_s[2];                     /* segment duration, uniform :114 */
+    double p_modes[4];                   /* accelerate, cruise, turn_left, turn_right :111-112 */
+    double p_after_turn[2];              /* accelerate, cruise :109 */
+    double acc_d_lo;                     /* accelerate: d ~ U(acc_d_lo, d_range[1]) :120 */
+    double cruise_d[2];                  /* :122 */
+    double turn_d_fast[2], turn_d_slow[2]; /* v > v_turn_max / otherwise :124 */
+    double stall_v, stall_d[2], stall_min_s; /* :131-133 */
+    double delta_clip;                   /* :141 */
+} tg_type2_rules;
+
+void tg_default_type1_rules(tg_type1_rules *r);
+void tg_default_type2_rules(tg_type2_rules *r);
+
+/* generation_type1.py:279-306 for B trajectories: x0[B][6] -> clean[B][T+1][6] (row 0 = x0), noisy[B][T+1][6],
+ * U[B][T][2], modes[B] (0 straight / 1 sinusoid).  Outputs may be NULL; non-NULL clean/noisy/U must be 16-byte aligned. */
+int tg_openloop_type1(tg_handle *h, int B, int T, const double *x0, const tg_type1_rules *rules, uint64_t ctrl_seed_base,
+                      int64_t traj_id0, double *clean, double *noisy, double *U, int8_t *modes);
+/* generation_type2.py:95-157,176-200 for B trajectories; modes[B][T]: 0 accelerate, 1 cruise, 2 turn_left, 3 turn_right. */
+int tg_openloop_type2(tg_handle *h, int B, int T, const double *x0, const tg_type2_rules *rules, uint64_t ctrl_seed_base,
+                      int64_t traj_id0, double *clean, double *noisy, double *U, int8_t *modes);
+int tg_openloop_type1_host(tg_handle *h, int B, int T, const double *x0, const tg_type1_rules *rules, uint64_t ctrl_seed_base,
+                           int64_t traj_id0, double *clean, double *noisy, double *U, int8_t *modes);
+int tg_openloop_type2_host(tg_handle *h, int B, int T, const double *x0, const tg_type2_rules *rules, uint64_t ctrl_seed_base,
+                           int64_t traj_id0, double *clean, double *noisy, double *U, int8_t *modes);
+
 /* host-side dataset writer -- replaces the DataFrame concat + to_csv of generation_type1.py:315-339 /
  * generation_type2.py:202-218,309-322.  HOST pointers clean[B][T+1][6], noisy[B][T+1][6], U[B][T][2]; writes the
  * clean file (with phi) and the noisy file (without), byte-identical to pandas' output for the same numbers

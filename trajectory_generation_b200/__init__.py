@@ -12,6 +12,7 @@ from .mpc import (BatchedMPC, Params, mpc_step, make_config, MODEL_MPC, MODEL_GE
 from .generation import (ClosedLoopGenerator, Scenarios, d_steady_state, sample_x0, to_frames, write_csv,
                          to_loader_tensors, PATH_PARABOLA, PATH_SINE, PATH_SPLINE, VREF_HOLD, VREF_CONST, VREF_RAMP,
                          VREF_TRAPEZOID, VREF_SINE, X0_RANGES_TYPE1, X0_RANGES_TYPE2, CLEAN_COLS, NOISY_COLS)
+from .openloop import OpenLoopGenerator, type1_rules, type2_rules, TYPE1_MODES, TYPE2_MODES, CTRL_SEED_BASE
 
 STATUS_STRINGS = _lib.STATUS_STRINGS
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -41,6 +41,29 @@ class TgConfig(ctypes.Structure):
     ]
 
 
+class TgType1Rules(ctypes.Structure):
+    """include/trajgen.h::tg_type1_rules (generation_type1.py's constants)."""
+    _fields_ = [
+        ("d_mean", d), ("d_std", d), ("delta_mean", d), ("delta_std", d),
+        ("du_lo", d * 2), ("du_hi", d * 2), ("u_lo", d * 2), ("u_hi", d * 2),
+        ("transient_s", d * 2), ("checkpoint_s", d * 2), ("period_s", d * 2), ("amp_frac", d * 2),
+        ("p_straight", d), ("tr_d_frac", d), ("tr_delta_frac", d), ("st_d_frac", d),
+        ("sin_noise_frac", d), ("straight_frac", d), ("ctrl_noise_frac", d),
+        ("mode", i32), ("reserved", i32),
+    ]
+
+
+class TgType2Rules(ctypes.Structure):
+    """include/trajgen.h::tg_type2_rules (generation_type2.py's ControlRules + literals)."""
+    _fields_ = [
+        ("v_turn_max", d), ("v_high", d), ("d_range", d * 2), ("delta_turn_range", d * 2),
+        ("delta_straight_noise", d), ("delta_rate_max", d), ("v_floor", d), ("d_boost_min", d),
+        ("seg_s", d * 2), ("p_modes", d * 4), ("p_after_turn", d * 2), ("acc_d_lo", d), ("cruise_d", d * 2),
+        ("turn_d_fast", d * 2), ("turn_d_slow", d * 2), ("stall_v", d), ("stall_d", d * 2), ("stall_min_s", d),
+        ("delta_clip", d),
+    ]
+
+
 REF_SPEC_DTYPE = np.dtype([("path_kind", np.int32), ("vref_kind", np.int32), ("spline_first", np.int32),
                            ("spline_count", np.int32), ("path", np.float64, 4), ("vref", np.float64, 6)], align=True)
 assert REF_SPEC_DTYPE.itemsize == 96
@@ -49,7 +72,8 @@ assert REF_SPEC_DTYPE.itemsize == 96
 EXPORTS = (
     "tg_last_error", "tg_version", "tg_default_config", "tg_create", "tg_destroy", "tg_set_stream", "tg_synchronize",
     "tg_kernel_launches", "tg_info", "tg_tyre_table_info", "tg_linearize", "tg_assemble", "tg_mpc_step", "tg_mpc_step_host", "tg_ref_window",
-    "tg_closed_loop", "tg_closed_loop_host", "tg_write_csv", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
+    "tg_closed_loop", "tg_closed_loop_host", "tg_default_type1_rules", "tg_default_type2_rules", "tg_openloop_type1",
+    "tg_openloop_type2", "tg_openloop_type1_host", "tg_openloop_type2_host", "tg_write_csv", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
     "tg_device_count", "tg_malloc", "tg_free", "tg_memcpy_h2d", "tg_memcpy_d2h", "tg_malloc_host", "tg_free_host",
 )
 
@@ -100,6 +124,13 @@ def load():
     L.tg_ref_window.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp, vp]
     L.tg_closed_loop.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     L.tg_closed_loop_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, vp]
+    L.tg_default_type1_rules.argtypes = [ctypes.POINTER(TgType1Rules)]
+    L.tg_default_type1_rules.restype = None
+    L.tg_default_type2_rules.argtypes = [ctypes.POINTER(TgType2Rules)]
+    L.tg_default_type2_rules.restype = None
+    for name, rules in (("tg_openloop_type1", TgType1Rules), ("tg_openloop_type2", TgType2Rules)):
+        for suffix in ("", "_host"):
+            getattr(L, name + suffix).argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(rules), u64, i64, vp, vp, vp, vp]
     L.tg_write_csv.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, d, i64, vp, vp, vp, ctypes.c_int, ctypes.c_int]
     L.tg_plant_rollout.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
     L.tg_sensor_noise.argtypes = [vp, i64, ctypes.c_int, ctypes.c_int, vp]

@@ -8,6 +8,8 @@
 //   tg_plant_kernel        generation_type1.py:70-84 (open-loop integration with clipping)
 //   tg_noise_kernel / tg_philox_kernel   Philox4x32-10 sensor-noise stream
 //   tg_fma_peak_kernel     FMA micro-benchmark (roofline denominator)
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +18,7 @@
 #include <vector>
 
 #include "tg_solver.cuh"
+#include "tg_openloop.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
@@ -703,6 +706,92 @@ int tg_sensor_noise(tg_handle *h, int64_t traj_id0, int n_traj, int n_rows, doub
     return TG_OK;
 }
 
+// ---- open-loop generators (tg_openloop.cuh)
+void tg_default_type1_rules(tg_type1_rules *r)
+{
+    memset(r, 0, sizeof(*r));
+    r->d_mean = 0.2161; r->d_std = 0.1314; r->delta_mean = 0.0035; r->delta_std = 0.0338;    // generation_type1.py:250
+    r->du_lo[0] = -0.1; r->du_hi[0] = 0.1; r->du_lo[1] = -0.04; r->du_hi[1] = 0.04;           // :251
+    r->u_lo[0] = -1.0; r->u_hi[0] = 1.0; r->u_lo[1] = -0.6; r->u_hi[1] = 0.6;                 // :288-289
+    r->transient_s[0] = 1.5; r->transient_s[1] = 3.0; r->checkpoint_s[0] = 3.0; r->checkpoint_s[1] = 5.0;
+    r->period_s[0] = 4.0; r->period_s[1] = 8.0; r->amp_frac[0] = 0.5; r->amp_frac[1] = 1.5;
+    r->p_straight = 0.5; r->tr_d_frac = 0.2; r->tr_delta_frac = 0.3; r->st_d_frac = 0.05;
+    r->sin_noise_frac = 0.1; r->straight_frac = 0.01; r->ctrl_noise_frac = 0.1; r->mode = -1;
+}
+
+void tg_default_type2_rules(tg_type2_rules *r)
+{
+    memset(r, 0, sizeof(*r));
+    r->v_turn_max = 1.2; r->v_high = 4.0; r->d_range[0] = 0.0; r->d_range[1] = 0.33;          // generation_type2.py:24-27
+    r->delta_turn_range[0] = 0.015; r->delta_turn_range[1] = 0.04; r->delta_straight_noise = 0.004;
+    r->delta_rate_max = 0.30; r->v_floor = 0.35; r->d_boost_min = 0.15;                         // :97,:100
+    r->seg_s[0] = 0.4; r->seg_s[1] = 1.5;                                                       // :114
+    r->p_modes[0] = 0.35; r->p_modes[1] = 0.35; r->p_modes[2] = 0.15; r->p_modes[3] = 0.15;     // :112
+    r->p_after_turn[0] = 0.5; r->p_after_turn[1] = 0.5;                                         // :109
+    r->acc_d_lo = 0.3; r->cruise_d[0] = -0.05; r->cruise_d[1] = 0.2;                            // :120,:122
+    r->turn_d_fast[0] = 0.0; r->turn_d_fast[1] = 0.15; r->turn_d_slow[0] = 0.05; r->turn_d_slow[1] = 0.25;   // :124
+    r->stall_v = 0.5; r->stall_d[0] = 0.5; r->stall_d[1] = 1.0; r->stall_min_s = 0.3;           // :131-133
+    r->delta_clip = 0.6;                                                                        // :141
+}
+
+static int openloop_check(tg_handle *h, int B, int T, const double *x0, const void *rules, const double *clean,
+                          const double *noisy, const double *U)
+{
+    if (!h || B < 0 || T < 1 || !rules || (B > 0 && !x0)) return fail(TG_ERR_INVALID, "bad argument (T >= 1 required)");
+    if (((uintptr_t)clean | (uintptr_t)noisy | (uintptr_t)U) & 15) return fail(TG_ERR_INVALID, "clean / noisy / U must be 16-byte aligned");
+    return TG_OK;
+}
+
+extern "C++" {
+template <int KIND, typename Rules>
+static int openloop_launch(tg_handle *h, int B, int T, const double *x0, const Rules &rules, uint64_t ctrl_seed_base,
+                           int64_t traj_id0, double *clean, double *noisy, double *U, int8_t *modes)
+{
+    if (B == 0) return TG_OK;
+    CK(cudaSetDevice(h->device));
+    OpenLoopArgs a;
+    a.B = B; a.T = T; a.x0 = x0; a.traj_id0 = traj_id0; a.ctrl_seed_base = ctrl_seed_base;
+    a.clean = clean; a.noisy = noisy; a.U = U; a.modes = (signed char *)modes;
+    const int per_cta = 32 * TG_OL_WARPS;
+    tg_openloop_kernel<KIND, Rules><<<(B + per_cta - 1) / per_cta, per_cta, TG_OL_WARPS * TG_OL_TILE * sizeof(double), h->stream>>>(h->dc, rules, a);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+}  // extern "C++"
+
+int tg_openloop_type1(tg_handle *h, int B, int T, const double *x0, const tg_type1_rules *rules, uint64_t ctrl_seed_base,
+                      int64_t traj_id0, double *clean, double *noisy, double *U, int8_t *modes)
+{
+    int rc = openloop_check(h, B, T, x0, rules, clean, noisy, U);
+    if (rc != TG_OK) return rc;
+    const tg_type1_rules &r = *rules;
+    const double Ts = h->dc.Ts;
+    if (!(r.transient_s[0] > 0) || r.transient_s[1] < r.transient_s[0] || !(r.checkpoint_s[0] > 0) || r.checkpoint_s[1] < r.checkpoint_s[0] ||
+        !(r.period_s[0] > 0) || r.period_s[1] < r.period_s[0] || r.mode < -1 || r.mode > 1)
+        return fail(TG_ERR_INVALID, "type-1 rules: bad range");
+    if ((int)(r.transient_s[0] / Ts) < 1) return fail(TG_ERR_INVALID, "type-1 rules: the transient must last at least one step");
+    {   // knots of the transient spline in the worst case (longest transient, densest checkpoints)
+        const double n_tr = std::min((double)T, std::floor(r.transient_s[1] / Ts));
+        const double every = std::max(1.0, std::nearbyint(r.checkpoint_s[0] / Ts));
+        if (std::ceil(n_tr / every) + 1 > TG_OL_MAX_KNOTS) return fail(TG_ERR_UNSUPPORTED, "type-1 rules: more than 16 spline knots in the transient");
+    }
+    return openloop_launch<1>(h, B, T, x0, r, ctrl_seed_base, traj_id0, clean, noisy, U, modes);
+}
+
+int tg_openloop_type2(tg_handle *h, int B, int T, const double *x0, const tg_type2_rules *rules, uint64_t ctrl_seed_base,
+                      int64_t traj_id0, double *clean, double *noisy, double *U, int8_t *modes)
+{
+    int rc = openloop_check(h, B, T, x0, rules, clean, noisy, U);
+    if (rc != TG_OK) return rc;
+    const tg_type2_rules &r = *rules;
+    double tot4 = 0, tot2 = 0;
+    for (int i = 0; i < 4; ++i) { if (!(r.p_modes[i] >= 0)) return fail(TG_ERR_INVALID, "type-2 rules: negative probability"); tot4 += r.p_modes[i]; }
+    for (int i = 0; i < 2; ++i) { if (!(r.p_after_turn[i] >= 0)) return fail(TG_ERR_INVALID, "type-2 rules: negative probability"); tot2 += r.p_after_turn[i]; }
+    if (!(tot4 > 0) || !(tot2 > 0) || !(r.seg_s[0] > 0) || r.seg_s[1] < r.seg_s[0]) return fail(TG_ERR_INVALID, "type-2 rules: bad range");
+    return openloop_launch<2>(h, B, T, x0, r, ctrl_seed_base, traj_id0, clean, noisy, U, modes);
+}
+
 int tg_philox_u32(tg_handle *h, uint64_t seed, uint32_t first, uint32_t block, int n, uint32_t *out)
 {
     if (!h || n < 0 || (n > 0 && !out)) return fail(TG_ERR_INVALID, "bad argument");
@@ -845,6 +934,54 @@ int tg_closed_loop_host(tg_handle *h, int B, int T, const double *x0, const doub
     if (iters_total) D2H(iters_total, d_it, s_it);
     CK(cudaStreamSynchronize(h->stream));
     return TG_OK;
+}
+
+extern "C++" {
+template <typename Rules, typename Fn>
+static int openloop_host(tg_handle *h, int B, int T, const double *x0, const Rules *rules, double *clean, double *noisy, double *U,
+                         int8_t *modes, size_t n_modes, Fn &&run)
+{
+    if (!h || B < 0 || T < 1 || !rules || (B > 0 && !x0)) return fail(TG_ERR_INVALID, "bad argument (T >= 1 required)");
+    if (B == 0) return TG_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t b8 = sizeof(double);
+    const size_t s_x0 = (size_t)B * 6 * b8, s_cl = (size_t)B * (T + 1) * 6 * b8, s_U = (size_t)B * T * 2 * b8;
+    const size_t total = PAD(s_x0) + 2 * PAD(s_cl) + PAD(s_U) + PAD(n_modes) + 4096;
+    int rc = ensure_dstage(h, total);
+    if (rc != TG_OK) return rc;
+    Arena ar{(char *)h->dstage, 0, h->dstage_bytes};
+    double *d_x0 = (double *)ar.take(s_x0);
+    double *d_cl = clean ? (double *)ar.take(s_cl) : nullptr, *d_no = noisy ? (double *)ar.take(s_cl) : nullptr;
+    double *d_U = U ? (double *)ar.take(s_U) : nullptr;
+    int8_t *d_m = modes ? (int8_t *)ar.take(n_modes) : nullptr;
+    H2D(d_x0, x0, s_x0);
+    rc = run(d_x0, d_cl, d_no, d_U, d_m);
+    if (rc != TG_OK) return rc;
+    if (clean) D2H(clean, d_cl, s_cl);
+    if (noisy) D2H(noisy, d_no, s_cl);
+    if (U) D2H(U, d_U, s_U);
+    if (modes) D2H(modes, d_m, n_modes);
+    CK(cudaStreamSynchronize(h->stream));
+    return TG_OK;
+}
+}  // extern "C++"
+
+int tg_openloop_type1_host(tg_handle *h, int B, int T, const double *x0, const tg_type1_rules *rules, uint64_t ctrl_seed_base,
+                           int64_t traj_id0, double *clean, double *noisy, double *U, int8_t *modes)
+{
+    return openloop_host(h, B, T, x0, rules, clean, noisy, U, modes, (size_t)(B > 0 ? B : 0),
+                         [&](double *dx, double *dc, double *dn, double *dU, int8_t *dm) {
+                             return tg_openloop_type1(h, B, T, dx, rules, ctrl_seed_base, traj_id0, dc, dn, dU, dm);
+                         });
+}
+
+int tg_openloop_type2_host(tg_handle *h, int B, int T, const double *x0, const tg_type2_rules *rules, uint64_t ctrl_seed_base,
+                           int64_t traj_id0, double *clean, double *noisy, double *U, int8_t *modes)
+{
+    return openloop_host(h, B, T, x0, rules, clean, noisy, U, modes, (size_t)(B > 0 ? B : 0) * (size_t)(T > 0 ? T : 0),
+                         [&](double *dx, double *dc, double *dn, double *dU, int8_t *dm) {
+                             return tg_openloop_type2(h, B, T, dx, rules, ctrl_seed_base, traj_id0, dc, dn, dU, dm);
+                         });
 }
 
 }  // extern "C"
