@@ -231,6 +231,13 @@ int tg_openloop_type2_host(tg_handle *h, int B, int T, const double *x0, const t
 int tg_write_csv(const char *clean_path, const char *noisy_path, int B, int T, double Ts, int64_t traj_id0,
                  const double *clean, const double *noisy, const double *U, int append, int n_threads);
 
+/* host-side merge -- replaces generation_traj/merge_datasets.py:33-52 for one pair of files: out = rows of `first`
+ * verbatim + rows of `second` with trajectory_id += offset, offset = id_offset if >= 0 else max(trajectory_id of first) + 1
+ * (:42-45; the reference re-uses the clean files' offset for the noisy pair, :62-63).  Both files must have the same
+ * header.  Text is copied, not re-parsed, so every number keeps its digits.  Outputs may be NULL. */
+int tg_merge_csv(const char *first_path, const char *second_path, const char *out_path, int64_t id_offset,
+                 int64_t *id_offset_used, int64_t *rows_written);
+
 /* measured FMA peak of this GPU (roofline denominator): TFLOP/s for dtype 0 = fp64, 1 = fp32 */
 int tg_fma_peak(tg_handle *h, int dtype, double *tflops);
 

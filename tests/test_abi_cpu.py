@@ -65,3 +65,25 @@ def test_no_gpu_fails_loudly():
         tg.BatchedMPC()
     with pytest.raises(tg.TrajgenError):           # the shim does not fall back to any CPU path either
         tg.mpc_step(np.zeros(6), np.zeros(2), np.zeros((21, 3)))
+
+
+def test_openloop_rule_defaults_are_the_generators_constants():
+    """tg_default_type{1,2}_rules == the constants of generation_type{1,2}.py as oracle/openloop.py (pinned) states them."""
+    from oracle import openloop as ool
+    for struct, ref in ((tg.type1_rules(), ool.Type1Rules()), (tg.type2_rules(), ool.Type2Rules())):
+        for name, _ in struct._fields_:
+            if name == "reserved":
+                continue
+            v = getattr(struct, name)
+            assert (tuple(v) if isinstance(v, ctypes.Array) else v) == getattr(ref, name), name
+        assert ctypes.sizeof(struct) % 8 == 0
+    r = tg.type1_rules(du_bounds=((-0.2, 0.3), (-0.01, 0.02)), mode="sinusoid", period_s=(2.0, 3.0))
+    assert (list(r.du_lo), list(r.du_hi), r.mode, list(r.period_s)) == ([-0.2, -0.01], [0.3, 0.02], 1, [2.0, 3.0])
+    with pytest.raises(TypeError):
+        tg.type2_rules(bogus=1)
+    with pytest.raises(ValueError):
+        tg.type2_rules(p_modes=(1, 2))
+    n = ctypes.c_int(0)
+    if not (_lib.load().tg_device_count(ctypes.byref(n)) == 0 and n.value > 0):
+        with pytest.raises(tg.TrajgenError):
+            tg.OpenLoopGenerator("type1")

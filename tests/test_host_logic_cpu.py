@@ -120,3 +120,41 @@ def test_batched_natural_splines_equal_scipy():
         f, n_ = sc.spec["spline_first"][2 + i], sc.spec["spline_count"][2 + i]
         assert n_ == K - 1 and np.array_equal(brk[f:f + n_], X[i, :-1]) and np.array_equal(cf[f:f + n_], coef[i])
     assert sc.spec["spline_first"][0] == 0 and sc.spec["spline_first"][2] == K - 1
+
+
+def test_merge_datasets_matches_the_reference_script(tmp_path):
+    """tg_merge_csv (host-only entry point) vs generation_traj/merge_datasets.py:33-70 restated with pandas.  With a
+    correctly rounded parser (float_precision='round_trip') pandas' re-serialisation is the identity on the numbers,
+    so the merged files must agree byte for byte; with pandas' default fast parser the reference's merge perturbs last
+    digits, which the verbatim merge never does."""
+    import pandas as pd
+    rng = np.random.default_rng(0)
+
+    def run(B, T):
+        return {"clean": rng.normal(size=(B, T + 1, 6)), "noisy": rng.normal(size=(B, T + 1, 6)), "U": rng.normal(size=(B, T, 2))}
+    p = lambda n: str(tmp_path / n)          # noqa: E731
+    tg.write_csv(run(3, 5), 0.01, p("pc.csv"), p("pn.csv"))
+    tg.write_csv(run(4, 7), 0.01, p("mc.csv"), p("mn.csv"))
+    info = tg.merge_datasets(p("pc.csv"), p("mc.csv"), p("oc.csv"), p("pn.csv"), p("mn.csv"), p("on.csv"))
+    assert info == {"id_offset": 3, "rows_clean": 3 * 6 + 4 * 8, "rows_noisy": 3 * 6 + 4 * 8}
+    off = None
+    for a, b, o in (("pc.csv", "mc.csv", "rc.csv"), ("pn.csv", "mn.csv", "rn.csv")):
+        d1 = pd.read_csv(p(a), float_precision="round_trip")
+        d2 = pd.read_csv(p(b), float_precision="round_trip")
+        if off is None:
+            off = d1["trajectory_id"].max() + 1                       # merge_datasets.py:42-45, re-used for the noisy pair
+        d2["trajectory_id"] = d2["trajectory_id"] + off
+        pd.concat([d1, d2], ignore_index=True, sort=False).to_csv(p(o), index=False)
+    assert open(p("oc.csv"), "rb").read() == open(p("rc.csv"), "rb").read()
+    assert open(p("on.csv"), "rb").read() == open(p("rn.csv"), "rb").read()
+    merged = pd.read_csv(p("oc.csv"))
+    assert sorted(merged["trajectory_id"].unique()) == list(range(7))
+    with pytest.raises(tg.TrajgenError, match="File not found"):
+        tg.merge_datasets(p("missing.csv"), p("mc.csv"), p("x.csv"))
+    with pytest.raises(tg.TrajgenError, match="different columns"):
+        tg.merge_datasets(p("pc.csv"), p("mn.csv"), p("x.csv"))
+    # a second file without a trailing newline and with CRLF line ends
+    open(p("crlf.csv"), "wb").write(b"t,X,trajectory_id\r\n0.0,1.5,0\r\n0.01,2.5,1")
+    open(p("lf.csv"), "wb").write(b"t,X,trajectory_id\n0.0,9.5,4\n")
+    tg.merge_datasets(p("lf.csv"), p("crlf.csv"), p("m.csv"))
+    assert open(p("m.csv")).read() == "t,X,trajectory_id\n0.0,9.5,4\n0.0,1.5,5\n0.01,2.5,6\n"

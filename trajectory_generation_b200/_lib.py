@@ -73,7 +73,7 @@ EXPORTS = (
     "tg_last_error", "tg_version", "tg_default_config", "tg_create", "tg_destroy", "tg_set_stream", "tg_synchronize",
     "tg_kernel_launches", "tg_info", "tg_tyre_table_info", "tg_linearize", "tg_assemble", "tg_mpc_step", "tg_mpc_step_host", "tg_ref_window",
     "tg_closed_loop", "tg_closed_loop_host", "tg_default_type1_rules", "tg_default_type2_rules", "tg_openloop_type1",
-    "tg_openloop_type2", "tg_openloop_type1_host", "tg_openloop_type2_host", "tg_write_csv", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
+    "tg_openloop_type2", "tg_openloop_type1_host", "tg_openloop_type2_host", "tg_write_csv", "tg_merge_csv", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
     "tg_device_count", "tg_malloc", "tg_free", "tg_memcpy_h2d", "tg_memcpy_d2h", "tg_malloc_host", "tg_free_host",
 )
 
@@ -132,6 +132,7 @@ def load():
         for suffix in ("", "_host"):
             getattr(L, name + suffix).argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(rules), u64, i64, vp, vp, vp, vp]
     L.tg_write_csv.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, d, i64, vp, vp, vp, ctypes.c_int, ctypes.c_int]
+    L.tg_merge_csv.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, i64, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.tg_plant_rollout.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
     L.tg_sensor_noise.argtypes = [vp, i64, ctypes.c_int, ctypes.c_int, vp]
     L.tg_philox_u32.argtypes = [vp, u64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, vp]

@@ -116,7 +116,114 @@ int write_one(const char *path, bool with_phi, int B, int T, double Ts, long lon
     return fclose(f) == 0 ? TG_OK : TG_ERR_INVALID;
 }
 
+// ---- merge (generation_traj/merge_datasets.py)
+struct LineReader {
+    FILE *f;
+    std::vector<char> buf;
+    size_t lo = 0, hi = 0;
+    bool eof = false;
+    explicit LineReader(FILE *f_) : f(f_), buf(8u << 20) {}
+    // next line without its terminator (handles a last line that lacks '\n'); false at end of file
+    bool next(const char *&line, size_t &len)
+    {
+        for (;;) {
+            if (lo < hi) {
+                const char *nl = (const char *)memchr(buf.data() + lo, '\n', hi - lo);
+                if (nl) { line = buf.data() + lo; len = (size_t)(nl - line); lo += len + 1; if (len && line[len - 1] == '\r') --len; return true; }
+                if (eof) { line = buf.data() + lo; len = hi - lo; lo = hi; if (len && line[len - 1] == '\r') --len; return len > 0; }
+            } else if (eof) return false;
+            if (lo > 0) { memmove(buf.data(), buf.data() + lo, hi - lo); hi -= lo; lo = 0; }
+            if (hi == buf.size()) buf.resize(buf.size() * 2);
+            const size_t got = fread(buf.data() + hi, 1, buf.size() - hi, f);
+            hi += got;
+            if (got == 0) eof = true;
+        }
+    }
+};
+
+// [begin, end) of column `col` of a CSV line without quoting (the schema is numeric)
+inline bool csv_field(const char *line, size_t len, int col, size_t &b, size_t &e)
+{
+    size_t pos = 0;
+    for (int c = 0; c < col; ++c) {
+        const char *k = (const char *)memchr(line + pos, ',', len - pos);
+        if (!k) return false;
+        pos = (size_t)(k - line) + 1;
+    }
+    const char *k = (const char *)memchr(line + pos, ',', len - pos);
+    b = pos; e = k ? (size_t)(k - line) : len;
+    return true;
+}
+
+inline bool parse_id(const char *s, size_t n, long long &v)
+{
+    auto r = std::from_chars(s, s + n, v);
+    if (r.ec != std::errc()) return false;
+    // pandas writes an integer column that went through NaN as "12.0": accept a zero fraction
+    const char *q = r.ptr;
+    if (q < s + n && *q == '.') { ++q; while (q < s + n && *q == '0') ++q; }
+    return q == s + n;
+}
+
 }  // namespace
+
+void tg_internal_set_error(const char *msg);   // trajgen.cu
+
+static int merge_fail(const std::string &msg) { tg_internal_set_error(msg.c_str()); return TG_ERR_INVALID; }
+
+extern "C" int tg_merge_csv(const char *first_path, const char *second_path, const char *out_path, int64_t id_offset,
+                            int64_t *id_offset_used, int64_t *rows_written)
+{
+    if (!first_path || !second_path || !out_path) return merge_fail("tg_merge_csv: null path");
+    FILE *fa = fopen(first_path, "rb");
+    if (!fa) return merge_fail(std::string("File not found: '") + first_path + "'");     // merge_datasets.py:26
+    FILE *fb = fopen(second_path, "rb");
+    if (!fb) { fclose(fa); return merge_fail(std::string("File not found: '") + second_path + "'"); }
+    FILE *fo = fopen(out_path, "wb");
+    if (!fo) { fclose(fa); fclose(fb); return merge_fail(std::string("cannot create '") + out_path + "'"); }
+    std::vector<char> obuf(8u << 20);
+    setvbuf(fo, obuf.data(), _IOFBF, obuf.size());
+    struct Closer { FILE *a, *b, *o; ~Closer() { if (a) fclose(a); if (b) fclose(b); if (o) fclose(o); } } closer{fa, fb, fo};
+    LineReader ra(fa), rb(fb);
+    const char *line; size_t len;
+    if (!ra.next(line, len)) return merge_fail("tg_merge_csv: first file is empty");
+    const std::string header(line, len);
+    int col = -1, ncol = 0;
+    for (size_t pos = 0;; ++ncol) {
+        const size_t k = header.find(',', pos);
+        if (header.compare(pos, (k == std::string::npos ? header.size() : k) - pos, "trajectory_id") == 0) col = ncol;
+        if (k == std::string::npos) { ++ncol; break; }
+        pos = k + 1;
+    }
+    if (col < 0) return merge_fail("tg_merge_csv: no trajectory_id column");
+    if (!rb.next(line, len) || header != std::string(line, len)) return merge_fail("tg_merge_csv: the two files have different columns");
+    fwrite(header.data(), 1, header.size(), fo); fputc('\n', fo);
+    long long max_id = -1, rows = 0;
+    while (ra.next(line, len)) {          // first file verbatim (merge_datasets.py:37,50)
+        size_t b, e; long long id;
+        if (!csv_field(line, len, col, b, e) || !parse_id(line + b, e - b, id)) return merge_fail("tg_merge_csv: bad trajectory_id in the first file");
+        if (id > max_id) max_id = id;
+        fwrite(line, 1, len, fo); fputc('\n', fo);
+        ++rows;
+    }
+    const long long off = id_offset >= 0 ? id_offset : max_id + 1;    // :42-45
+    char num[32];
+    while (rb.next(line, len)) {          // second file with re-indexed ids (:48)
+        size_t b, e; long long id;
+        if (!csv_field(line, len, col, b, e) || !parse_id(line + b, e - b, id)) return merge_fail("tg_merge_csv: bad trajectory_id in the second file");
+        fwrite(line, 1, b, fo);
+        char *q = put_int(num, id + off);
+        fwrite(num, 1, (size_t)(q - num), fo);
+        fwrite(line + e, 1, len - e, fo);
+        fputc('\n', fo);
+        ++rows;
+    }
+    closer.o = nullptr;
+    if (fclose(fo) != 0) return merge_fail("tg_merge_csv: write failed");
+    if (id_offset_used) *id_offset_used = off;
+    if (rows_written) *rows_written = rows;
+    return TG_OK;
+}
 
 extern "C" int tg_write_csv(const char *clean_path, const char *noisy_path, int B, int T, double Ts, int64_t traj_id0,
                             const double *clean, const double *noisy, const double *U, int append, int n_threads)

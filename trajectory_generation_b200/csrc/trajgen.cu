@@ -22,6 +22,7 @@
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+void tg_internal_set_error(const char *msg) { g_err = msg; }   // for tg_csv.cpp
 #define CK(call)                                                                                       \
     do {                                                                                               \
         cudaError_t e_ = (call);                                                                       \

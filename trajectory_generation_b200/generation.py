@@ -230,6 +230,21 @@ def write_csv(result, Ts, clean_path, noisy_path, traj_id0=0, append=False, engi
                                         int(n_threads)))
 
 
+def merge_datasets(first_clean, second_clean, out_clean, first_noisy=None, second_noisy=None, out_noisy=None):
+    """generation_traj/merge_datasets.py:33-70: concatenate two generation runs, re-indexing the second run's
+    trajectory ids by max(id of the first clean file) + 1; the noisy pair re-uses the clean pair's offset (:62-63).
+    Native streaming merge (tg_merge_csv): rows are copied as text, so no number is re-rounded.  Raises
+    TrajgenError("File not found: ...") like the script's check (:23-27).  -> dict(id_offset, rows_clean, rows_noisy)."""
+    L = _lib.load()
+    off, rows_c, rows_n = _lib.i64(), _lib.i64(), _lib.i64()
+    _lib.check(L.tg_merge_csv(str(first_clean).encode(), str(second_clean).encode(), str(out_clean).encode(), -1,
+                              ctypes.byref(off), ctypes.byref(rows_c)))
+    if first_noisy is not None:
+        _lib.check(L.tg_merge_csv(str(first_noisy).encode(), str(second_noisy).encode(), str(out_noisy).encode(), off.value,
+                                  None, ctypes.byref(rows_n)))
+    return {"id_offset": off.value, "rows_clean": rows_c.value, "rows_noisy": rows_n.value}
+
+
 def to_loader_tensors(result, T_steps):
     """The arrays KalmanNet/data_loader.py:33-53 would build from the CSVs, without the CSV round trip:
     y[B,5,T] noisy (X,Y,vx,vy,omega), u[B,2,T], x[B,6,T] clean; float32."""
