@@ -268,6 +268,46 @@ __device__ __forceinline__ void tg_plant_step_lanes(const DevCfg &c, double x[6]
     }
 }
 
+// Plant step of the generator plants (TG_PLANT_GEN1 / GEN2) by ONE thread, for the open-loop kernels where a thread owns
+// a trajectory.  vx_eff = max(|vx|, vx_zero) > 0 there (generation_type1.py:41), so atan2(y, vx_eff) = atan(y / vx_eff),
+// and the tyre curve comes from the handle's table wherever the slip angle lies inside the clamp interval (always for
+// the front tyre and for GEN2's rear tyre; GEN1 leaves the rear angle free, :46, and falls back to atan / sin outside).
+__device__ __forceinline__ void tg_plant_step_gen(const DevCfg &c, double x[6], double d, double delta)
+{
+    const double *__restrict__ p = c.p;
+    const double vx = x[3], vy = x[4], om = x[5];
+    const double ma = p[P_maxAlpha];
+    const double vmag = fmax(fabs(vx), p[P_vx_zero]);
+    const double af = tg_clamp(delta - tg_atan((om * p[P_lf] + vy) / vmag), -ma, ma);
+    double ar = tg_atan((om * p[P_lr] - vy) / vmag);
+    if (c.plant != TG_PLANT_GEN1) ar = tg_clamp(ar, -ma, ma);
+    double gf, gr, dg;
+    if (c.tyre_tab) {
+        tg_tyre_tab(c.tyre_tab, af, ma, c.tab_scale, gf, dg);
+        if (fabs(ar) <= ma) tg_tyre_tab(c.tyre_tab + TG_TAB_NI * TG_TAB_NC, ar, ma, c.tab_scale, gr, dg);
+        else gr = tg_sin(p[P_Cr] * tg_atan(p[P_Br] * ar));
+    } else {
+        gf = tg_sin(p[P_Cf] * tg_atan(p[P_Bf] * af));
+        gr = tg_sin(p[P_Cr] * tg_atan(p[P_Br] * ar));
+    }
+    const double Fyf = p[P_Df] * gf, Fyr = p[P_Dr] * gr;
+    const double Frx = (p[P_Cm1] - p[P_Cm2] * vmag) * d - p[P_Cr0] - p[P_Cr2] * (vmag * vmag);
+    double sd, cd, sp, cp;
+    TG_SINCOS(delta, sd, cd);
+    TG_SINCOS(x[2], sp, cp);
+    const double m = p[P_m], Ts = c.Ts;
+    const double f0 = vx * cp - vy * sp, f1 = vx * sp + vy * cp;
+    const double f3 = (Frx - Fyf * sd + m * vy * om) / m;
+    const double f4 = (Fyr + Fyf * cd - m * vx * om) / m;
+    const double f5 = (Fyf * p[P_lf] * cd - Fyr * p[P_lr]) / p[P_Iz];
+    x[0] = x[0] + Ts * f0;
+    x[1] = x[1] + Ts * f1;
+    x[2] = x[2] + Ts * om;
+    x[3] = fmax(x[3] + Ts * f3, 0.0);                 // generation_type1.py:81-82
+    x[4] = x[4] + Ts * f4;
+    x[5] = tg_clamp(x[5] + Ts * f5, -6.0, 6.0);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Compact linearisation record of one stage.  For every variant and both Jacobian modes the full
 // 6x6 / 6x2 matrices have this sparsity exactly (f does not depend on X,Y; phi enters rows 0,1 only;
@@ -544,16 +584,12 @@ __device__ __forceinline__ void tg_sincos_2pi_u(uint32_t r, double &sn, double &
     pc = __fma_rn(pc, a2, 1.0 / 24.0);
     pc = __fma_rn(pc, a2, -0.5);
     const double ck = __fma_rn(pc, a2, 1.0);
-    switch (oct) {
-        case 0: sn = sk; cs = ck; break;
-        case 1: sn = ck; cs = sk; break;
-        case 2: sn = ck; cs = -sk; break;
-        case 3: sn = sk; cs = -ck; break;
-        case 4: sn = -sk; cs = -ck; break;
-        case 5: sn = -ck; cs = -sk; break;
-        case 6: sn = -ck; cs = sk; break;
-        default: sn = -sk; cs = ck; break;
-    }
+    // octant symmetries without a branch (lanes of a warp hold different octants): sin takes the cosine kernel in
+    // octants 1,2,5,6; sin < 0 in octants 4-7; cos < 0 in octants 2-5.  Same values as an 8-way switch.
+    const bool swap = ((oct + 1u) & 2u) != 0u;
+    const double s0 = swap ? ck : sk, c0 = swap ? sk : ck;
+    sn = (oct & 4u) ? -s0 : s0;
+    cs = ((oct + 2u) & 4u) ? -c0 : c0;
 }
 
 __device__ __forceinline__ void tg_box_muller(uint32_t r0, uint32_t r1, double &n0, double &n1)

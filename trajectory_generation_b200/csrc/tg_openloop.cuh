@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(32 * TG_OL_WARPS) tg_openloop_kernel(const __g
                 }
                 col[6 * TG_OL_STRIDE] = d_cmd;
                 col[7 * TG_OL_STRIDE] = delta_cmd;
-                tg_plant_step(c, x, d_cmd, delta_cmd);
+                if (c.plant == TG_PLANT_MPC) tg_plant_step(c, x, d_cmd, delta_cmd);
+                else tg_plant_step_gen(c, x, d_cmd, delta_cmd);
             }
         }
         __syncwarp();

@@ -282,7 +282,8 @@ __global__ void tg_plant_kernel(const __grid_constant__ DevCfg c, int B, int T, 
     double *Xo = X + (size_t)b * (T + 1) * 6;
     for (int i = 0; i < 6; ++i) { xs[i] = x0[6 * (size_t)b + i]; Xo[i] = xs[i]; }
     for (int t = 0; t < T; ++t) {
-        tg_plant_step(c, xs, U[((size_t)b * T + t) * 2], U[((size_t)b * T + t) * 2 + 1]);
+        if (c.plant == TG_PLANT_MPC) tg_plant_step(c, xs, U[((size_t)b * T + t) * 2], U[((size_t)b * T + t) * 2 + 1]);
+        else tg_plant_step_gen(c, xs, U[((size_t)b * T + t) * 2], U[((size_t)b * T + t) * 2 + 1]);
         for (int i = 0; i < 6; ++i) Xo[6 * (size_t)(t + 1) + i] = xs[i];
     }
 }
