@@ -223,6 +223,22 @@ int tg_openloop_type1_host(tg_handle *h, int B, int T, const double *x0, const t
 int tg_openloop_type2_host(tg_handle *h, int B, int T, const double *x0, const tg_type2_rules *rules, uint64_t ctrl_seed_base,
                            int64_t traj_id0, double *clean, double *noisy, double *U, int8_t *modes);
 
+/* ---- estimator-side physics: KalmanNet's prior step, fused.  DEVICE pointers (e.g. the
+ * data_ptr() of torch CUDA tensors), dtype 0 = fp64, 1 = fp32 (torch's default, what the reference runs in); Ts and the
+ * vehicle parameters come from the handle, the data-set limits (Params["x_min"] ... ["omega_max"],
+ * KalmanNet/training.py:60-90) from `lim`. */
+typedef struct tg_state_limits { double lo[6], hi[6]; } tg_state_limits;
+/* VehicleModel.f, KalmanNet/vehicle_model.py:109-134 (with pt_f_cont :43-79): x[B][6], u[B][2] -> x_next[B][6] */
+int tg_estimator_step(tg_handle *h, int B, int dtype, const void *x, const void *u, const tg_state_limits *lim, void *x_next);
+/* its vector-Jacobian product as torch.autograd computes it: grad_x[B][6] = (d x_next / d x)^T grad_next, grad_u[B][2]
+ * likewise (either may be NULL) -- lets the fused step sit inside KalmanNet's back-propagation through time */
+int tg_estimator_step_vjp(tg_handle *h, int B, int dtype, const void *x, const void *u, const tg_state_limits *lim,
+                          const void *grad_next, void *grad_x, void *grad_u);
+/* rollout_open_loop, KalmanNet/test_prediction.py:68-87: x0[B][6], U[B][2][T_u] -> preds[B][6][Hn] with
+ * Hn = min(H, T_u - t_start) (returned in *H_out; the caller sizes preds for H) */
+int tg_estimator_rollout(tg_handle *h, int B, int dtype, int T_u, int t_start, int H, const void *x0, const void *U,
+                         const tg_state_limits *lim, void *preds, int32_t *H_out);
+
 /* host-side dataset writer -- replaces the DataFrame concat + to_csv of generation_type1.py:315-339 /
  * generation_type2.py:202-218,309-322.  HOST pointers clean[B][T+1][6], noisy[B][T+1][6], U[B][T][2]; writes the
  * clean file (with phi) and the noisy file (without), byte-identical to pandas' output for the same numbers

@@ -33,6 +33,11 @@ def golden_openloop():
 
 
 @pytest.fixture(scope="session")
+def golden_estimator():
+    return np.load(os.path.join(GOLDEN, "reference_estimator.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_loop():
     return np.load(os.path.join(GOLDEN, "oracle_closed_loop.npz"))
 

@@ -153,6 +153,44 @@ def reference_openloop_fixtures():
     print("reference open-loop fixtures written")
 
 
+def reference_estimator_fixtures():
+    """Outputs + autograd gradients of the reference's own KalmanNet/vehicle_model.py (VehicleModel.f) and of
+    rollout_open_loop (KalmanNet/test_prediction.py:68-87, whose module body runs an evaluation, so the function's
+    source is compiled on its own) -> reference_estimator.npz, in fp32 and fp64."""
+    import inspect, re, torch
+    vm = refload._import_from("KalmanNet", "vehicle_model")
+    src = open(os.path.join(refload.REFERENCE_ROOT, "KalmanNet", "test_prediction.py")).read()
+    m = re.search(r"@torch.no_grad\(\)\ndef rollout_open_loop.*?\n(?=def )", src, flags=re.S)
+    ns = {"torch": torch}
+    exec(compile(m.group(0), "rollout_open_loop", "exec"), ns)
+    rng = np.random.default_rng(5)
+    B = 96
+    lo = np.array([-3.0, -3.0, -3.2, 0.05, -0.4, -5.0]); hi = np.array([3.0, 3.0, 3.2, 2.2, 0.4, 5.0])
+    X = np.stack([rng.uniform(-3.5, 3.5, B), rng.uniform(-3.5, 3.5, B), rng.uniform(-3.5, 3.5, B), rng.uniform(-0.2, 2.6, B),
+                  rng.uniform(-0.5, 0.5, B), rng.uniform(-6, 6, B)], axis=1)
+    U = np.stack([rng.uniform(-1, 1, B), rng.uniform(-0.6, 0.6, B)], axis=1)
+    G = rng.normal(size=(B, 6))
+    out = {"lo": lo, "hi": hi, "X": X, "U": U, "G": G, "Ts": np.array(0.01)}
+    T, H, t0 = 40, 25, 20
+    Useq = np.stack([np.clip(0.25 + 0.1 * rng.normal(size=(8, T)), -1, 1), 0.05 * rng.normal(size=(8, T))], axis=1)   # [8,2,T]
+    out["Useq"], out["roll_meta"] = Useq, np.array([T, H, t0])
+    for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        prm = dict(vm.Params)
+        for i, k in enumerate(("x", "y", "phi", "vx", "vy", "omega")):
+            prm[k + "_min"], prm[k + "_max"] = float(lo[i]), float(hi[i])
+        model = vm.VehicleModel(0.01, 10, 10, None, None, None, None)
+        model.Params = prm
+        x = torch.tensor(X, dtype=dt, requires_grad=True); u = torch.tensor(U, dtype=dt, requires_grad=True)
+        y = model.f(x.unsqueeze(2), u.unsqueeze(2)).squeeze(2)
+        y.backward(torch.tensor(G, dtype=dt))
+        out[f"next_{name}"], out[f"gx_{name}"], out[f"gu_{name}"] = y.detach().numpy(), x.grad.numpy(), u.grad.numpy()
+        out[f"h_{name}"] = model.h(x.detach().unsqueeze(2)).squeeze(2).numpy()
+        x0 = torch.tensor(X[:8], dtype=dt).unsqueeze(2)
+        out[f"roll_{name}"] = ns["rollout_open_loop"](model, x0, torch.tensor(Useq, dtype=dt), t0, H).numpy()     # stops at T
+    np.savez_compressed(os.path.join(HERE, "reference_estimator.npz"), **out)
+    print("reference estimator fixtures written")
+
+
 def oracle_qp_fixtures():
     rng = np.random.default_rng(7)
     cases = []
@@ -205,5 +243,6 @@ if __name__ == "__main__":
         raise SystemExit("the reference tree is not mounted; fixtures can only be regenerated in the build container")
     reference_fixtures()
     reference_openloop_fixtures()
+    reference_estimator_fixtures()
     oracle_qp_fixtures()
     oracle_closed_loop_fixtures()

@@ -260,3 +260,28 @@ def test_philox_sources_keep_the_generators_contract():
         for k in change:
             assert not (m[k] >= 2 and m[k + 1] >= 2)                          # generation_type2.py:107-109
     assert (counts > 0).all()
+
+
+# ------------------------------------------------------------------ estimator physics
+def test_estimator_step_and_rollout_reproduce_reference(golden_estimator):
+    """oracle/estimator.py == KalmanNet's VehicleModel.f (values and autograd gradients) and rollout_open_loop, bit for bit."""
+    import torch
+    from oracle import estimator as oe
+    g = golden_estimator
+    p = oe.with_limits(g["lo"], g["hi"])
+    Ts = float(g["Ts"])
+    T, H, t0 = (int(v) for v in g["roll_meta"])
+    for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        x = torch.tensor(g["X"], dtype=dt, requires_grad=True)
+        u = torch.tensor(g["U"], dtype=dt, requires_grad=True)
+        y = oe.step(x, u, Ts, p)
+        y.backward(torch.tensor(g["G"], dtype=dt))
+        np.testing.assert_array_equal(y.detach().numpy(), g[f"next_{name}"])
+        np.testing.assert_array_equal(x.grad.numpy(), g[f"gx_{name}"])
+        np.testing.assert_array_equal(u.grad.numpy(), g[f"gu_{name}"])
+        r = oe.rollout(torch.tensor(g["X"][:8], dtype=dt), torch.tensor(g["Useq"], dtype=dt), t0, H, Ts, p)
+        assert r.shape == (8, 6, T - t0)                                    # the reference stops at the end of u
+        np.testing.assert_array_equal(r.numpy(), g[f"roll_{name}"])
+        np.testing.assert_array_equal(g[f"h_{name}"], g["X"].astype(g[f"h_{name}"].dtype)[:, [0, 1, 3, 4, 5]])
+    # the fixture exercises every clamp and the low-speed branch
+    assert (((g["X"] < g["lo"]) | (g["X"] > g["hi"])).sum(0) > 0).all() and (np.abs(g["X"][:, 3]) < 0.3).any()

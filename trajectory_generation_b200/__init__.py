@@ -14,5 +14,14 @@ from .generation import (ClosedLoopGenerator, Scenarios, d_steady_state, sample_
                          VREF_TRAPEZOID, VREF_SINE, X0_RANGES_TYPE1, X0_RANGES_TYPE2, CLEAN_COLS, NOISY_COLS)
 from .openloop import OpenLoopGenerator, type1_rules, type2_rules, TYPE1_MODES, TYPE2_MODES, CTRL_SEED_BASE
 
+
+def __getattr__(name):          # torch is imported only when the estimator mirror is asked for
+    if name in ("VehicleModel", "rollout_open_loop", "estimator"):
+        import importlib
+        mod = importlib.import_module(".estimator", __name__)
+        return mod if name == "estimator" else getattr(mod, name)
+    raise AttributeError(name)
+
+
 STATUS_STRINGS = _lib.STATUS_STRINGS
 __all__ = [n for n in dir() if not n.startswith("_")]

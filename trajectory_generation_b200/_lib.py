@@ -64,6 +64,10 @@ class TgType2Rules(ctypes.Structure):
     ]
 
 
+class TgStateLimits(ctypes.Structure):
+    _fields_ = [("lo", d * 6), ("hi", d * 6)]
+
+
 REF_SPEC_DTYPE = np.dtype([("path_kind", np.int32), ("vref_kind", np.int32), ("spline_first", np.int32),
                            ("spline_count", np.int32), ("path", np.float64, 4), ("vref", np.float64, 6)], align=True)
 assert REF_SPEC_DTYPE.itemsize == 96
@@ -73,7 +77,8 @@ EXPORTS = (
     "tg_last_error", "tg_version", "tg_default_config", "tg_create", "tg_destroy", "tg_set_stream", "tg_synchronize",
     "tg_kernel_launches", "tg_info", "tg_tyre_table_info", "tg_linearize", "tg_assemble", "tg_mpc_step", "tg_mpc_step_host", "tg_ref_window",
     "tg_closed_loop", "tg_closed_loop_host", "tg_default_type1_rules", "tg_default_type2_rules", "tg_openloop_type1",
-    "tg_openloop_type2", "tg_openloop_type1_host", "tg_openloop_type2_host", "tg_write_csv", "tg_merge_csv", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
+    "tg_openloop_type2", "tg_openloop_type1_host", "tg_openloop_type2_host", "tg_write_csv", "tg_merge_csv", "tg_estimator_step", "tg_estimator_step_vjp",
+    "tg_estimator_rollout", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
     "tg_device_count", "tg_malloc", "tg_free", "tg_memcpy_h2d", "tg_memcpy_d2h", "tg_malloc_host", "tg_free_host",
 )
 
@@ -133,6 +138,10 @@ def load():
             getattr(L, name + suffix).argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(rules), u64, i64, vp, vp, vp, vp]
     L.tg_write_csv.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, d, i64, vp, vp, vp, ctypes.c_int, ctypes.c_int]
     L.tg_merge_csv.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, i64, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    L.tg_estimator_step.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.POINTER(TgStateLimits), vp]
+    L.tg_estimator_step_vjp.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.POINTER(TgStateLimits), vp, vp, vp]
+    L.tg_estimator_rollout.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
+                                       ctypes.POINTER(TgStateLimits), vp, ctypes.POINTER(i32)]
     L.tg_plant_rollout.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
     L.tg_sensor_noise.argtypes = [vp, i64, ctypes.c_int, ctypes.c_int, vp]
     L.tg_philox_u32.argtypes = [vp, u64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, vp]

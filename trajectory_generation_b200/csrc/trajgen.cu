@@ -19,6 +19,7 @@
 
 #include "tg_solver.cuh"
 #include "tg_openloop.cuh"
+#include "tg_estimator.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
@@ -792,6 +793,82 @@ int tg_openloop_type2(tg_handle *h, int B, int T, const double *x0, const tg_typ
     for (int i = 0; i < 2; ++i) { if (!(r.p_after_turn[i] >= 0)) return fail(TG_ERR_INVALID, "type-2 rules: negative probability"); tot2 += r.p_after_turn[i]; }
     if (!(tot4 > 0) || !(tot2 > 0) || !(r.seg_s[0] > 0) || r.seg_s[1] < r.seg_s[0]) return fail(TG_ERR_INVALID, "type-2 rules: bad range");
     return openloop_launch<2>(h, B, T, x0, r, ctrl_seed_base, traj_id0, clean, noisy, U, modes);
+}
+
+// ---- estimator physics (tg_estimator.cuh)
+extern "C++" {
+template <typename T>
+static EstCfg<T> make_est_cfg(const tg_handle *h, const tg_state_limits *lim)
+{
+    EstCfg<T> e;
+    const double *p = h->cfg.params;
+    e.Ts = (T)h->cfg.Ts;
+    for (int i = 0; i < 6; ++i) { e.lo[i] = (T)lim->lo[i]; e.hi[i] = (T)lim->hi[i]; }
+    e.Cm1 = (T)p[P_Cm1]; e.Cm2 = (T)p[P_Cm2]; e.Cr0 = (T)p[P_Cr0]; e.Cr2 = (T)p[P_Cr2];
+    e.Br = (T)p[P_Br]; e.Cr = (T)p[P_Cr]; e.Dr = (T)p[P_Dr]; e.Bf = (T)p[P_Bf]; e.Cf = (T)p[P_Cf]; e.Df = (T)p[P_Df];
+    e.m = (T)p[P_m]; e.Iz = (T)p[P_Iz]; e.lf = (T)p[P_lf]; e.lr = (T)p[P_lr]; e.maxAlpha = (T)p[P_maxAlpha];
+    // KalmanNet/vehicle_model.py:26 builds the threshold as a float32 tensor whatever the state dtype
+    e.vx_zero = (T)(float)p[P_vx_zero];
+    return e;
+}
+}  // extern "C++"
+
+static int est_check(tg_handle *h, int B, int dtype, const tg_state_limits *lim)
+{
+    if (!h || B < 0 || !lim || (dtype != 0 && dtype != 1)) return fail(TG_ERR_INVALID, "bad argument (dtype: 0 = fp64, 1 = fp32)");
+    for (int i = 0; i < 6; ++i)
+        if (!(lim->lo[i] <= lim->hi[i])) return fail(TG_ERR_INVALID, "state limits: lo > hi");
+    return TG_OK;
+}
+
+int tg_estimator_step(tg_handle *h, int B, int dtype, const void *x, const void *u, const tg_state_limits *lim, void *x_next)
+{
+    int rc = est_check(h, B, dtype, lim);
+    if (rc != TG_OK) return rc;
+    if (B == 0) return TG_OK;
+    if (!x || !u || !x_next) return fail(TG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    const int blocks = (B + 127) / 128;
+    if (dtype == 0) tg_estimator_step_kernel<double><<<blocks, 128, 0, h->stream>>>(make_est_cfg<double>(h, lim), B, (const double *)x, (const double *)u, (double *)x_next);
+    else tg_estimator_step_kernel<float><<<blocks, 128, 0, h->stream>>>(make_est_cfg<float>(h, lim), B, (const float *)x, (const float *)u, (float *)x_next);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_estimator_step_vjp(tg_handle *h, int B, int dtype, const void *x, const void *u, const tg_state_limits *lim,
+                          const void *grad_next, void *grad_x, void *grad_u)
+{
+    int rc = est_check(h, B, dtype, lim);
+    if (rc != TG_OK) return rc;
+    if (B == 0) return TG_OK;
+    if (!x || !u || !grad_next) return fail(TG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    const int blocks = (B + 127) / 128;
+    if (dtype == 0) tg_estimator_vjp_kernel<double><<<blocks, 128, 0, h->stream>>>(make_est_cfg<double>(h, lim), B, (const double *)x, (const double *)u, (const double *)grad_next, (double *)grad_x, (double *)grad_u);
+    else tg_estimator_vjp_kernel<float><<<blocks, 128, 0, h->stream>>>(make_est_cfg<float>(h, lim), B, (const float *)x, (const float *)u, (const float *)grad_next, (float *)grad_x, (float *)grad_u);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_estimator_rollout(tg_handle *h, int B, int dtype, int T_u, int t_start, int H, const void *x0, const void *U,
+                         const tg_state_limits *lim, void *preds, int32_t *H_out)
+{
+    int rc = est_check(h, B, dtype, lim);
+    if (rc != TG_OK) return rc;
+    if (T_u < 0 || t_start < 0 || H < 0) return fail(TG_ERR_INVALID, "bad argument");
+    const int Hn = std::max(0, std::min(H, T_u - t_start));       // test_prediction.py:79: stop at the end of u
+    if (H_out) *H_out = Hn;
+    if (B == 0 || Hn == 0) return TG_OK;
+    if (!x0 || !U || !preds) return fail(TG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    const int blocks = (B + 63) / 64;
+    if (dtype == 0) tg_estimator_rollout_kernel<double><<<blocks, 64, 0, h->stream>>>(make_est_cfg<double>(h, lim), B, T_u, t_start, Hn, (const double *)x0, (const double *)U, (double *)preds);
+    else tg_estimator_rollout_kernel<float><<<blocks, 64, 0, h->stream>>>(make_est_cfg<float>(h, lim), B, T_u, t_start, Hn, (const float *)x0, (const float *)U, (float *)preds);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return TG_OK;
 }
 
 int tg_philox_u32(tg_handle *h, uint64_t seed, uint32_t first, uint32_t block, int n, uint32_t *out)
