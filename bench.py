@@ -188,6 +188,43 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def measure_widened_rows(stream, hbm_peak):
+    """SURVEY.md 8(f) rows measured beside the headline (never part of `value`): the open-loop generator kernels
+    (rank 2; 65536 trajectories x 1200 steps, device-resident, CUDA events, L2 flushed) against the HBM roofline on their
+    algorithmic output bytes (112 B per trajectory-step)."""
+    import torch
+    import trajectory_generation_b200 as tg
+    out, launches = {}, 0
+    B, T = 65536, 1200
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for kind in ("type1", "type2"):
+        g = tg.OpenLoopGenerator(kind, Ts=TS)
+        g.set_stream(stream.cuda_stream)
+        x0 = torch.from_numpy(np.ascontiguousarray(np.tile(g.sample_x0(1024), (B // 1024, 1)))).cuda()
+        clean = torch.empty((B, T + 1, 6), dtype=torch.float64, device="cuda")
+        noisy, U = torch.empty_like(clean), torch.empty((B, T, 2), dtype=torch.float64, device="cuda")
+        ms = []
+        with torch.cuda.stream(stream):
+            for rep in range(5):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                g.generate_device(x0.data_ptr(), B, T, clean.data_ptr(), noisy.data_ptr(), U.data_ptr(), None)
+                e1.record(stream)
+                e1.synchronize()
+                launches += 1
+                if rep >= 2:
+                    ms.append(e0.elapsed_time(e1))
+        t = float(np.mean(ms)) * 1e-3
+        nbytes = B * (T + 1) * 96 + B * T * 16 + B * 48
+        out[f"openloop_{kind}"] = {"kernel": f"tg_openloop_kernel<{kind}>", "trajectory_steps_per_s": B * T / t, "kernel_ms": t * 1e3,
+                                  "batch": B, "T": T, "roofline": {"bound": "hbm", "achieved": nbytes / t / 1e9, "peak": hbm_peak,
+                                                                   "unit": "GB/s", "frac": nbytes / t / 1e9 / hbm_peak}}
+        g.close()
+        del clean, noisy, U
+    return out, launches
+
+
 def run_gpu(args, rank, world, local_rank):
     import ctypes
     import torch
@@ -341,6 +378,13 @@ def run_gpu(args, rank, world, local_rank):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_closed_loop_traffic.json"))).get("dram_bytes_per_launch")
         except Exception:
             pass
+        widened = None
+        if not args.no_extra:
+            try:
+                widened, n_l = measure_widened_rows(stream, hbm_peak)
+                gpu_launches += n_l
+            except Exception as e:          # never let a side measurement take the headline line down
+                widened = {"error": repr(e)}
         cores = os.cpu_count() or 1
         cb_traj, cb_steps = cores, 60
         cb_val, cb_info = (0.0, {"skipped": True}) if args.no_cpu else cpu_baseline(cb_traj, cb_steps, cores)
@@ -370,6 +414,7 @@ def run_gpu(args, rank, world, local_rank):
             "cpu_baseline": {"value": cb_val, "unit": "MPC steps/s", "cores": cores, "kind": "port",
                              "sample": f"{cb_traj} trajectories x {cb_steps} closed-loop steps of the same workload, one process per core", **cb_info},
             "clocks": clocks,
+            "widened_rows": widened,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -387,6 +432,7 @@ def main():
     ap.add_argument("--horizon-steps", type=int, default=1200, help="closed-loop steps T per trajectory")
     ap.add_argument("--check-every", type=int, default=0, help="override the ADMM termination-check interval (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (development runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements of the widened rows (open-loop generators)")
     ap.add_argument("--solver-opt", action="append", default=[], help="development: key=value override of a tg_config solver field")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
