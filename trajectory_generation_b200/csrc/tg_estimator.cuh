@@ -24,6 +24,29 @@ template <> struct EstMath<float> {
     static __device__ __forceinline__ void sincos_(float x, float &s, float &c) { sincosf(x, &s, &c); }
 };
 
+// 2-wide vector access: rows of 6 (state) and 2 (input) values are 8-byte (fp32) / 16-byte (fp64) aligned pairs
+template <typename T> struct EstVec;
+template <> struct EstVec<double> { using V2 = double2; };
+template <> struct EstVec<float> { using V2 = float2; };
+template <typename T> __device__ __forceinline__ void est_load6(const T *__restrict__ p, T v[6])
+{
+    using V2 = typename EstVec<T>::V2;
+    const V2 a = __ldg(reinterpret_cast<const V2 *>(p)), b = __ldg(reinterpret_cast<const V2 *>(p) + 1), c = __ldg(reinterpret_cast<const V2 *>(p) + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+}
+template <typename T> __device__ __forceinline__ void est_load2(const T *__restrict__ p, T &a, T &b)
+{
+    using V2 = typename EstVec<T>::V2;
+    const V2 v = __ldg(reinterpret_cast<const V2 *>(p));
+    a = v.x; b = v.y;
+}
+template <typename T> __device__ __forceinline__ void est_store2(T *__restrict__ p, T a, T b)
+{
+    using V2 = typename EstVec<T>::V2;
+    V2 v; v.x = a; v.y = b;
+    *reinterpret_cast<V2 *>(p) = v;
+}
+
 template <typename T>
 struct EstCfg {
     T Ts, lo[6], hi[6];
@@ -86,13 +109,14 @@ __global__ void tg_estimator_step_kernel(const __grid_constant__ EstCfg<T> c, in
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    T xs[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) xs[i] = x[6 * (size_t)b + i];
+    T xs[6], d, delta;
+    est_load6(x + 6 * (size_t)b, xs);
+    est_load2(u + 2 * (size_t)b, d, delta);
     EstFwd<T> w;
-    est_forward(c, xs, u[2 * (size_t)b], u[2 * (size_t)b + 1], w);
+    est_forward(c, xs, d, delta, w);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) out[6 * (size_t)b + i] = est_clamp(w.pre[i], c.lo[i], c.hi[i]);   // :124-130
+    for (int i = 0; i < 6; i += 2)                                                                  // :124-130
+        est_store2(out + 6 * (size_t)b + i, est_clamp(w.pre[i], c.lo[i], c.hi[i]), est_clamp(w.pre[i + 1], c.lo[i + 1], c.hi[i + 1]));
 }
 
 // grad_x = J_x^T g, grad_u = J_u^T g of the map (x, u) -> VehicleModel.f(x, u), as torch.autograd differentiates it
@@ -102,14 +126,14 @@ __global__ void tg_estimator_vjp_kernel(const __grid_constant__ EstCfg<T> c, int
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    T xs[6], go[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) xs[i] = x[6 * (size_t)b + i];
-    const T d = u[2 * (size_t)b], delta = u[2 * (size_t)b + 1];
+    T xs[6], go[6], d, delta;
+    est_load6(x + 6 * (size_t)b, xs);
+    est_load6(g + 6 * (size_t)b, go);
+    est_load2(u + 2 * (size_t)b, d, delta);
     EstFwd<T> w;
     est_forward(c, xs, d, delta, w);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) go[i] = g[6 * (size_t)b + i] * est_inside(w.pre[i], c.lo[i], c.hi[i]);   // output clamps
+    for (int i = 0; i < 6; ++i) go[i] *= est_inside(w.pre[i], c.lo[i], c.hi[i]);   // output clamps
     const T gf0 = c.Ts * go[0], gf1 = c.Ts * go[1], gf2 = c.Ts * go[2], gf3 = c.Ts * go[3], gf4 = c.Ts * go[4], gf5 = c.Ts * go[5];
     const T im = T(1) / c.m, iI = T(1) / c.Iz;
     T g_phi = gf0 * (-w.vx * w.sp - w.vy * w.cp) + gf1 * (w.vx * w.cp - w.vy * w.sp);
@@ -136,14 +160,13 @@ __global__ void tg_estimator_vjp_kernel(const __grid_constant__ EstCfg<T> c, int
     const T sel = avx > c.vx_zero ? T(1) : (avx == c.vx_zero ? T(0.5) : T(0));
     g_vx += g_ve * sel * (w.vx > T(0) ? T(1) : (w.vx < T(0) ? T(-1) : T(0)));
     if (gx) {
-        gx[6 * (size_t)b + 0] = go[0];
-        gx[6 * (size_t)b + 1] = go[1];
-        gx[6 * (size_t)b + 2] = go[2] + g_phi * est_inside(xs[2], c.lo[2], c.hi[2]);      // input clamps of pt_f_cont
-        gx[6 * (size_t)b + 3] = go[3] + g_vx * est_inside(xs[3], c.lo[3], c.hi[3]);
-        gx[6 * (size_t)b + 4] = go[4] + g_vy * est_inside(xs[4], c.lo[4], c.hi[4]);
-        gx[6 * (size_t)b + 5] = go[5] + g_om * est_inside(xs[5], c.lo[5], c.hi[5]);
+        est_store2(gx + 6 * (size_t)b, go[0], go[1]);
+        est_store2(gx + 6 * (size_t)b + 2, go[2] + g_phi * est_inside(xs[2], c.lo[2], c.hi[2]),     // input clamps of pt_f_cont
+                   go[3] + g_vx * est_inside(xs[3], c.lo[3], c.hi[3]));
+        est_store2(gx + 6 * (size_t)b + 4, go[4] + g_vy * est_inside(xs[4], c.lo[4], c.hi[4]),
+                   go[5] + g_om * est_inside(xs[5], c.lo[5], c.hi[5]));
     }
-    if (gu) { gu[2 * (size_t)b] = g_d; gu[2 * (size_t)b + 1] = g_delta; }
+    if (gu) est_store2(gu + 2 * (size_t)b, g_d, g_delta);
 }
 
 // rollout_open_loop: preds[b][:, k] = f(preds[b][:, k-1], U[b][:, t_start + k]) for k < Hn; U is [B][2][T_u], preds [B][6][Hn]

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <new>
 #include <string>
 #include <vector>
@@ -813,6 +814,14 @@ static EstCfg<T> make_est_cfg(const tg_handle *h, const tg_state_limits *lim)
 }
 }  // extern "C++"
 
+static bool est_aligned(int dtype, std::initializer_list<const void *> ptrs)
+{
+    const uintptr_t mask = dtype == 0 ? 15 : 7;      // the kernels move pairs of values
+    for (const void *p : ptrs)
+        if ((uintptr_t)p & mask) return false;
+    return true;
+}
+
 static int est_check(tg_handle *h, int B, int dtype, const tg_state_limits *lim)
 {
     if (!h || B < 0 || !lim || (dtype != 0 && dtype != 1)) return fail(TG_ERR_INVALID, "bad argument (dtype: 0 = fp64, 1 = fp32)");
@@ -827,6 +836,7 @@ int tg_estimator_step(tg_handle *h, int B, int dtype, const void *x, const void 
     if (rc != TG_OK) return rc;
     if (B == 0) return TG_OK;
     if (!x || !u || !x_next) return fail(TG_ERR_INVALID, "null argument");
+    if (!est_aligned(dtype, {x, u, x_next})) return fail(TG_ERR_INVALID, "buffers must be aligned to two elements (8 B fp32 / 16 B fp64)");
     CK(cudaSetDevice(h->device));
     const int blocks = (B + 127) / 128;
     if (dtype == 0) tg_estimator_step_kernel<double><<<blocks, 128, 0, h->stream>>>(make_est_cfg<double>(h, lim), B, (const double *)x, (const double *)u, (double *)x_next);
@@ -843,6 +853,7 @@ int tg_estimator_step_vjp(tg_handle *h, int B, int dtype, const void *x, const v
     if (rc != TG_OK) return rc;
     if (B == 0) return TG_OK;
     if (!x || !u || !grad_next) return fail(TG_ERR_INVALID, "null argument");
+    if (!est_aligned(dtype, {x, u, grad_next, grad_x, grad_u})) return fail(TG_ERR_INVALID, "buffers must be aligned to two elements (8 B fp32 / 16 B fp64)");
     CK(cudaSetDevice(h->device));
     const int blocks = (B + 127) / 128;
     if (dtype == 0) tg_estimator_vjp_kernel<double><<<blocks, 128, 0, h->stream>>>(make_est_cfg<double>(h, lim), B, (const double *)x, (const double *)u, (const double *)grad_next, (double *)grad_x, (double *)grad_u);

@@ -30,7 +30,8 @@ def _dtype_code(t):
 def _cuda_contig(t, name):
     if not t.is_cuda:
         raise _lib.TrajgenError(f"{name} must be a CUDA tensor: the B200 path has no CPU fallback")
-    return t.contiguous()
+    t = t.contiguous()
+    return t.clone() if t.data_ptr() % 16 else t          # the kernels move 2-element vectors
 
 
 class _StepFn(torch.autograd.Function):
@@ -46,7 +47,7 @@ class _StepFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, u = ctx.saved_tensors
-        g = g.contiguous()
+        g = _cuda_contig(g, "grad")
         gx, gu = torch.empty_like(x), torch.empty_like(u)
         ctx.model._call("tg_estimator_step_vjp", x, x.shape[0], _dtype_code(x), x.data_ptr(), u.data_ptr(), ctx.model._limits(),
                         g.data_ptr(), gx.data_ptr(), gu.data_ptr())
