@@ -30,12 +30,18 @@ def _worker(rank, world, port, ret):
     u0 = np.zeros((B, 2))
     lo, hi, local = tgd.generate_sharded(_fake_generate, x0, u0, [None] * B, T, rank, world)
     out = tgd.gather_results(local, lo, hi, B, dist)
+
+    class FakeOpenLoop:          # stand-in for OpenLoopGenerator: same generate(x0, T, traj_id0) contract
+        def generate(self, x0_, T_, traj_id0=0):
+            return _fake_generate(x0_, None, None, T_, traj_id0)
+    lo2, hi2, local2 = tgd.generate_openloop_sharded(FakeOpenLoop(), x0, T, rank, world)
+    out2 = tgd.gather_results(local2, lo2, hi2, B, dist)
     if rank == 0:
         full = _fake_generate(x0, u0, None, T, 0)
-        ret["ok"] = all(np.array_equal(out[k], full[k]) for k in full)
+        ret["ok"] = all(np.array_equal(out[k], full[k]) for k in full) and all(np.array_equal(out2[k], full[k]) for k in full)
         ret["shapes"] = {k: out[k].shape for k in out}
     else:
-        ret["other"] = out is None
+        ret["other"] = out is None and out2 is None
     dist.barrier()
     dist.destroy_process_group()
 

@@ -25,6 +25,13 @@ def generate_sharded(generate_fn, x0, u0, scenarios, T, rank=0, world_size=1):
     return lo, hi, generate_fn(x0[lo:hi], u0[lo:hi], sc, T, lo)
 
 
+def generate_openloop_sharded(generator, x0, T, rank=0, world_size=1):
+    """The open-loop generator modes (OpenLoopGenerator.generate) on this rank's id block; control and noise streams are
+    keyed by the global trajectory id, so the union over ranks equals the single-GPU result.  Returns (lo, hi, local_result)."""
+    lo, hi = shard_range(len(x0), rank, world_size)
+    return lo, hi, generator.generate(x0[lo:hi], T, traj_id0=lo)
+
+
 def gather_results(local, lo, hi, num_traj, dist=None, dst=0, device=None):
     """Final gather of per-rank result dicts (arrays with leading dimension = local trajectories) onto
     rank ``dst`` in global id order.  ``dist`` = torch.distributed (initialised) or None for one process.
