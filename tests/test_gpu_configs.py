@@ -138,3 +138,37 @@ def test_config5_sharding_is_invariant_and_contiguous(tmp_path):
     tg.write_csv(full, Ts, tmp_path / "c1.csv", tmp_path / "n1.csv")
     assert open(tmp_path / "c.csv").read() == open(tmp_path / "c1.csv").read()
     assert open(tmp_path / "n.csv").read() == open(tmp_path / "n1.csv").read()
+
+
+def test_closed_loop_host_direct_pinned_output_equals_staged():
+    """tg_closed_loop_host stores the rows straight into pinned result buffers (no D2H copy after the kernel); pageable
+    buffers go through the staging arena.  Same bits either way."""
+    import ctypes
+    from trajectory_generation_b200 import _lib
+    L = _lib.load()
+    B, T = 96, 50
+    gen = tg.ClosedLoopGenerator(N=20, Ts=0.01, plant=tg.PLANT_GEN2)
+    x0 = tg.sample_x0(B, seed=5); x0[:, 1:3] = 0.0; x0[:, 3] += 0.4
+    u0 = np.stack([tg.d_steady_state(x0[:, 3]), np.zeros(B)], 1)
+    sc = tg.Scenarios(B); sc.set_sine(slice(0, B, 2), A=0.3, k=0.6)
+    staged = gen.generate(x0, u0, sc, T)                                   # numpy (pageable) result buffers
+    shapes = {"clean": (B, T + 1, 6), "noisy": (B, T + 1, 6), "U": (B, T, 2)}
+    ptrs, views = {}, {}
+    for k, shp in shapes.items():
+        p = ctypes.c_void_p()
+        _lib.check(L.tg_malloc_host(ctypes.byref(p), int(np.prod(shp)) * 8))
+        ptrs[k] = p
+        views[k] = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_double)), shape=shp)
+        views[k][...] = -7.0
+    scnt = np.zeros((B, 6), np.int32); its = np.zeros(B, np.int64)
+    spec = np.ascontiguousarray(sc.spec)
+    try:
+        _lib.check(L.tg_closed_loop_host(gen.handle, B, T, _lib.ptr(x0), _lib.ptr(u0), spec.ctypes.data, None, 0, None, 0, 0,
+                                         ptrs["clean"], ptrs["noisy"], ptrs["U"], _lib.ptr(scnt), _lib.ptr(its)))
+        for k in shapes:
+            np.testing.assert_array_equal(views[k], staged[k])
+        np.testing.assert_array_equal(scnt, staged["status_counts"])
+        np.testing.assert_array_equal(its, staged["iters_total"])
+    finally:
+        for p in ptrs.values():
+            L.tg_free_host(p)

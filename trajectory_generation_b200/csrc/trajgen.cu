@@ -992,6 +992,14 @@ int tg_mpc_step_host(tg_handle *h, int B, const double *x0, const double *u_prev
     return TG_OK;
 }
 
+// device alias of a pinned (cudaHostAlloc'ed / registered) host buffer, or null for pageable memory
+static void *pinned_device_alias(const void *p)
+{
+    cudaPointerAttributes at;
+    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 int tg_closed_loop_host(tg_handle *h, int B, int T, const double *x0, const double *u0, const tg_ref_spec *spec,
                         const double *brk, int64_t n_breaks, const double *coef, int64_t n_coef, int64_t traj_id0,
                         double *clean, double *noisy, double *U, int32_t *status_counts, int64_t *iters_total)
@@ -1003,14 +1011,25 @@ int tg_closed_loop_host(tg_handle *h, int B, int T, const double *x0, const doub
     const size_t s_x0 = (size_t)B * 6 * b8, s_u0 = (size_t)B * 2 * b8, s_sp = (size_t)B * sizeof(tg_ref_spec);
     const size_t s_bk = (size_t)(n_breaks > 0 ? n_breaks : 0) * b8, s_cf = (size_t)(n_coef > 0 ? n_coef : 0) * 4 * b8;
     const size_t s_cl = (size_t)B * (T + 1) * 6 * b8, s_U = (size_t)B * T * 2 * b8, s_sc = (size_t)B * TG_NUM_STATUS * 4, s_it = (size_t)B * 8;
-    const size_t total = PAD(s_x0) + PAD(s_u0) + PAD(s_sp) + PAD(s_bk) + PAD(s_cf) + 2 * PAD(s_cl) + PAD(s_U) + PAD(s_sc) + PAD(s_it) + 4096;
+    // Rows leave the SM at ~1 GB/s (112 B per MPC step), far below what PCIe carries, so when the caller's result buffers
+    // are pinned the kernel stores straight into them (posted writes overlap the computation) and the device-to-host copy
+    // of the rows after the kernel disappears.  Pageable buffers are staged through the device arena.
+    // TRAJGEN_HOST_OUTPUT=staged forces the staged path (measurement knob).
+    const char *mode = getenv("TRAJGEN_HOST_OUTPUT");
+    const bool allow_direct = !(mode && strcmp(mode, "staged") == 0);
+    double *a_cl = allow_direct ? (double *)pinned_device_alias(clean) : nullptr;
+    double *a_no = allow_direct ? (double *)pinned_device_alias(noisy) : nullptr;
+    double *a_U = allow_direct ? (double *)pinned_device_alias(U) : nullptr;
+    const bool direct = a_cl && a_no && (a_U || !s_U);
+    const size_t total = PAD(s_x0) + PAD(s_u0) + PAD(s_sp) + PAD(s_bk) + PAD(s_cf) + (direct ? 0 : 2 * PAD(s_cl) + PAD(s_U)) + PAD(s_sc) + PAD(s_it) + 4096;
     int rc = ensure_dstage(h, total);
     if (rc != TG_OK) return rc;
     Arena ar{(char *)h->dstage, 0, h->dstage_bytes};
     double *d_x0 = (double *)ar.take(s_x0), *d_u0 = (double *)ar.take(s_u0);
     tg_ref_spec *d_sp = (tg_ref_spec *)ar.take(s_sp);
     double *d_bk = s_bk ? (double *)ar.take(s_bk) : nullptr, *d_cf = s_cf ? (double *)ar.take(s_cf) : nullptr;
-    double *d_cl = (double *)ar.take(s_cl), *d_no = (double *)ar.take(s_cl), *d_U = (double *)ar.take(s_U ? s_U : 8);
+    double *d_cl = direct ? a_cl : (double *)ar.take(s_cl), *d_no = direct ? a_no : (double *)ar.take(s_cl);
+    double *d_U = direct ? a_U : (double *)ar.take(s_U ? s_U : 8);
     int32_t *d_sc = (int32_t *)ar.take(s_sc);
     long long *d_it = (long long *)ar.take(s_it);
     H2D(d_x0, x0, s_x0); H2D(d_u0, u0, s_u0); H2D(d_sp, spec, s_sp);
@@ -1018,8 +1037,10 @@ int tg_closed_loop_host(tg_handle *h, int B, int T, const double *x0, const doub
     if (s_cf) H2D(d_cf, coef, s_cf);
     rc = tg_closed_loop(h, B, T, d_x0, d_u0, d_sp, d_bk, d_cf, traj_id0, d_cl, d_no, d_U, d_sc, (int64_t *)d_it);
     if (rc != TG_OK) return rc;
-    D2H(clean, d_cl, s_cl); D2H(noisy, d_no, s_cl);
-    if (s_U) D2H(U, d_U, s_U);
+    if (!direct) {
+        D2H(clean, d_cl, s_cl); D2H(noisy, d_no, s_cl);
+        if (s_U) D2H(U, d_U, s_U);
+    }
     if (status_counts) D2H(status_counts, d_sc, s_sc);
     if (iters_total) D2H(iters_total, d_it, s_it);
     CK(cudaStreamSynchronize(h->stream));
