@@ -120,7 +120,8 @@ int tg_set_stream(tg_handle *h, void *cuda_stream);
 int tg_synchronize(tg_handle *h);
 int tg_kernel_launches(tg_handle *h, int64_t *count); /* kernels launched through this handle so far */
 /* launch geometry the handle chose: resident CTAs per SM, threads per CTA (= per problem), dynamic shared memory per CTA, SM count */
-/* the tyre-curve table of this handle: whether the kernels use it, and its largest deviation
+/* the tyre-curve table of this handle: whether the kernels use it (in_use bit 0; bit 1 = the
+ * slip-angle atan table is in use as well), and its largest deviation
  * from libm (value of sin(C atan(B alpha)), slope) on the check grid of tg_create */
 int tg_tyre_table_info(tg_handle *h, int32_t *in_use, double *max_value_err, double *max_slope_err);
 int tg_info(tg_handle *h, int32_t *ctas_per_sm, int32_t *threads_per_cta, int32_t *smem_bytes, int32_t *num_sms);

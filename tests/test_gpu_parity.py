@@ -382,7 +382,7 @@ def test_tyre_table_is_verified_and_optional(golden_physics, monkeypatch):
     g = golden_physics
     ctl = tg.BatchedMPC(N=20, Ts=0.02)
     info = ctl.tyre_table_info()
-    assert info["in_use"] and info["max_value_err"] < 4e-16 and info["max_slope_err"] < 1e-12
+    assert info["in_use"] and info["atan_in_use"] and info["max_value_err"] < 4e-16 and info["max_slope_err"] < 1e-12
     A1, B1, g1, x1 = ctl.linearize(g["XL"][:4], g["UL"][:4])
     monkeypatch.setenv("TRAJGEN_NO_TYRE_TABLE", "1")
     ctl2 = tg.BatchedMPC(N=20, Ts=0.02)

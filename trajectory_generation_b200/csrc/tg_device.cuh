@@ -16,6 +16,8 @@
 #define TG_LIN 28  // compact per-stage linearisation record (see lin_store)
 #define TG_TAB_NI 64   // intervals of the tyre-curve table
 #define TG_TAB_NC 10   // coefficients per interval (degree 9 in the local variable s in [-1, 1])
+#define TG_ATAN_NI 128 // intervals of the atan table on [-TG_ATAN_T0, TG_ATAN_T0]
+#define TG_ATAN_T0 4.0
 
 struct DevCfg {
     int N, n;         // horizon, 2N
@@ -31,6 +33,7 @@ struct DevCfg {
     double inv_m, inv_Iz;   // 1.0/m, 1.0/Iz (the MPC variant multiplies by them, MPC/mpc_6stati.py:67-69)
     const double *tyre_tab; // [2][TG_TAB_NI][TG_TAB_NC] piecewise polynomials of sin(C atan(B alpha)) on [-maxAlpha, maxAlpha], or null
     double tab_scale;       // TG_TAB_NI / (2 maxAlpha)
+    const double *atan_tab; // [TG_ATAN_NI][TG_TAB_NC] piecewise polynomials of atan on [-TG_ATAN_T0, TG_ATAN_T0], or null
     double q_c, q_phi, q_vx;
     double Rs[4], Rds[4];  // symmetric parts
     double u_lo[2], u_hi[2], du_lo[2], du_hi[2], x_lo[6], x_hi[6];
@@ -193,6 +196,45 @@ __device__ __forceinline__ void tg_tyre_tab(const double *__restrict__ tab, doub
     dg = d_ * (2.0 * scale);
 }
 
+// 1 / x for x > 0 to ~1 ulp without the IEEE division sequence: hardware seed + two Newton steps
+__device__ __forceinline__ double tg_rcp_pos(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
+// atan(t) for |t| <= TG_ATAN_T0 from the table (1e-16; nearest singularities of atan are at +-i, far from every interval)
+__device__ __forceinline__ double tg_atan_tab(const double *__restrict__ tab, double t)
+{
+    const double u = (t + TG_ATAN_T0) * (TG_ATAN_NI / (2.0 * TG_ATAN_T0));
+    int i = (int)u;
+    i = i < 0 ? 0 : (i > TG_ATAN_NI - 1 ? TG_ATAN_NI - 1 : i);
+    const double s_ = 2.0 * (u - (double)i) - 1.0;
+    const double2 *c2 = reinterpret_cast<const double2 *>(tab + i * TG_TAB_NC);
+    const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3), c89 = __ldg(c2 + 4);
+    // two interleaved Horner chains in s^2 (even / odd coefficients): half the dependent depth of a plain Horner
+    const double s2 = s_ * s_;
+    double ev = fma(c89.x, s2, c67.x), od = fma(c89.y, s2, c67.y);
+    ev = fma(ev, s2, c45.x); od = fma(od, s2, c45.y);
+    ev = fma(ev, s2, c23.x); od = fma(od, s2, c23.y);
+    ev = fma(ev, s2, c01.x); od = fma(od, s2, c01.y);
+    return fma(od, s_, ev);
+}
+
+// atan2(y, x) for the slip angles: x = vx_eff.  With x > 0 (always for the generator variants, and for the MPC variant
+// while the vehicle moves forward) atan2(y, x) = atan(y / x); the table covers |y / x| <= 4, anything else takes libdevice.
+__device__ __forceinline__ double tg_slip_atan(const double *__restrict__ atan_tab, double y, double x)
+{
+    if (atan_tab && x > 0.0) {
+        const double t = y * tg_rcp_pos(x);
+        if (fabs(t) <= TG_ATAN_T0) return tg_atan_tab(atan_tab, t);
+    }
+    return tg_atan2(y, x);
+}
+
 // sin / cos of phi + dphi from sin / cos of phi, |dphi| <= 0.25 (Taylor to x^13 / x^12: < 3e-18)
 __device__ __forceinline__ void tg_rotate_small(double &sp, double &cp, double dphi)
 {
@@ -223,7 +265,7 @@ __device__ __forceinline__ void tg_f_cont_tab(const DevCfg &c, int variant, cons
     const double vmag = fmax(fabs(vx), p[P_vx_zero]);
     const double vx_eff = (variant == TG_MODEL_MPC) ? (double)((vx > 0.0) - (vx < 0.0)) * vmag : vmag;
     const double nl = rear ? (om * p[P_lr] - vy) : (om * p[P_lf] + vy);
-    const double at = tg_atan2(nl, vx_eff);
+    const double at = tg_slip_atan(c.atan_tab, nl, vx_eff);
     const double alpha_raw = rear ? at : (-at + delta);
     const double alpha = tg_clamp(alpha_raw, -p[P_maxAlpha], p[P_maxAlpha]);
     double g, dg;
@@ -278,8 +320,8 @@ __device__ __forceinline__ void tg_plant_step_gen(const DevCfg &c, double x[6], 
     const double vx = x[3], vy = x[4], om = x[5];
     const double ma = p[P_maxAlpha];
     const double vmag = fmax(fabs(vx), p[P_vx_zero]);
-    const double af = tg_clamp(delta - tg_atan((om * p[P_lf] + vy) / vmag), -ma, ma);
-    double ar = tg_atan((om * p[P_lr] - vy) / vmag);
+    const double af = tg_clamp(delta - tg_slip_atan(c.atan_tab, om * p[P_lf] + vy, vmag), -ma, ma);
+    double ar = tg_slip_atan(c.atan_tab, om * p[P_lr] - vy, vmag);
     if (c.plant != TG_PLANT_GEN1) ar = tg_clamp(ar, -ma, ma);
     double gf, gr, dg;
     if (c.tyre_tab) {

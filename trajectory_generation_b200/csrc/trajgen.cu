@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <initializer_list>
 #include <new>
 #include <string>
@@ -344,23 +345,24 @@ static bool pick_shape(int N, Shape &s)
 // g(alpha) = sin(C atan(B alpha)) in long double, converted to monomials of s in [-1, 1].  Returns the largest
 // deviation from libm on a dense check grid (value and slope) so the caller can refuse a table that is not at
 // rounding level for unusual B, C.
-static double build_tyre_table(double B, double C, double ma, double *tab /*[NI][NC]*/, double *slope_err)
+static double build_cheb_table(const std::function<long double(long double)> &fun, const std::function<long double(long double)> &dfun,
+                               long double lo, long double hi, int NI, double *tab /*[NI][NC]*/, double *slope_err)
 {
-    const int NI = TG_TAB_NI, NC = TG_TAB_NC;
+    const int NC = TG_TAB_NC;
     const long double PI = 3.141592653589793238462643383279502884L;
     long double T[TG_TAB_NC][TG_TAB_NC] = {};   // T[k][i] = coefficient of s^i in T_k(s)
     T[0][0] = 1.0L;
     if (NC > 1) T[1][1] = 1.0L;
     for (int k = 2; k < NC; ++k)
         for (int i = 0; i < NC; ++i) T[k][i] = (i > 0 ? 2.0L * T[k - 1][i - 1] : 0.0L) - T[k - 2][i];
-    const long double hw = (long double)ma / NI;
+    const long double hw = (hi - lo) / (2 * NI);
     double worst = 0.0, worst_d = 0.0;
     for (int it = 0; it < NI; ++it) {
-        const long double ctr = -(long double)ma + (2 * it + 1) * hw;
+        const long double ctr = lo + (2 * it + 1) * hw;
         long double fv[TG_TAB_NC], a[TG_TAB_NC];
         for (int j = 0; j < NC; ++j) {
             const long double sj = cosl(PI * (j + 0.5L) / NC);
-            fv[j] = sinl((long double)C * atanl((long double)B * (ctr + hw * sj)));
+            fv[j] = fun(ctr + hw * sj);
         }
         for (int k = 0; k < NC; ++k) {
             long double acc = 0.0L;
@@ -376,15 +378,28 @@ static double build_tyre_table(double B, double C, double ma, double *tab /*[NI]
             const double sq = -1.0 + q / 8.0;
             double v = tab[it * NC + NC - 1], dv = 0.0;
             for (int i = NC - 2; i >= 0; --i) { dv = dv * sq + v; v = v * sq + tab[it * NC + i]; }
-            const long double al = ctr + hw * sq, ba = (long double)B * al;
-            const long double ref = sinl((long double)C * atanl(ba));
-            const long double dref = cosl((long double)C * atanl(ba)) * C * B / (1.0L + ba * ba);
-            worst = fmax(worst, fabs((double)(v - ref)));
-            worst_d = fmax(worst_d, fabs((double)(dv / (double)hw - dref)));
+            const long double al = ctr + hw * sq;
+            worst = fmax(worst, fabs((double)(v - fun(al))));
+            worst_d = fmax(worst_d, fabs((double)(dv / (double)hw - dfun(al))));
         }
     }
     if (slope_err) *slope_err = worst_d;
     return worst;
+}
+
+static double build_tyre_table(double B, double C, double ma, double *tab /*[NI][NC]*/, double *slope_err)
+{
+    auto f = [=](long double al) { return sinl((long double)C * atanl((long double)B * al)); };
+    auto df = [=](long double al) { const long double ba = (long double)B * al; return cosl((long double)C * atanl(ba)) * C * B / (1.0L + ba * ba); };
+    return build_cheb_table(f, df, -(long double)ma, (long double)ma, TG_TAB_NI, tab, slope_err);
+}
+
+// atan on [-TG_ATAN_T0, TG_ATAN_T0] (the slip-angle argument n / vx_eff of the sequential nominal rollout): same form
+static double build_atan_table(double *tab /*[TG_ATAN_NI][NC]*/)
+{
+    auto f = [](long double t) { return atanl(t); };
+    auto df = [](long double t) { return 1.0L / (1.0L + t * t); };
+    return build_cheb_table(f, df, -(long double)TG_ATAN_T0, (long double)TG_ATAN_T0, TG_ATAN_NI, tab, nullptr);
 }
 
 struct tg_handle {
@@ -485,16 +500,18 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     d.inv_m = 1.0 / d.p[P_m]; d.inv_Iz = 1.0 / d.p[P_Iz];
     d.tyre_tab = nullptr; d.tab_scale = 0.0;
     if (d.p[P_maxAlpha] > 0.0 && !getenv("TRAJGEN_NO_TYRE_TABLE")) {
-        std::vector<double> tab(2 * TG_TAB_NI * TG_TAB_NC);
+        std::vector<double> tab(2 * TG_TAB_NI * TG_TAB_NC + TG_ATAN_NI * TG_TAB_NC);
         double se_f = 0.0, se_r = 0.0;
         const double e_f = build_tyre_table(d.p[P_Bf], d.p[P_Cf], d.p[P_maxAlpha], tab.data(), &se_f);
         const double e_r = build_tyre_table(d.p[P_Br], d.p[P_Cr], d.p[P_maxAlpha], tab.data() + TG_TAB_NI * TG_TAB_NC, &se_r);
+        const double e_at = build_atan_table(tab.data() + 2 * TG_TAB_NI * TG_TAB_NC);
         h->tab_err[0] = fmax(e_f, e_r); h->tab_err[1] = fmax(se_f, se_r);
         if (h->tab_err[0] <= 4e-16 && h->tab_err[1] <= 1e-12) {
             CK(cudaMalloc(&h->tyre_tab, tab.size() * sizeof(double)));
             CK(cudaMemcpy(h->tyre_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
             d.tyre_tab = h->tyre_tab;
             d.tab_scale = TG_TAB_NI / (2.0 * d.p[P_maxAlpha]);
+            if (e_at <= 4e-16) d.atan_tab = h->tyre_tab + 2 * TG_TAB_NI * TG_TAB_NC;
         }
     }
     d.q_c = cfg->q_c; d.q_phi = cfg->q_phi; d.q_vx = cfg->q_vx;
@@ -576,7 +593,7 @@ int tg_debug_phases(long long *out16, int reset)
 int tg_tyre_table_info(tg_handle *h, int32_t *in_use, double *max_value_err, double *max_slope_err)
 {
     if (!h) return fail(TG_ERR_INVALID, "null handle");
-    if (in_use) *in_use = h->tyre_tab != nullptr;
+    if (in_use) *in_use = (h->dc.tyre_tab ? 1 : 0) | (h->dc.atan_tab ? 2 : 0);   // bit 0: tyre curve, bit 1: slip-angle atan
     if (max_value_err) *max_value_err = h->tab_err[0];
     if (max_slope_err) *max_slope_err = h->tab_err[1];
     return TG_OK;

@@ -112,7 +112,7 @@ class BatchedMPC:
         """dict(in_use, max_value_err, max_slope_err) of the tyre-curve table built for this handle's B, C, maxAlpha."""
         u, a, b = ctypes.c_int32(), ctypes.c_double(), ctypes.c_double()
         _lib.check(_lib.load().tg_tyre_table_info(self._h, ctypes.byref(u), ctypes.byref(a), ctypes.byref(b)))
-        return {"in_use": bool(u.value), "max_value_err": a.value, "max_slope_err": b.value}
+        return {"in_use": bool(u.value & 1), "atan_in_use": bool(u.value & 2), "max_value_err": a.value, "max_slope_err": b.value}
 
     # -- host-array API
     @staticmethod
