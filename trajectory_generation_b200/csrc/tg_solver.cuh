@@ -86,8 +86,22 @@ struct StepResult {
 // reduced in fp32 (rounded up): non-negative floats order like their bit patterns, which lets one REDUX
 // instruction per value replace a 5-stage 64-bit shuffle tree.  NaN (0x7fc00000) wins every max and is
 // detected by the caller.
-template <int NRED>
-__device__ __forceinline__ void tg_block_reduce_max(double (&vals)[NRED], double *red, int tid, int nthreads)
+// Barrier of the threads of ONE problem.  A CTA may hold several problems side by side (TG_PPC in trajgen.cu), each with
+// its own shared-memory block and its own named barrier, so that the problems of a CTA run the same instruction stream
+// at nearly the same time (shared instruction fetches) without ever waiting for one another inside a step.
+__device__ __forceinline__ void tg_sync(int bar, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads) : "memory");
+}
+// MULTI = false: the CTA is one problem and the barrier is the plain CTA barrier
+template <bool MULTI>
+__device__ __forceinline__ void tg_psync(int bar, int nthreads)
+{
+    if constexpr (MULTI) tg_sync(bar, nthreads); else __syncthreads();
+}
+
+template <int NRED, bool MULTI>
+__device__ __forceinline__ void tg_block_reduce_max(double (&vals)[NRED], double *red, int tid, int nthreads, int bar)
 {
     const int lane = tid & 31, wid = tid >> 5, nw = (nthreads + 31) >> 5;
     unsigned int *ured = reinterpret_cast<unsigned int *>(red);
@@ -101,30 +115,31 @@ __device__ __forceinline__ void tg_block_reduce_max(double (&vals)[NRED], double
         if (lane == 0)
 #pragma unroll
             for (int i = 0; i < NRED; ++i) ured[wid * 16 + i] = u[i];
-        __syncthreads();
+        tg_psync<MULTI>(bar, nthreads);
 #pragma unroll
         for (int i = 0; i < NRED; ++i) {
             unsigned int v = ured[i];
             for (int w = 1; w < nw; ++w) v = max(v, ured[w * 16 + i]);
             u[i] = v;
         }
-        __syncthreads();
+        tg_psync<MULTI>(bar, nthreads);
     }
 #pragma unroll
     for (int i = 0; i < NRED; ++i) vals[i] = (double)__uint_as_float(u[i]);
 }
 
-__device__ __forceinline__ double tg_block_reduce_sum(double v, double *red, int tid, int nthreads)
+template <bool MULTI>
+__device__ __forceinline__ double tg_block_reduce_sum(double v, double *red, int tid, int nthreads, int bar)
 {
     const int lane = tid & 31, wid = tid >> 5, nw = (nthreads + 31) >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (nw > 1) {
         if (lane == 0) red[wid * 8] = v;
-        __syncthreads();
+        tg_psync<MULTI>(bar, nthreads);
         v = red[0];
         for (int w = 1; w < nw; ++w) v += red[w * 8];
-        __syncthreads();
+        tg_psync<MULTI>(bar, nthreads);
     }
     return v;
 }
@@ -222,10 +237,11 @@ __device__ __forceinline__ void tg_build_K(const DevCfg &c, const SmemLayout &L,
 // update with w_i = a_ik/a_kk (w = 1 - 1/a_kk on the pivot row, which turns the generic update of row k into
 // a_kj/a_kk); the pivot itself is repaired in place (static register: square blocks).  The pivot-row index
 // inside a block is a compile-time constant because the k loop is unrolled by BS.
-template <int BS, int TG>
+template <int BS, int TG, bool MULTI>
 __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayout &L, double *sm, double (&a)[BS][BS],
-                                                int br, int bc)
+                                                int br, int bc, int bar)
 {
+    constexpr int NT = TG * TG;
     constexpr int BSP = TgPad<BS>::BSP;
     const int n = c.n, NPP = c.NPP;
     double *vb = sm + L.v;
@@ -238,7 +254,7 @@ __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayou
 #pragma unroll
         for (int i = 0; i < BS; ++i) dsc[br * BSP + i] = (br * BS + i < n) ? rsqrt(a[i][i]) : 0.0;
     }
-    __syncthreads();
+    tg_psync<MULTI>(bar, NT);
     {
         double dr[BS], dc[BS];
         tg_ld_block<BS>(dsc + br * BSP, dr);
@@ -264,7 +280,7 @@ __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayou
                     for (int j = 0; j < BS; ++j) v[bc * BSP + j] = a[kr][j];
                     if (bc == kb) { v[bc * BSP + kr] = a[kr][kr] - 1.0; v[NPP] = rp_next; }
                 }
-                __syncthreads();
+                tg_psync<MULTI>(bar, NT);
                 double vr[BS], vc[BS];
                 tg_ld_block<BS>(v + br * BSP, vr);
                 tg_ld_block<BS>(v + bc * BSP, vc);
@@ -294,7 +310,7 @@ __device__ __forceinline__ void tg_sweep_invert(const DevCfg &c, const SmemLayou
 #pragma unroll
             for (int j = 0; j < BS; ++j) a[i][j] *= dr[i] * dc[j];
     }
-    __syncthreads();
+    tg_psync<MULTI>(bar, NT);
 }
 
 // x~ = K^{-1} v for the register tile (a = -K^{-1}); v is block-padded, the result goes to xt (dense)
@@ -351,11 +367,11 @@ __device__ __forceinline__ void tg_ref_window_warp(const DevCfg &c, const SmemLa
 // builds it from the scenario in sm[L.spec] -- the reference window (Xr, Yr, Pr, vref); if `warm`, the
 // warm-start dU in sm[L.x] and duals in sm[L.y].  On exit sm[L.xt] holds dU* (x-tilde of the last check),
 // sm[L.y] the duals, and the result is returned to every thread.
-template <int BS, int TG>
+template <int BS, int TG, bool MULTI>
 __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, double *sm, bool warm, double *Hws,
-                                       const StepTaps &tap, const FusedCtx *fx)
+                                       const StepTaps &tap, const FusedCtx *fx, int tid, int bar)
 {
-    const int tid = threadIdx.x, NT = blockDim.x;
+    constexpr int NT = TG * TG;   // threads of this problem (tid = 0..NT-1); `bar` = its named barrier
     constexpr int BSP = TgPad<BS>::BSP;
     const int N = c.N, n = c.n, NP = c.NP, NPP = c.NPP, ms = c.ms, m = c.m, ns = c.ns;
     const int br = tid / TG, bc = tid % TG, R0 = br * BS, C0 = bc * BS;   // blockDim.x == TG*TG
@@ -421,7 +437,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     for (int i = tid; i < 2 * (NPP + 2); i += NT) sm[L.v + i] = 0.0;
     for (int i = tid; i < NP + 2; i += NT) xt[i] = 0.0;
     for (int i = tid; i < ms * (NP - n); i += NT) Gs[(i / (NP - n)) * NP + n + i % (NP - n)] = 0.0;  // pad columns
-    __syncthreads();
+    tg_psync<MULTI>(bar, NT);
     TG_TICK(0);
 
     // ---------------- K1b: linearise every stage (mpc_6stati.py:175-178) + tracking residuals at xbar
@@ -451,12 +467,12 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         }
         // constant term: stage costs at xbar + N u_prev' R u_prev (only the step API reports the objective)
         if (!fx) {
-            double c0 = tg_block_reduce_sum(c0_part, red, tid, NT);
+            double c0 = tg_block_reduce_sum<MULTI>(c0_part, red, tid, NT, bar);
             c0 += (double)N * (ud * (c.Rs[0] * ud + c.Rs[1] * udel) + udel * (c.Rs[2] * ud + c.Rs[3] * udel));
             if (tid == 0) misc[M_C0] = c0;
         }
     }
-    __syncthreads();
+    tg_psync<MULTI>(bar, NT);
     if (tap.A || tap.Bm || tap.g || tap.xbar) {
         for (int k = tid; k < N; k += NT)
             tg_lin_expand(lin + TG_LIN * k, tap.A ? tap.A + 36 * k : nullptr, tap.Bm ? tap.Bm + 12 * k : nullptr,
@@ -517,7 +533,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                     }
                 }
             }
-            __syncthreads();
+            tg_psync<MULTI>(bar, NT);
 #pragma unroll 1
             for (int s_i = 0; s_i < kb; ++s_i) {
                 const int k = k0 + s_i;
@@ -564,7 +580,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 if (R0 + i < n) dH[R0 + i] = a[i][i];
         }
     }
-    __syncthreads();
+    tg_psync<MULTI>(bar, NT);
     TG_TICK(10);
 
     // ---------------- bounds (mpc_6stati.py:198-221) and per-row rho = rho0 / max_j(a_ij^2 / H_jj)
@@ -613,10 +629,10 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     for (int i = tid; i < n; i += NT) nq = fmax(nq, fabs(q[i]));
     {
         double vals[1] = {nq};
-        tg_block_reduce_max<1>(vals, red, tid, NT);
+        tg_block_reduce_max<1, MULTI>(vals, red, tid, NT, bar);
         nq = vals[0];
     }
-    __syncthreads();   // bounds / rho / q visible to every thread
+    tg_psync<MULTI>(bar, NT);   // bounds / rho / q visible to every thread
     if (tap.q) for (int i = tid; i < n; i += NT) tap.q[i] = q[i];
     if (tap.c0 && tid == 0) tap.c0[0] = misc[M_C0];
     if (tap.l) for (int i = tid; i < m; i += NT) { tap.l[i] = lb[i]; tap.u[i] = ub[i]; }
@@ -626,7 +642,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
 
     // ---------------- K3: factor
     tg_build_K<BS>(c, L, sm, a, R0, C0);
-    tg_sweep_invert<BS, TG>(c, L, sm, a, br, bc);
+    tg_sweep_invert<BS, TG, MULTI>(c, L, sm, a, br, bc, bar);
     TG_TICK(4);
 
     // ---------------- ADMM
@@ -660,7 +676,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 z[2 * n + i] = tg_clamp(acc, lb[2 * n + i], ub[2 * n + i]);
             }
         }
-        __syncthreads();
+        tg_psync<MULTI>(bar, NT);
         TG_TICK(7);
 #pragma unroll 1
         for (it = 1; it <= c.max_iter; ++it) {
@@ -672,7 +688,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 // such steps take ~1e3 iterations where the shifted start ran into max_iter): restart from zero
                 for (int i = tid; i < n; i += NT) x[i] = 0.0;
                 for (int i = tid; i < m; i += NT) { z[i] = 0.0; y[i] = 0.0; }
-                __syncthreads();
+                tg_psync<MULTI>(bar, NT);
             }
             // (a) rhs = sigma x - q + A'(rho z - y)
             if (tid < n) {
@@ -682,10 +698,10 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 for (int i = 0; i < ms; ++i) r_ = fma(Gs[i * NP + j], rho[2 * n + i] * z[2 * n + i] - y[2 * n + i], r_);
                 v[jpad] = r_;
             }
-            __syncthreads();
+            tg_psync<MULTI>(bar, NT);
             // (b) x~ = K^{-1} rhs
             tg_matvec<BS, TG>(a, v, xt, br, bc, n);
-            __syncthreads();
+            tg_psync<MULTI>(bar, NT);
             // (c) relaxation, projection, dual update
             double rp = 0.0, nzt = 0.0, nz = 0.0;
             if (tid < n) {
@@ -719,7 +735,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 dy[i] = yn - y[i]; y[i] = yn; z[i] = zn; zt[i] = ztl;
                 rp = fmax(rp, fabs(ztl - zn)); nzt = fmax(nzt, fabs(ztl)); nz = fmax(nz, fabs(zn));
             }
-            __syncthreads();
+            tg_psync<MULTI>(bar, NT);
             TG_TICK(8);
             if (!check) continue;
 
@@ -742,7 +758,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
             }
             for (int i = tid; i < m; i += NT) ndy = fmax(ndy, fabs(dy[i]));
             double vals[9] = {rp, nzt, nz, rd, nh, na, natdy, ndy, bad ? 1.0 : 0.0};
-            tg_block_reduce_max<9>(vals, red, tid, NT);
+            tg_block_reduce_max<9, MULTI>(vals, red, tid, NT, bar);
             const double eps_p = c.eps_abs + c.eps_rel * fmax(vals[1], vals[2]);
             const double eps_d = c.eps_abs + c.eps_rel * fmax(fmax(vals[4], vals[5]), nq);
             if (vals[8] > 0.0 || !(vals[0] == vals[0]) || !(vals[3] == vals[3])) { status = TG_STATUS_NAN; break; }
@@ -770,7 +786,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                     else if (d_ < -thr) part += (lb[i] <= -TG_INF) ? 1e300 : lb[i] * d_;
                 }
                 if (tid < n) part += natdy * fmax(fabs(lb[tid]), fabs(ub[tid]));
-                const double cert_sum = tg_block_reduce_sum(part, red, tid, NT);
+                const double cert_sum = tg_block_reduce_sum<MULTI>(part, red, tid, NT, bar);
                 if (vals[7] > 1e-30 && cert_sum < -1e-9 * vals[7]) { status = TG_STATUS_INFEASIBLE; break; }
             }
             if (c.adaptive_rho && Hws && it >= c.adaptive_rho_min_iter) {
@@ -785,9 +801,9 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                     for (int i = 0; i < BS; ++i)
 #pragma unroll
                         for (int j = 0; j < BS; ++j) a[i][j] = Hws[(i * BS + j) * NT + tid];
-                    __syncthreads();
+                    tg_psync<MULTI>(bar, NT);
                     tg_build_K<BS>(c, L, sm, a, R0, C0);
-                    tg_sweep_invert<BS, TG>(c, L, sm, a, br, bc);
+                    tg_sweep_invert<BS, TG, MULTI>(c, L, sm, a, br, bc, bar);
                 }
             }
         }
@@ -801,7 +817,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 const double hx = v[jpad] - sigma * xt[j] - atr;
                 objp = xt[j] * (0.5 * hx + q[j]);
             }
-            obj = tg_block_reduce_sum(objp, red, tid, NT);
+            obj = tg_block_reduce_sum<MULTI>(objp, red, tid, NT, bar);
         }
     }
     TG_TICK(5);
@@ -810,7 +826,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     res.iters = it;
     res.objective = obj + misc[M_C0];
     if (tid == 0) misc[M_RHOSCALE] = rho_scale;
-    __syncthreads();
+    tg_psync<MULTI>(bar, NT);
     TG_TICK(6);
     return res;
 }

@@ -41,6 +41,7 @@ void tg_internal_set_error(const char *msg) { g_err = msg; }   // for tg_csv.cpp
 #endif
 #define TG_MINB(BS, TG) ((TG) == 8 ? TG_MINB8 : ((BS) <= 5 ? 2 : 1))
 #define TG_KATTR(BS, TG) __launch_bounds__(TG_NT(BS, TG), TG_MINB(BS, TG))
+#define TG_PPC_MAX 8       // most problems one CTA of the closed-loop kernel holds (64-thread shapes): 512 threads
 
 // ------------------------------------------------------------------------------------------------ kernels
 struct StepArgs {
@@ -51,19 +52,26 @@ struct StepArgs {
     double *A, *Bm, *g, *xbar, *H, *q, *c0, *l, *u, *Gs;
     int stop;
     double *ws_x, *ws_y; int *ws_valid;   // per-problem warm-start state (step API), may be null
-    double *Hws;                          // per-CTA H workspace, may be null
+    double *Hws;                          // per-problem-slot H workspace, may be null
+    int ppc;                              // problems per CTA
 };
 
-template <int BS, int TG>
-__global__ void TG_KATTR(BS, TG)
+// a.ppc problems per CTA, side by side (see tg_closed_loop_kernel): problem slot = threadIdx.x / NT
+template <int BS, int TG, bool MULTI>
+__global__ void __launch_bounds__(TG_NT(BS, TG) * (MULTI ? TG_PPC_MAX : 1), MULTI ? 1 : TG_MINB(BS, TG))
 tg_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, const __grid_constant__ StepArgs a)
 {
-    extern __shared__ __align__(16) double sm[];
-    const int tid = threadIdx.x, NT = blockDim.x;
+    extern __shared__ __align__(16) double sm_all[];
+    constexpr int NT = TG_NT(BS, TG);
+    const int P = MULTI ? a.ppc : 1, prob = MULTI ? threadIdx.x / NT : 0, tid = MULTI ? threadIdx.x % NT : threadIdx.x, bar = 1 + prob;
+    double *sm = sm_all + (size_t)prob * ((L.total + 1) & ~1);
     const int N = c.N, n = c.n, m = c.m;
-    double *Hws = a.Hws ? a.Hws + (size_t)blockIdx.x * c.NP * c.NP : nullptr;
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-        __syncthreads();
+    double *Hws = a.Hws ? a.Hws + ((size_t)blockIdx.x * P + prob) * c.NP * c.NP : nullptr;
+    for (int b0 = blockIdx.x * P; b0 < a.B; b0 += gridDim.x * P) {
+        const int b = b0 + prob;
+        if (MULTI && P > 1 && a.B - b0 >= P) tg_sync(15, NT * P);   // all slots busy: start the round together
+        if (b >= a.B) continue;
+        tg_psync<MULTI>(bar, NT);
         if (tid < 6) sm[L.x0 + tid] = a.x0[6 * (size_t)b + tid];
         if (tid < 2) sm[L.uprev + tid] = a.u_prev[2 * (size_t)b + tid];
         const double vx0 = a.x0[6 * (size_t)b + 3];
@@ -80,7 +88,7 @@ tg_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Sme
             for (int i = tid; i < n; i += NT) sm[L.x + i] = a.ws_x[(size_t)b * n + i];
             for (int i = tid; i < m; i += NT) sm[L.y + i] = a.ws_y[(size_t)b * m + i];
         }
-        __syncthreads();
+        tg_psync<MULTI>(bar, NT);
         StepTaps tap;
         tap.A = a.A ? a.A + (size_t)b * N * 36 : nullptr;
         tap.Bm = a.Bm ? a.Bm + (size_t)b * N * 12 : nullptr;
@@ -93,7 +101,7 @@ tg_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Sme
         tap.u = a.u ? a.u + (size_t)b * m : nullptr;
         tap.Gs = a.Gs ? a.Gs + (size_t)b * c.ms * n : nullptr;
         tap.stop = a.stop;
-        const StepResult r = tg_mpc_step_body<BS, TG>(c, L, sm, warm, Hws, tap, nullptr);
+        const StepResult r = tg_mpc_step_body<BS, TG, MULTI>(c, L, sm, warm, Hws, tap, nullptr, tid, bar);
         if (a.stop) continue;
         const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);  // :261
         const double ud = sm[L.uprev], udel = sm[L.uprev + 1];
@@ -167,28 +175,42 @@ struct LoopArgs {
     int *status_counts;
     long long *iters_total;
     double *Hws;
+    int ppc;   // problems per CTA
 };
 
-template <int BS, int TG>
-__global__ void TG_KATTR(BS, TG)
+// P problems per CTA, side by side: problem p = threadIdx.x / NT owns its own shared-memory block and named barrier 1 + p.
+// The step body is ~110 KB of code that every trajectory walks through once per step; with one problem per CTA the 7
+// CTAs of an SM drift into different phases and the instruction caches thrash (ncu: L1 instruction hit rate 70 %, the
+// GPC instruction cache at 87 % of its request peak).  Problems of one CTA are re-aligned at every step boundary
+// (barrier 15), so they fetch the same lines at the same time.
+// P = a.ppc is a launch parameter (1..TG_PPC_MAX for the 64-thread shapes, 1 otherwise): the register budget is that of
+// the largest CTA (512 threads x 128 registers = one full register file), which is also what 8 single-problem CTAs get.
+template <int BS, int TG, bool MULTI>
+__global__ void __launch_bounds__(TG_NT(BS, TG) * (MULTI ? TG_PPC_MAX : 1), MULTI ? 1 : TG_MINB(BS, TG))
 tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, const __grid_constant__ LoopArgs a)
 {
-    extern __shared__ __align__(16) double sm[];
-    const int tid = threadIdx.x, NT = blockDim.x;
+    extern __shared__ __align__(16) double sm_all[];
+    constexpr int NT = TG_NT(BS, TG);
+    const int P = MULTI ? a.ppc : 1;
+    const int prob = MULTI ? threadIdx.x / NT : 0, tid = MULTI ? threadIdx.x % NT : threadIdx.x, bar = 1 + prob;
+    double *sm = sm_all + (size_t)prob * ((L.total + 1) & ~1);
     const int n = c.n, ms = c.ms, ns = c.ns, T = a.T;
-    double *Hws = a.Hws ? a.Hws + (size_t)blockIdx.x * c.NP * c.NP : nullptr;
+    double *Hws = a.Hws ? a.Hws + ((size_t)blockIdx.x * P + prob) * c.NP * c.NP : nullptr;
     const StepTaps tap = {};
     int *cnt = reinterpret_cast<int *>(sm + L.misc + M_CNT);                 // 6 status counters
     long long *itsum = reinterpret_cast<long long *>(sm + L.misc + M_CNT + 3);
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-        __syncthreads();
+    for (int b0 = blockIdx.x * P; b0 < a.B; b0 += gridDim.x * P) {
+        const int b = b0 + prob;
+        const bool lockstep = MULTI && (P > 1) && (a.B - b0 >= P);   // every problem slot of this CTA is busy in this round
+        if (b >= a.B) continue;
+        tg_psync<MULTI>(bar, NT);
         if (tid < 12) sm[L.spec + tid] = reinterpret_cast<const double *>(a.spec + b)[tid];   // scenario -> shared memory
         if (tid < 6) { const double v_ = a.x0[6 * (size_t)b + tid]; sm[L.x0 + tid] = v_; a.clean[(size_t)b * (T + 1) * 6 + tid] = v_; }
         if (tid < 2) sm[L.uprev + tid] = a.u0[2 * (size_t)b + tid];
         if (tid < TG_NUM_STATUS) cnt[tid] = 0;
         if (tid == 0) *itsum = 0;
         bool warm = false;
-        __syncthreads();
+        tg_psync<MULTI>(bar, NT);
 #pragma unroll 1
         for (int t = 0; t <= T; ++t) {
             FusedCtx fx;
@@ -209,7 +231,7 @@ tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
                 }
                 break;
             }
-            const StepResult r = tg_mpc_step_body<BS, TG>(c, L, sm, warm, Hws, tap, &fx);
+            const StepResult r = tg_mpc_step_body<BS, TG, MULTI>(c, L, sm, warm, Hws, tap, &fx, tid, bar);
             const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);
             if (tid == 0) { cnt[r.status] += 1; *itsum += r.iters; }
             // shifted warm start for the next step, in the next step's dU coordinates
@@ -239,7 +261,7 @@ tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
 #pragma unroll
                 for (int r_ = 0; r_ < 4; ++r_) { const int i = tid + r_ * NT; tmp[r_] = (i + ns < ms) ? sm[L.y + 2 * n + i + ns] : 0.0; }
             }
-            __syncthreads();
+            tg_psync<MULTI>(bar, NT);
             // commit the new state / warm start
             if (tid < 6) sm[L.x0 + tid] = sm[L.misc + M_XNEXT + tid];
             if (tid < 2) sm[L.uprev + tid] = sm[L.misc + M_UCMD + tid];
@@ -249,9 +271,9 @@ tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
                 for (int r_ = 0; r_ < 4; ++r_) { const int i = tid + r_ * NT; if (i < ms) sm[L.y + 2 * n + i] = tmp[r_]; }
             }
             warm = ok && c.warm_start;
-            __syncthreads();
+            if (lockstep) tg_sync(15, NT * P); else tg_psync<MULTI>(bar, NT);
         }
-        __syncthreads();
+        tg_psync<MULTI>(bar, NT);
         if (tid < TG_NUM_STATUS && a.status_counts) a.status_counts[(size_t)b * TG_NUM_STATUS + tid] = cnt[tid];
         if (tid == 0 && a.iters_total) a.iters_total[b] = *itsum;
     }
@@ -408,6 +430,8 @@ struct tg_handle {
     SmemLayout L;
     Shape shape;
     int device, num_sms, grid_cap;
+    int ppc_max, ppc_env;     // closed-loop kernel: most problems per CTA that fit / TRAJGEN_PPC override (0 = automatic)
+    size_t smem_optin;
     size_t smem_bytes;
     cudaStream_t stream;
     long long launches;
@@ -434,6 +458,26 @@ static int dispatch_shape(const Shape &s, F &&f)
     if (s.BS == 7 && s.TG == 16) return f(std::integral_constant<int, 7>(), std::integral_constant<int, 16>());
 #endif
     return fail(TG_ERR_UNSUPPORTED, "no kernel shape for this horizon");
+}
+
+// kernel instance for a shape: `multi` = several problems per CTA (64-thread shapes only)
+template <typename F>
+static int dispatch_loop(const Shape &s, bool multi, F &&f)
+{
+    return dispatch_shape(s, [&](auto BS_, auto TG_) -> int {
+        constexpr int BS = decltype(BS_)::value, TG = decltype(TG_)::value;
+        if constexpr (TG == 8) { if (multi) return f(tg_closed_loop_kernel<BS, TG, true>); }
+        return f(tg_closed_loop_kernel<BS, TG, false>);
+    });
+}
+template <typename F>
+static int dispatch_step(const Shape &s, bool multi, F &&f)
+{
+    return dispatch_shape(s, [&](auto BS_, auto TG_) -> int {
+        constexpr int BS = decltype(BS_)::value, TG = decltype(TG_)::value;
+        if constexpr (TG == 8) { if (multi) return f(tg_mpc_step_kernel<BS, TG, true>); }
+        return f(tg_mpc_step_kernel<BS, TG, false>);
+    });
 }
 
 extern "C" {
@@ -534,25 +578,34 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
         return fail(TG_ERR_UNSUPPORTED, "state-bound rows x horizon exceed the 227 KB shared memory of one CTA");
     }
     int occ = 0;
-    int rc = dispatch_shape(sh, [&](auto BS_, auto TG_) -> int {
-        auto k1 = tg_mpc_step_kernel<decltype(BS_)::value, decltype(TG_)::value>;
-        auto k2 = tg_closed_loop_kernel<decltype(BS_)::value, decltype(TG_)::value>;
-        CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-        CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-        CK(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CK(cudaFuncSetAttribute(k2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        int o1 = 0, o2 = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k1, sh.NT, h->smem_bytes));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k2, sh.NT, h->smem_bytes));
-        occ = o1 < o2 ? o1 : o2;
-        return TG_OK;
-    });
+    const size_t stride = (((size_t)h->L.total + 1) & ~(size_t)1) * sizeof(double);   // shared memory of one problem
+    h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+    h->ppc_max = 1;
+    if (sh.NT == 64) {   // several problems per CTA for the 64-thread shapes, as many as fit in shared memory
+        h->ppc_max = TG_PPC_MAX;
+        while (h->ppc_max > 1 && (size_t)h->ppc_max * stride > h->smem_optin) h->ppc_max -= 1;
+    }
+    h->ppc_env = 0;   // TRAJGEN_PPC = 1..8 pins the number of problems per CTA (measurement knob)
+    if (const char *e = getenv("TRAJGEN_PPC")) { const int v = atoi(e); if (v >= 1 && v <= h->ppc_max) h->ppc_env = v; }
+    int rc = TG_OK;
+    for (int multi = 0; multi <= (h->ppc_max > 1 ? 1 : 0) && rc == TG_OK; ++multi) {
+        const size_t bytes = multi ? (size_t)h->ppc_max * stride : h->smem_bytes;
+        auto setup = [&](auto kern) -> int {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            if (!multi) { int o = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, sh.NT, h->smem_bytes)); occ = (occ == 0 || o < occ) ? o : occ; }
+            return TG_OK;
+        };
+        rc = dispatch_step(sh, multi != 0, setup);
+        if (rc == TG_OK) rc = dispatch_loop(sh, multi != 0, setup);
+    }
     if (rc != TG_OK) return rc;
     if (occ < 1) return fail(TG_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration");
     h->grid_cap = occ * h->num_sms;
     CK(cudaFuncSetAttribute(tg_ref_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     if (d.adaptive_rho) {
-        h->Hws_elems = (size_t)h->grid_cap * d.NP * d.NP;
+        const size_t slots = std::max((size_t)h->grid_cap, (size_t)h->num_sms * TG_PPC_MAX);   // resident problems, either kernel
+        h->Hws_elems = slots * d.NP * d.NP;
         CK(cudaMalloc(&h->Hws, h->Hws_elems * sizeof(double)));
     }
     h->stream = 0;
@@ -600,14 +653,41 @@ int tg_tyre_table_info(tg_handle *h, int32_t *in_use, double *max_value_err, dou
 }
 int tg_kernel_launches(tg_handle *h, int64_t *count) { if (!h || !count) return fail(TG_ERR_INVALID, "null argument"); *count = h->launches; return TG_OK; }
 
+// Problems per CTA (64-thread shapes; a 256-thread CTA is one problem): problems of one CTA run in lockstep and share
+// their instruction fetches.
+static int choose_ppc(const tg_handle *h, int B)
+{
+    if (h->ppc_max <= 1) return 1;
+    if (h->ppc_env) return h->ppc_env;
+    // measured on the headline workload (1024 trajectories, 21 KB of shared memory each): 4 per CTA (two CTAs per SM, out
+    // of phase with each other) 1.53e7 steps/s, 8 per CTA 1.49e7, 2 per CTA 1.41e7, 1 per CTA 1.07e7.  Resident problems
+    // come first, though: with state-bound rows a problem needs 40+ KB and long, unequal solves, where 5 free-running
+    // single-problem CTAs per SM beat 4 problems in lockstep (config 4, N = 20: 1.5e6 vs 1.1e6 steps/s).
+    const size_t stride = (((size_t)h->L.total + 1) & ~(size_t)1) * sizeof(double);
+    int best = 1, best_res = 0;
+    for (int p = 1; p <= 4 && p <= h->ppc_max; p *= 2) {
+        if (p > 1 && B < p * h->num_sms) break;                   // small batches keep at least one CTA per SM
+        const int by_regs = TG_PPC_MAX / p, by_smem = (int)(h->smem_optin / ((size_t)p * stride));
+        const int res = p * (by_regs < by_smem ? by_regs : by_smem);
+        if (res >= best_res) { best = p; best_res = res; }
+    }
+    return best;
+}
+
 static int launch_step(tg_handle *h, StepArgs &a)
 {
     if (a.B <= 0) return TG_OK;   // empty batch: nothing to do
     CK(cudaSetDevice(h->device));
     a.Hws = h->Hws;
-    const int grid = a.B < h->grid_cap ? a.B : h->grid_cap;
-    int rc = dispatch_shape(h->shape, [&](auto BS_, auto TG_) -> int {
-        tg_mpc_step_kernel<decltype(BS_)::value, decltype(TG_)::value><<<grid, h->shape.NT, h->smem_bytes, h->stream>>>(h->dc, h->L, a);
+    const int ppc = choose_ppc(h, a.B);
+    a.ppc = ppc;
+    const size_t smem = ppc > 1 ? (size_t)ppc * (((size_t)h->L.total + 1) & ~(size_t)1) * sizeof(double) : h->smem_bytes;
+    int per_sm = 0;
+    int rc = dispatch_step(h->shape, ppc > 1, [&](auto kern) -> int {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, h->shape.NT * ppc, smem));
+        if (per_sm < 1) return fail(TG_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration");
+        const int ctas = (a.B + ppc - 1) / ppc, cap = per_sm * h->num_sms;
+        kern<<<ctas < cap ? ctas : cap, h->shape.NT * ppc, smem, h->stream>>>(h->dc, h->L, a);
         return TG_OK;
     });
     if (rc != TG_OK) return rc;
@@ -693,9 +773,15 @@ int tg_closed_loop(tg_handle *h, int B, int T, const double *x0, const double *u
     a.B = B; a.T = T; a.x0 = x0; a.u0 = u0; a.spec = spec; a.brk = brk; a.coef = coef; a.traj_id0 = traj_id0;
     a.clean = clean; a.noisy = noisy; a.U = U; a.status_counts = status_counts; a.iters_total = (long long *)iters_total;
     a.Hws = h->Hws;
-    const int grid = B < h->grid_cap ? B : h->grid_cap;
-    int rc = dispatch_shape(h->shape, [&](auto BS_, auto TG_) -> int {
-        tg_closed_loop_kernel<decltype(BS_)::value, decltype(TG_)::value><<<grid, h->shape.NT, h->smem_bytes, h->stream>>>(h->dc, h->L, a);
+    const int ppc = choose_ppc(h, B);
+    a.ppc = ppc;
+    const size_t loop_smem = ppc > 1 ? (size_t)ppc * (((size_t)h->L.total + 1) & ~(size_t)1) * sizeof(double) : h->smem_bytes;
+    int per_sm = 0;
+    int rc = dispatch_loop(h->shape, ppc > 1, [&](auto kern) -> int {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, h->shape.NT * ppc, loop_smem));
+        if (per_sm < 1) return fail(TG_ERR_UNSUPPORTED, "closed-loop kernel does not fit on an SM with this configuration");
+        const int ctas = (B + ppc - 1) / ppc, cap = per_sm * h->num_sms;
+        kern<<<ctas < cap ? ctas : cap, h->shape.NT * ppc, loop_smem, h->stream>>>(h->dc, h->L, a);
         return TG_OK;
     });
     if (rc != TG_OK) return rc;
