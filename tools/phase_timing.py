@@ -15,8 +15,8 @@ out = (ctypes.c_longlong * 16)()
 L.tg_debug_phases(None, 1)
 import time; t = time.time(); res = gen.generate(x0, u0, sc, T); dt = time.time() - t
 L.tg_debug_phases(out, 0)
-v = np.array(out[:13], dtype=float)
-names = ["rollout(+zero,sincos)", "linearise+resid", "K2 condense", "R-terms,bounds,rho", "buildK+sweep", "ADMM tail", "objective/exit", "ADMM init", "ADMM iterations", "ADMM check", "R-terms+dH", "bounds+rho", "H taps/copy"]
+v = np.array(out[:16], dtype=float)
+names = ["rollout(+zero,sincos)", "linearise+resid", "K2 condense", "R-terms,bounds,rho", "buildK+sweep", "ADMM tail", "objective/exit", "ADMM init", "ADMM iterations", "ADMM check", "R-terms+dH", "bounds+rho", "H taps/copy", "K2 producer (G, W rows)", "K2 barrier wait", "K2 consumer (rank-3)"]
 ntraj0 = len(range(0, B, min(B, gen.info()["ctas_per_sm"] * gen.info()["num_sms"])))
 steps = T * ntraj0
 print(f"B={B} T={T} wall {dt*1e3:.1f} ms  -> {B*T/dt:.3e} steps/s; CTA0 ran {ntraj0} trajectories")

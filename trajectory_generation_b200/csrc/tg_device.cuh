@@ -290,6 +290,39 @@ __device__ __forceinline__ void tg_f_cont_tab(const DevCfg &c, int variant, cons
     }
 }
 
+// The velocity part of f_cont by a lane pair with the tables (see tg_f_cont_tab).  (vx, vy, omega) do not depend on the
+// pose, so the nominal rollout integrates them alone along its sequential chain and recovers heading and position
+// afterwards (tg_solver.cuh, K1a).  aux (optional, lanes 0/1) receives the slip angle before the clamp.
+__device__ __forceinline__ void tg_f_vel_tab(const DevCfg &c, int variant, double vx, double vy, double om, double d, double delta,
+                                             double sd, double cd, int lane, double &f3, double &f4, double &f5, double *aux = nullptr)
+{
+    const double *__restrict__ p = c.p;
+    const int rear = lane & 1, base = lane & ~1;
+    const double vmag = fmax(fabs(vx), p[P_vx_zero]);
+    const double vx_eff = (variant == TG_MODEL_MPC) ? (double)((vx > 0.0) - (vx < 0.0)) * vmag : vmag;
+    const double nl = rear ? (om * p[P_lr] - vy) : (om * p[P_lf] + vy);
+    const double at = tg_slip_atan(c.atan_tab, nl, vx_eff);
+    const double alpha_raw = rear ? at : (-at + delta);
+    const double alpha = tg_clamp(alpha_raw, -p[P_maxAlpha], p[P_maxAlpha]);
+    double g, dg;
+    tg_tyre_tab(c.tyre_tab + rear * (TG_TAB_NI * TG_TAB_NC), alpha, p[P_maxAlpha], c.tab_scale, g, dg);
+    const double F = (rear ? p[P_Dr] : p[P_Df]) * g;
+    if (aux && lane < 2) aux[rear] = alpha_raw;
+    const double Fyf = __shfl_sync(0xffffffffu, F, base), Fyr = __shfl_sync(0xffffffffu, F, base + 1);
+    const double vl = (variant == TG_MODEL_MPC) ? vx : vx_eff;
+    const double Frx = (p[P_Cm1] - p[P_Cm2] * vl) * d - p[P_Cr0] - p[P_Cr2] * (vl * vl);
+    const double m = p[P_m];
+    if (variant == TG_MODEL_MPC) {
+        f3 = c.inv_m * (Frx - Fyf * sd + m * vy * om);       // (1.0/m) * (...), MPC/mpc_6stati.py:67
+        f4 = c.inv_m * (Fyr + Fyf * cd - m * vx * om);
+        f5 = c.inv_Iz * (Fyf * p[P_lf] * cd - Fyr * p[P_lr]);
+    } else {
+        f3 = (Frx - Fyf * sd + m * vy * om) / m;
+        f4 = (Fyr + Fyf * cd - m * vx * om) / m;
+        f5 = (Fyf * p[P_lf] * cd - Fyr * p[P_lr]) / p[P_Iz];
+    }
+}
+
 // plant step by a whole warp (see tg_f_cont_lanes)
 __device__ __forceinline__ void tg_plant_step_lanes(const DevCfg &c, double x[6], double d, double delta, int lane)
 {

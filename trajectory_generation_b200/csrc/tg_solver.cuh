@@ -395,21 +395,50 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
         for (int i = 0; i < 6; ++i) xs[i] = sm[L.x0 + i];
         if (tid < 6) xbar[tid] = sm[L.x0 + tid];
         const bool use_tab = c.tyre_tab && c.model != TG_MODEL_GEN1;
-        double sp = 0.0, cp = 1.0;
-        if (use_tab) TG_SINCOS(xs[2], sp, cp);
+        if (use_tab) {
+            // (vx, vy, omega) do not depend on the pose, so only they ride the sequential chain (slip angle -> tyre force ->
+            // Euler update, from tables); heading and position are recovered afterwards: the heading by one lane's running
+            // sum (the reference's summation order), sin / cos of all headings by one lane per stage in parallel, the
+            // position by two lanes' running sums.  (Integrating the pose inside the chain cost ~3x: the in-order warp
+            // stalled on the pose's dependent instructions between two stages of the velocity recurrence.)
+            double vx = xs[3], vy = xs[4], om = xs[5];
 #pragma unroll 1
-        for (int k = 0; k < N; ++k) {
-            if (use_tab) tg_f_cont_tab(c, c.model, xs, ud, udel, sd, cd, sp, cp, tid, f, sm + L.aux + 6 * k);
-            else tg_f_cont_lanes(c.p, c.inv_m, c.inv_Iz, c.model, xs, ud, udel, sd, cd, tid, f, sm + L.aux + 6 * k);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) xs[i] = xs[i] + c.Ts * f[i];
-            if (use_tab) {   // sin / cos of the new heading by a small rotation (phi advances by Ts * omega)
-                const double dphi = c.Ts * f[2];
-                if (fabs(dphi) <= 0.25) tg_rotate_small(sp, cp, dphi); else TG_SINCOS(xs[2], sp, cp);
+            for (int k = 0; k < N; ++k) {
+                double f3, f4, f5;
+                tg_f_vel_tab(c, c.model, vx, vy, om, ud, udel, sd, cd, tid, f3, f4, f5, sm + L.aux + 6 * k);
+                vx = vx + c.Ts * f3; vy = vy + c.Ts * f4; om = om + c.Ts * f5;
+                if (tid == 0) { xbar[6 * (k + 1) + 3] = vx; xbar[6 * (k + 1) + 4] = vy; xbar[6 * (k + 1) + 5] = om; }
             }
+            __syncwarp();
             if (tid == 0) {
+                double phi = xs[2];
+                for (int k = 0; k < N; ++k) { phi = phi + c.Ts * xbar[6 * k + 5]; xbar[6 * (k + 1) + 2] = phi; }
+            }
+            __syncwarp();
+            for (int k = tid; k < N; k += 32) {
+                double s_, c_;
+                TG_SINCOS(xbar[6 * k + 2], s_, c_);
+                const double vxk = xbar[6 * k + 3], vyk = xbar[6 * k + 4];
+                double *ax = sm + L.aux + 6 * k;
+                ax[2] = s_; ax[3] = c_;
+                ax[4] = vxk * c_ - vyk * s_;          // Xdot, Ydot of the stage
+                ax[5] = vxk * s_ + vyk * c_;
+            }
+            __syncwarp();
+            if (tid < 2) {
+                double pos = xs[tid];
+                for (int k = 0; k < N; ++k) { pos = pos + c.Ts * sm[L.aux + 6 * k + 4 + tid]; xbar[6 * (k + 1) + tid] = pos; }
+            }
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) {
+                tg_f_cont_lanes(c.p, c.inv_m, c.inv_Iz, c.model, xs, ud, udel, sd, cd, tid, f, sm + L.aux + 6 * k);
 #pragma unroll
-                for (int i = 0; i < 6; ++i) xbar[6 * (k + 1) + i] = xs[i];
+                for (int i = 0; i < 6; ++i) xs[i] = xs[i] + c.Ts * f[i];
+                if (tid == 0) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) xbar[6 * (k + 1) + i] = xs[i];
+                }
             }
         }
     } else if (tid < 64) {
@@ -499,29 +528,30 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
             double *wblk = wbuf + ((k0 / TG_KB) & 1) * TG_KB * 3 * NPP;
             if (tid < n) {
                 const int j = tid;
-#pragma unroll 1
-                for (int s_i = 0; s_i < kb; ++s_i) {
-                    const int k = k0 + s_i;
-                    double r[22];   // stage record: all 128-bit loads issued before the FMAs that use them
+                // One stage of the G recursion for column j, branch-free: a column that has not started yet holds zeros and
+                // A_k 0 = 0, so only the stage in which the column is born (j / 2 == k: it becomes a column of B_k) needs a
+                // select.  The critical path runs through G alone (three dependent FMAs per stage); the staged rows, the
+                // gradient term and the stores hang off it, and with the stages of a block unrolled the scheduler overlaps
+                // them with the next stage's recursion (a rolled, branchy loop cost ~900 cycles per stage).
+                auto stage = [&](int k, int s_i) {
+                    double r[22];
                     {
                         const double2 *r2 = reinterpret_cast<const double2 *>(lin + TG_LIN * k);
 #pragma unroll
                         for (int i = 0; i < 11; ++i) { const double2 t = r2[i]; r[2 * i] = t.x; r[2 * i + 1] = t.y; }
                     }
                     double *wb = wblk + s_i * 3 * NPP;
-                    if (j < 2 * k) {  // G_{k+1} = A_k G_k
-                        const double n0 = G0 + r[0] * G2 + r[1] * G3 + r[2] * G4;
-                        const double n1 = G1 + r[3] * G2 + r[4] * G3 + r[5] * G4;
-                        const double n2 = G2 + r[6] * G5;
-                        const double n3 = r[7] * G3 + r[8] * G4 + r[9] * G5;
-                        const double n4 = r[10] * G3 + r[11] * G4 + r[12] * G5;
-                        const double n5 = r[13] * G3 + r[14] * G4 + r[15] * G5;
-                        G0 = n0; G1 = n1; G2 = n2; G3 = n3; G4 = n4; G5 = n5;
-                    } else if (j < 2 * k + 2) {  // new block column: B_k
-                        const bool c1 = (j - 2 * k) != 0;
-                        G0 = 0.0; G1 = 0.0; G2 = 0.0;
-                        G3 = c1 ? r[17] : r[16]; G4 = c1 ? r[19] : r[18]; G5 = c1 ? r[21] : r[20];
-                    }
+                    const double n0 = G0 + r[0] * G2 + r[1] * G3 + r[2] * G4;   // G_{k+1} = A_k G_k
+                    const double n1 = G1 + r[3] * G2 + r[4] * G3 + r[5] * G4;
+                    const double n2 = G2 + r[6] * G5;
+                    const double n3 = r[7] * G3 + r[8] * G4 + r[9] * G5;
+                    const double n4 = r[10] * G3 + r[11] * G4 + r[12] * G5;
+                    const double n5 = r[13] * G3 + r[14] * G4 + r[15] * G5;
+                    const bool born = (j >> 1) == k, c1 = (j & 1) != 0;            // new block column: B_k
+                    G0 = born ? 0.0 : n0; G1 = born ? 0.0 : n1; G2 = born ? 0.0 : n2;
+                    G3 = born ? (c1 ? r[17] : r[16]) : n3;
+                    G4 = born ? (c1 ? r[19] : r[18]) : n4;
+                    G5 = born ? (c1 ? r[21] : r[20]) : n5;
                     const int kk = k + 1;
                     const double wc = sqc * (sn[kk] * G0 - cs[kk] * G1), wp = sqp * G2, wv = sqv * G3;
                     wb[jpad] = wc; wb[NPP + jpad] = wp; wb[2 * NPP + jpad] = wv;
@@ -531,9 +561,18 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                         const double gv = (sx == 0) ? G0 : (sx == 1) ? G1 : (sx == 2) ? G2 : (sx == 3) ? G3 : (sx == 4) ? G4 : G5;
                         Gs[(k * ns + si) * NP + j] = gv;
                     }
+                };
+                if (kb == TG_KB) {
+#pragma unroll
+                    for (int s_i = 0; s_i < TG_KB; ++s_i) stage(k0 + s_i, s_i);
+                } else {
+#pragma unroll 1
+                    for (int s_i = 0; s_i < kb; ++s_i) stage(k0 + s_i, s_i);
                 }
             }
+            TG_TICK(13);
             tg_psync<MULTI>(bar, NT);
+            TG_TICK(14);
 #pragma unroll 1
             for (int s_i = 0; s_i < kb; ++s_i) {
                 const int k = k0 + s_i;
@@ -561,6 +600,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 }
             }
         }
+        TG_TICK(15);
         if (tid < n) {
             const int cc = tid & 1;
             q[tid] = qacc + 2.0 * (c.Rs[cc * 2] * sm[L.uprev] + c.Rs[cc * 2 + 1] * sm[L.uprev + 1]);
