@@ -12,49 +12,49 @@ __global__ void k(double *out, long long *t, double a, double b, const double *t
         for (int j = 0; j < 16; ++j) x = fma(x, b, a);
     }
     long long t1 = clock64();
-    double y = x;
+    double y = a * 3.0 + threadIdx.x;
 #pragma unroll 1
     for (int i = 0; i < 64; ++i) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) y = y * b;
     }
     long long t2 = clock64();
-    double z = y;
+    double z = a * 5.0;
 #pragma unroll 1
     for (int i = 0; i < 64; ++i) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { sm[threadIdx.x] = z; z = sm[threadIdx.x ^ 1] + 1.0; }
+        for (int j = 0; j < 16; ++j) { sm[threadIdx.x] = z; __syncwarp(); z = sm[threadIdx.x ^ 1] + 1.0; __syncwarp(); }
     }
     long long t3 = clock64();
-    double w = z;
+    double w = a * 7.0;
 #pragma unroll 1
     for (int i = 0; i < 64; ++i) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) w = __shfl_sync(0xffffffffu, w, (threadIdx.x + 1) & 31) + 1.0;
     }
     long long t4 = clock64();
-    double v = w;
+    double v = a * 9.0;
 #pragma unroll 1
     for (int i = 0; i < 64; ++i) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v = __ldg(tab + ((int)v & 63)) + v;
     }
     long long t5 = clock64();
-    double q = v;
+    double q = a * 11.0;
 #pragma unroll 1
     for (int i = 0; i < 64; ++i) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) { __syncthreads(); q = q + 1.0; }
     }
     long long t6 = clock64();
-    float fq = (float)q;
+    float fq = (float)a;
 #pragma unroll 1
     for (int i = 0; i < 64; ++i) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) fq = fmaf(fq, 1.0001f, 0.5f);
     }
     long long t7 = clock64();
-    out[threadIdx.x] = q + fq;
+    out[threadIdx.x] = q + fq + x + y + z + w + v;
     if (threadIdx.x == 0) { t[0] = t1 - t0; t[1] = t2 - t1; t[2] = t3 - t2; t[3] = t4 - t3; t[4] = t5 - t4; t[5] = t6 - t5; t[6] = t7 - t6; }
 }
 int main()
