@@ -63,8 +63,12 @@ tg_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Sme
 {
     extern __shared__ __align__(16) double sm_all[];
     constexpr int NT = TG_NT(BS, TG);
-    const int P = MULTI ? a.ppc : 1, prob = MULTI ? threadIdx.x / NT : 0, tid = MULTI ? threadIdx.x % NT : threadIdx.x, bar = 1 + prob;
-    double *sm = sm_all + (size_t)prob * ((L.total + 1) & ~1);
+    const int P = MULTI ? a.ppc : 1;
+    int prob = MULTI ? threadIdx.x / NT : 0, tid = MULTI ? threadIdx.x % NT : threadIdx.x;
+    unsigned sm_off = (unsigned)prob * (unsigned)((L.total + 1) & ~1) * 8u;
+    asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));   // see tg_closed_loop_kernel
+    const int bar = 1 + prob;
+    double *sm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm_all) + sm_off);
     const int N = c.N, n = c.n, m = c.m;
     double *Hws = a.Hws ? a.Hws + ((size_t)blockIdx.x * P + prob) * c.NP * c.NP : nullptr;
     for (int b0 = blockIdx.x * P; b0 < a.B; b0 += gridDim.x * P) {
@@ -192,8 +196,13 @@ tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
     extern __shared__ __align__(16) double sm_all[];
     constexpr int NT = TG_NT(BS, TG);
     const int P = MULTI ? a.ppc : 1;
-    const int prob = MULTI ? threadIdx.x / NT : 0, tid = MULTI ? threadIdx.x % NT : threadIdx.x, bar = 1 + prob;
-    double *sm = sm_all + (size_t)prob * ((L.total + 1) & ~1);
+    int prob = MULTI ? threadIdx.x / NT : 0, tid = MULTI ? threadIdx.x % NT : threadIdx.x;
+    unsigned sm_off = (unsigned)prob * (unsigned)((L.total + 1) & ~1) * 8u;
+    // opaque to the compiler: under register pressure it otherwise re-reads %tid.x and redoes this arithmetic at every use
+    // (45 S2R sites, 7 % of the executed instructions in the several-problems-per-CTA kernel)
+    asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));
+    const int bar = 1 + prob;
+    double *sm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm_all) + sm_off);
     const int n = c.n, ms = c.ms, ns = c.ns, T = a.T;
     double *Hws = a.Hws ? a.Hws + ((size_t)blockIdx.x * P + prob) * c.NP * c.NP : nullptr;
     const StepTaps tap = {};
