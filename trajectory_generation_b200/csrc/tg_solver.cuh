@@ -374,8 +374,12 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     constexpr int NT = TG * TG;   // threads of this problem (tid = 0..NT-1); `bar` = its named barrier
     constexpr int BSP = TgPad<BS>::BSP;
     const int N = c.N, n = c.n, NP = c.NP, NPP = c.NPP, ms = c.ms, m = c.m, ns = c.ns;
-    const int br = tid / TG, bc = tid % TG, R0 = br * BS, C0 = bc * BS;   // blockDim.x == TG*TG
-    const int jpad = (tid / BS) * BSP + tid % BS;                          // block-padded position of vector entry `tid`
+    int br_ = tid / TG, bc_ = tid % TG, jpad_ = (tid / BS) * BSP + tid % BS;
+#ifndef TG_NO_OPAQUE_TILE_INDEX
+    asm volatile("" : "+r"(br_), "+r"(bc_), "+r"(jpad_));   // kept in registers instead of being re-derived from tid at every use
+#endif
+    const int br = br_, bc = bc_, R0 = br * BS, C0 = bc * BS;           // tile block of this thread (NT == TG*TG)
+    const int jpad = jpad_;                                                // block-padded position of vector entry `tid`
     StepResult res;
     res.status = TG_STATUS_NAN; res.iters = 0; res.objective = 0.0;
 
