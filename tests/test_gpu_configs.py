@@ -172,3 +172,35 @@ def test_closed_loop_host_direct_pinned_output_equals_staged():
     finally:
         for p in ptrs.values():
             L.tg_free_host(p)
+
+
+def test_results_do_not_depend_on_problems_per_cta(monkeypatch):
+    """The 64-thread kernels run 1, 2, 4 or 8 trajectories per CTA in lockstep (shared instruction fetches); trajectories
+    share nothing else, so every grouping must give the same bits -- also when the batch leaves CTAs partly filled and
+    when it needs several rounds."""
+    B, T = 1500, 40                                             # > 1184 resident slots: two rounds, ragged tail
+    x0 = tg.sample_x0(B, seed=11); x0[:, 1:3] = 0.0; x0[:, 3] += 0.4
+    u0 = np.stack([tg.d_steady_state(x0[:, 3]), np.zeros(B)], 1)
+    sc = tg.Scenarios(B); sc.set_sine(slice(0, B, 2), A=0.4, k=0.7); sc.set_parabola(slice(1, B, 4), 0.05)
+    ref = None
+    for ppc in ("1", "2", "4", "8", "3"):
+        monkeypatch.setenv("TRAJGEN_PPC", ppc)
+        gen = tg.ClosedLoopGenerator(N=20, Ts=0.01, plant=tg.PLANT_GEN1)
+        res = gen.generate(x0, u0, sc, T, traj_id0=7)
+        if ref is None:
+            ref = res
+            assert res["status_counts"][:, :2].sum() == B * T
+        else:
+            for k in ("clean", "noisy", "U", "status_counts", "iters_total"):
+                np.testing.assert_array_equal(res[k], ref[k], err_msg=f"TRAJGEN_PPC={ppc}: {k}")
+    monkeypatch.delenv("TRAJGEN_PPC")
+    auto = tg.ClosedLoopGenerator(N=20, Ts=0.01, plant=tg.PLANT_GEN1).generate(x0, u0, sc, T, traj_id0=7)
+    np.testing.assert_array_equal(auto["clean"], ref["clean"])
+    # the step API with several problems per CTA (a batch larger than the resident slots) against single-problem CTAs
+    ctl = tg.BatchedMPC(N=20, Ts=0.01)
+    pr, vr = gen.ref_window(x0, sc)
+    a = ctl.step(x0, u0, pr, vr)
+    monkeypatch.setenv("TRAJGEN_PPC", "1")
+    b = tg.BatchedMPC(N=20, Ts=0.01).step(x0, u0, pr, vr)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
