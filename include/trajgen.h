@@ -119,7 +119,8 @@ int tg_destroy(tg_handle *h);
 int tg_set_stream(tg_handle *h, void *cuda_stream);
 int tg_synchronize(tg_handle *h);
 int tg_kernel_launches(tg_handle *h, int64_t *count); /* kernels launched through this handle so far */
-/* launch geometry the handle chose: resident CTAs per SM, threads per CTA (= per problem), dynamic shared memory per CTA, SM count */
+/* launch geometry of one problem: resident problems per SM, threads per problem, dynamic shared memory per problem, SM count
+ * (the 64-thread kernels place up to 8 problems side by side in one CTA) */
 /* the tyre-curve table of this handle: whether the kernels use it (in_use bit 0; bit 1 = the
  * slip-angle atan table is in use as well), and its largest deviation
  * from libm (value of sin(C atan(B alpha)), slope) on the check grid of tg_create */
