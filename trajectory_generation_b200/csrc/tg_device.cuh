@@ -323,49 +323,6 @@ __device__ __forceinline__ void tg_f_vel_tab(const DevCfg &c, int variant, doubl
     }
 }
 
-// Same as tg_f_vel_tab but every lane evaluates both tyres itself: two independent slip-angle / tyre-curve chains that
-// the scheduler interleaves (ILP 2) instead of a lane pair joined by two 64-bit shuffles per stage.  The rare cases
-// (|n / vx_eff| beyond the atan table, vx_eff <= 0) are patched after the common path so that it stays branch-free.
-__device__ __forceinline__ void tg_f_vel_tab2(const DevCfg &c, int variant, double vx, double vy, double om, double d, double delta,
-                                              double sd, double cd, double &f3, double &f4, double &f5, double *aux = nullptr)
-{
-    const double *__restrict__ p = c.p;
-    const double ma = p[P_maxAlpha];
-    const double vmag = fmax(fabs(vx), p[P_vx_zero]);
-    const double vx_eff = (variant == TG_MODEL_MPC) ? (double)((vx > 0.0) - (vx < 0.0)) * vmag : vmag;
-    const double nf = om * p[P_lf] + vy, nr = om * p[P_lr] - vy;
-    double atf, atr;
-    if (c.atan_tab && vx_eff > 0.0) {
-        const double r = tg_rcp_pos(vx_eff);
-        const double tf = nf * r, tr = nr * r;
-        atf = tg_atan_tab(c.atan_tab, tf);
-        atr = tg_atan_tab(c.atan_tab, tr);
-        if (fabs(tf) > TG_ATAN_T0) atf = tg_atan2(nf, vx_eff);
-        if (fabs(tr) > TG_ATAN_T0) atr = tg_atan2(nr, vx_eff);
-    } else {
-        atf = tg_atan2(nf, vx_eff);
-        atr = tg_atan2(nr, vx_eff);
-    }
-    const double af_raw = -atf + delta, ar_raw = atr;
-    double gf, gr, dgf, dgr;
-    tg_tyre_tab(c.tyre_tab, tg_clamp(af_raw, -ma, ma), ma, c.tab_scale, gf, dgf);
-    tg_tyre_tab(c.tyre_tab + TG_TAB_NI * TG_TAB_NC, tg_clamp(ar_raw, -ma, ma), ma, c.tab_scale, gr, dgr);
-    const double Fyf = p[P_Df] * gf, Fyr = p[P_Dr] * gr;
-    if (aux) { aux[0] = af_raw; aux[1] = ar_raw; }
-    const double vl = (variant == TG_MODEL_MPC) ? vx : vx_eff;
-    const double Frx = (p[P_Cm1] - p[P_Cm2] * vl) * d - p[P_Cr0] - p[P_Cr2] * (vl * vl);
-    const double m = p[P_m];
-    if (variant == TG_MODEL_MPC) {
-        f3 = c.inv_m * (Frx - Fyf * sd + m * vy * om);       // (1.0/m) * (...), MPC/mpc_6stati.py:67
-        f4 = c.inv_m * (Fyr + Fyf * cd - m * vx * om);
-        f5 = c.inv_Iz * (Fyf * p[P_lf] * cd - Fyr * p[P_lr]);
-    } else {
-        f3 = (Frx - Fyf * sd + m * vy * om) / m;
-        f4 = (Fyr + Fyf * cd - m * vx * om) / m;
-        f5 = (Fyf * p[P_lf] * cd - Fyr * p[P_lr]) / p[P_Iz];
-    }
-}
-
 // plant step by a whole warp (see tg_f_cont_lanes)
 __device__ __forceinline__ void tg_plant_step_lanes(const DevCfg &c, double x[6], double d, double delta, int lane)
 {

@@ -20,9 +20,6 @@
 #pragma once
 #include "tg_device.cuh"
 
-#ifndef TG_ROLLOUT_ILP
-#define TG_ROLLOUT_ILP 0   // 1: every lane evaluates both tyres (two interleaved chains) instead of a lane pair + shuffles
-#endif
 #ifndef TG_KB
 #define TG_KB 4   // horizon stages condensed per barrier in K2
 #endif
@@ -412,11 +409,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
 #pragma unroll 1
             for (int k = 0; k < N; ++k) {
                 double f3, f4, f5;
-#if TG_ROLLOUT_ILP
-                tg_f_vel_tab2(c, c.model, vx, vy, om, ud, udel, sd, cd, f3, f4, f5, tid == 0 ? sm + L.aux + 6 * k : nullptr);
-#else
                 tg_f_vel_tab(c, c.model, vx, vy, om, ud, udel, sd, cd, tid, f3, f4, f5, sm + L.aux + 6 * k);
-#endif
                 vx = vx + c.Ts * f3; vy = vy + c.Ts * f4; om = om + c.Ts * f5;
                 if (tid == 0) { xbar[6 * (k + 1) + 3] = vx; xbar[6 * (k + 1) + 4] = vy; xbar[6 * (k + 1) + 5] = om; }
             }
