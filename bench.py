@@ -74,6 +74,31 @@ def make_workload(B, traj_id0=0, seed=2025):
 GEN_KW = dict(N=N_HORIZON, Ts=TS, plant=1, vref_advance=True)   # plant 1 = generation_type1's clipped plant
 
 
+def parity_vs_golden(golden=None, gen_kw=None, device=0):
+    """Parity of the benchmarked configuration, measured OUTSIDE the timed region: the first n_traj ids of make_workload
+    run through the public generator API for the golden file's full T and compared with the oracle closed loops stored
+    in tests/golden/oracle_bench_config.npz (exact per-step optimum, and the restated OSQP at eps 1e-5)."""
+    import trajectory_generation_b200 as tg
+    if golden is None:
+        golden = np.load(os.path.join(ROOT, "tests", "golden", "oracle_bench_config.npz"))
+    n, T = int(golden["n_traj"]), int(golden["T"])
+    x0, u0, sc = make_workload(n)
+    assert np.array_equal(x0, golden["x0"]) and np.array_equal(u0, golden["u0"]), "workload generator changed: regenerate the golden file"
+    gen = tg.ClosedLoopGenerator(device=device, **(gen_kw or GEN_KW))
+    res = gen.generate(x0, u0, sc, T)
+    gen.close()
+    eX, eU = np.abs(res["clean"] - golden["X_ipm"]), np.abs(res["U"] - golden["U_ipm"])
+    oX, oU = np.abs(res["clean"] - golden["X_osqp"]), np.abs(res["U"] - golden["U_osqp"])
+    return {"reference": "oracle closed loop (MPC/main.py:85-101 restated), exact optimum per step", "n_traj": n, "T": T,
+            "max_abs_err_X": float(eX.max()), "max_abs_err_U": float(eU.max()),
+            "rms_err_X": float(np.sqrt((eX ** 2).mean())), "rms_err_U": float(np.sqrt((eU ** 2).mean())),
+            "max_abs_err_X_vs_osqp": float(oX.max()), "max_abs_err_U_vs_osqp": float(oU.max()),
+            "oracle_ipm_vs_osqp_X": float(np.abs(golden["X_ipm"] - golden["X_osqp"]).max()),
+            "oracle_ipm_vs_osqp_U": float(np.abs(golden["U_ipm"] - golden["U_osqp"]).max()),
+            "all_steps_accepted": bool(res["status_counts"][:, :2].sum() == n * T),
+            "mean_admm_iters": float(res["iters_total"].sum() / (n * T))}
+
+
 def algorithmic_flops_per_step(N, iters, check_every):
     """SURVEY.md section 8(d) convention (add/mul = 1, FMA = 2, transcendental/div/sqrt = 1), analytic Jacobians."""
     F_lin = 420 * N
