@@ -87,14 +87,25 @@ def parity_vs_golden(golden=None, gen_kw=None, device=0):
     gen = tg.ClosedLoopGenerator(device=device, **(gen_kw or GEN_KW))
     res = gen.generate(x0, u0, sc, T)
     gen.close()
-    eX, eU = np.abs(res["clean"] - golden["X_ipm"]), np.abs(res["U"] - golden["U_ipm"])
-    oX, oU = np.abs(res["clean"] - golden["X_osqp"]), np.abs(res["U"] - golden["U_osqp"])
+    # Steps at which the reference's central differences straddle a JUMP of f_cont (golden["fd_jump"])
+    # are not comparable: there the reference's Jacobian is the jump divided by 2 eps.  A trajectory is compared up to its
+    # first such step; what follows it is reported separately (the loops re-converge within a few steps).
+    jump = golden["fd_jump"]
+    first = np.where(jump.any(1), jump.argmax(1), T)                      # first artefact step per trajectory, T = none
+    mU = np.arange(T)[None, :] < first[:, None]                             # U[t] comparable
+    mX = np.arange(T + 1)[None, :] <= first[:, None]                        # X[t] comparable (X[first] is still pre-artefact)
+    dX, dU = np.abs(res["clean"] - golden["X_ipm"]), np.abs(res["U"] - golden["U_ipm"])
+    eX, eU = dX[mX], dU[mU]
+    oX, oU = np.abs(res["clean"] - golden["X_osqp"])[mX], np.abs(res["U"] - golden["U_osqp"])[mU]
     return {"reference": "oracle closed loop (MPC/main.py:85-101 restated), exact optimum per step", "n_traj": n, "T": T,
             "max_abs_err_X": float(eX.max()), "max_abs_err_U": float(eU.max()),
             "rms_err_X": float(np.sqrt((eX ** 2).mean())), "rms_err_U": float(np.sqrt((eU ** 2).mean())),
             "max_abs_err_X_vs_osqp": float(oX.max()), "max_abs_err_U_vs_osqp": float(oU.max()),
-            "oracle_ipm_vs_osqp_X": float(np.abs(golden["X_ipm"] - golden["X_osqp"]).max()),
-            "oracle_ipm_vs_osqp_U": float(np.abs(golden["U_ipm"] - golden["U_osqp"]).max()),
+            "oracle_ipm_vs_osqp_X": float(np.abs(golden["X_ipm"] - golden["X_osqp"])[mX].max()),
+            "oracle_ipm_vs_osqp_U": float(np.abs(golden["U_ipm"] - golden["U_osqp"])[mU].max()),
+            "compared_steps": int(mU.sum()), "fd_jump_trajectories": np.nonzero(jump.any(1))[0].tolist(),
+            "max_abs_err_X_after_fd_jump": float(dX[~mX].max()) if (~mX).any() else 0.0,
+            "max_abs_err_X_last_100_steps": float(dX[:, -100:].max()),
             "all_steps_accepted": bool(res["status_counts"][:, :2].sum() == n * T),
             "mean_admm_iters": float(res["iters_total"].sum() / (n * T))}
 

@@ -93,7 +93,7 @@ typedef struct tg_config {
     double noise_std[6];
     uint64_t noise_seed_base;
     int32_t threads_per_problem; /* reserved, must be 0: the launch geometry follows from N (tg_info reports it) */
-    int32_t reserved;
+    int32_t solver_flags;        /* bit 0: do NOT start solves that have no active row in "free" mode (rho 1e-6, alpha 1) */
 } tg_config;
 
 /* one reference scenario per trajectory (closed loop) */

@@ -39,7 +39,16 @@ def _one(args):
                                      spline=spline, vref_kind=int(spec["vref_kind"]), vref_prm=tuple(spec["vref"]),
                                      vref_advance=True, plant=dyn.PLANT_GEN1, solver=solver)
     ok = np.array([s in ompc.ACCEPTED for s in st])
-    return b, solver, X, U, ok, its
+    jump = np.zeros(T, bool)
+    if solver == "ipm":
+        # steps at which the reference's central differences (MPC/mpc_6stati.py:73-97) straddle a JUMP of f_cont -- the
+        # atan2 branch cut behind vx_eff < 0 or the sign flip at vx = 0, reached when the nominal rollout brakes through
+        # standstill -- and return the jump divided by 2 eps (entries of ~2e5 in Ad) instead of a derivative
+        up = np.vstack([u0, U[:-1]])
+        for t in range(T):
+            A = dyn.linearize_horizon(X[t], up[t], bench.TS, bench.N_HORIZON)[0]
+            jump[t] = np.abs(A).max() > 1e3
+    return b, solver, X, U, ok, its, jump
 
 
 def main():
@@ -59,11 +68,14 @@ def main():
         out[f"U_{s}"] = np.stack([r[3] for r in rs])
         out[f"ok_{s}"] = np.stack([r[4] for r in rs])
         out[f"iters_{s}"] = np.stack([r[5] for r in rs]).astype(np.int32)
+        if s == "ipm":
+            out["fd_jump"] = np.stack([r[6] for r in rs])
     path = os.path.join(ROOT, "tests", "golden", "oracle_bench_config.npz")
     np.savez_compressed(path, **out)
     d = np.abs(out["X_ipm"] - out["X_osqp"]).max(), np.abs(out["U_ipm"] - out["U_osqp"]).max()
     print(f"wrote {path} in {time.time() - t0:.0f} s; |X_ipm - X_osqp| {d[0]:.2e}, |U_ipm - U_osqp| {d[1]:.2e}; "
-          f"non-accepted steps ipm {int((~out['ok_ipm']).sum())}, osqp {int((~out['ok_osqp']).sum())}")
+          f"non-accepted steps ipm {int((~out['ok_ipm']).sum())}, osqp {int((~out['ok_osqp']).sum())}; "
+          f"steps with a finite-difference jump artefact {int(out['fd_jump'].sum())} in trajectories {np.nonzero(out['fd_jump'].any(1))[0].tolist()}")
 
 
 if __name__ == "__main__":

@@ -15,13 +15,13 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
-# Stated tolerances.  The closed loop is a feedback system: a per-step solver error e_t is fed back through the plant and
-# largely rejected by the next solve, so the distance between two runs stays of the order of the per-step solver tolerance
-# times a modest gain.  The oracle's own two solvers differ by |dX| 3.8e-3 / |dU| 8.0e-3 over these runs (OSQP at eps 1e-5
-# stops up to ~1e-2 from the optimum on single steps), which is the yardstick for "within the solver
-# tolerance"; the CUDA path is held to 1e-3 of the EXACT optimum, i.e. tighter than the reference's own solver is.
-TOL_X_VS_EXACT = 1e-3
-TOL_U_VS_EXACT = 1e-3
+# Stated tolerance.  The closed loop is a feedback system: a per-step solver error is fed back through the plant, amplified by
+# the stiff yaw dynamics for a step or two (x40 was observed where the duty cycle leaves its bound) and then rejected.  The
+# oracle's own two solvers differ by |dX| 3.8e-3 / |dU| 8.0e-3 over these runs (OSQP at CVXPY's eps = 1e-5 stops up to ~1e-2
+# from the optimum on single steps).  The CUDA path is held to 1e-4 of the EXACT-optimum loop over all 1200
+# steps; measured 7e-7 (X) / 2e-6 (U) with the library defaults (eps 1e-6; unconstrained steps are solved to rounding).
+TOL_X_VS_EXACT = 1e-4
+TOL_U_VS_EXACT = 1e-4
 
 
 @pytest.fixture(scope="module")
@@ -34,11 +34,15 @@ def test_benchmarked_configuration_matches_oracle_closed_loop(golden):
     print(par)
     assert par["n_traj"] >= 32 and par["T"] == 1200
     assert par["all_steps_accepted"]
+    # 2 of the 32 trajectories brake through standstill in the nominal rollout of one early step, where the reference's central
+    # differences straddle a jump of f (fd_jump); they are compared up to that step and must have re-converged by the end
+    assert par["compared_steps"] >= 32 * 1200 - 2 * 1200
+    assert par["max_abs_err_X_last_100_steps"] <= TOL_X_VS_EXACT, par
     assert par["max_abs_err_X"] <= TOL_X_VS_EXACT, par
     assert par["max_abs_err_U"] <= TOL_U_VS_EXACT, par
     # distance to the restated OSQP at matched eps: not larger than the oracle's own IPM-vs-OSQP distance
-    assert par["max_abs_err_X_vs_osqp"] <= 1.05 * par["oracle_ipm_vs_osqp_X"] + TOL_X_VS_EXACT
-    assert par["max_abs_err_U_vs_osqp"] <= 1.05 * par["oracle_ipm_vs_osqp_U"] + TOL_U_VS_EXACT
+    assert par["max_abs_err_X_vs_osqp"] <= par["oracle_ipm_vs_osqp_X"] + TOL_X_VS_EXACT
+    assert par["max_abs_err_U_vs_osqp"] <= par["oracle_ipm_vs_osqp_U"] + TOL_U_VS_EXACT
 
 
 def test_benchmarked_configuration_is_batch_and_shard_invariant(golden):

@@ -37,7 +37,7 @@ class TgConfig(ctypes.Structure):
         ("max_iter", i32), ("check_every", i32), ("adaptive_rho", i32), ("adaptive_rho_min_iter", i32),
         ("warm_start", i32), ("vref_advance", i32),
         ("noise_std", d * 6), ("noise_seed_base", u64),
-        ("threads_per_problem", i32), ("reserved", i32),
+        ("threads_per_problem", i32), ("solver_flags", i32),
     ]
 
 

@@ -13,11 +13,13 @@
 
 #include "../../include/trajgen.h"
 
-#define TG_LIN 28  // compact per-stage linearisation record (see lin_store)
-#define TG_TAB_NI 64   // intervals of the tyre-curve table
+#define TG_LIN 20  // compact per-stage linearisation record (see tg_lin_expand); g is kept separately (6 per stage)
+#define TG_TAB_NI 64   // the tyre-curve table has TG_TAB_NI + 1 intervals, centred on alpha_i = -maxAlpha + i * 2 maxAlpha / TG_TAB_NI
 #define TG_TAB_NC 10   // coefficients per interval (degree 9 in the local variable s in [-1, 1])
-#define TG_ATAN_NI 128 // intervals of the atan table on [-TG_ATAN_T0, TG_ATAN_T0]
+#define TG_ATAN_NI 128 // likewise the atan table on [-TG_ATAN_T0, TG_ATAN_T0]: TG_ATAN_NI + 1 intervals
 #define TG_ATAN_T0 4.0
+#define TG_TAB_ROWS (TG_TAB_NI + 1)
+#define TG_ATAN_ROWS (TG_ATAN_NI + 1)
 
 struct DevCfg {
     int N, n;         // horizon, 2N
@@ -28,6 +30,7 @@ struct DevCfg {
     int NP;           // padded matrix width TG*BS
     int NPP;          // length of a block-padded vector, TG*BSP
     int max_iter, check_every, adaptive_rho, adaptive_rho_min_iter, warm_start, vref_advance;
+    int free_mode;    // start solves that have no active row with rho = 1e-6, alpha = 1 (tw_solver.cuh)
     double Ts;
     double p[TG_NPARAMS];
     double inv_m, inv_Iz;   // 1.0/m, 1.0/Iz (the MPC variant multiplies by them, MPC/mpc_6stati.py:67-69)
@@ -173,14 +176,35 @@ __device__ __forceinline__ void tg_f_cont_lanes(const double *__restrict__ p, do
 // not at rounding level for the caller's B, C).  It replaces two of the three dependent fp64 transcendentals of
 // every stage of the sequential nominal rollout -- the longest dependent chain of an MPC step -- by an index
 // computation and nine FMAs, and gives the linearisation dg/dalpha for free.
+// Row and local variable of a table look-up.  Interval i is CENTRED on the grid point u = i (u = (x - lo) * scale, i = 0 .. NI),
+// so the index is round-to-nearest of u: adding 1.5 * 2^52 leaves it in the low mantissa word (no F2I / I2F on the chain)
+// and subtracting it again gives the rounded value; s = 2 (u - i) lies in [-1, 1].  0 <= u <= NI is the caller's duty.
+__device__ __forceinline__ const double *tg_tab_row(const double *__restrict__ tab, double u, double &s_)
+{
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+    const double m = u + MAGIC;
+    const int i = __double2loint(m);
+    s_ = 2.0 * (u - (m - MAGIC));
+    return tab + i * TG_TAB_NC;
+}
+// value of a table row at s: two interleaved Horner chains in s^2 (even / odd coefficients), half the dependent depth
+__device__ __forceinline__ double tg_tab_val(const double *__restrict__ row, double s_)
+{
+    const double2 *c2 = reinterpret_cast<const double2 *>(row);
+    const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3), c89 = __ldg(c2 + 4);
+    const double s2 = s_ * s_;
+    double ev = fma(c89.x, s2, c67.x), od = fma(c89.y, s2, c67.y);
+    ev = fma(ev, s2, c45.x); od = fma(od, s2, c45.y);
+    ev = fma(ev, s2, c23.x); od = fma(od, s2, c23.y);
+    ev = fma(ev, s2, c01.x); od = fma(od, s2, c01.y);
+    return fma(od, s_, ev);
+}
+
 __device__ __forceinline__ void tg_tyre_tab(const double *__restrict__ tab, double alpha, double ma, double scale,
                                             double &g, double &dg)
 {
-    const double u = (alpha + ma) * scale;
-    int i = (int)u;
-    i = i < 0 ? 0 : (i > TG_TAB_NI - 1 ? TG_TAB_NI - 1 : i);
-    const double s_ = 2.0 * (u - (double)i) - 1.0;
-    const double2 *c2 = reinterpret_cast<const double2 *>(tab + i * TG_TAB_NC);
+    double s_;
+    const double2 *c2 = reinterpret_cast<const double2 *>(tg_tab_row(tab, (alpha + ma) * scale, s_));
     const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3), c89 = __ldg(c2 + 4);
     double v = c89.y, d_ = 0.0;   // Horner for the value and its derivative together
     d_ = fma(d_, s_, v); v = fma(v, s_, c89.x);
@@ -194,6 +218,13 @@ __device__ __forceinline__ void tg_tyre_tab(const double *__restrict__ tab, doub
     d_ = fma(d_, s_, v); v = fma(v, s_, c01.x);
     g = v;
     dg = d_ * (2.0 * scale);
+}
+// the value alone (nominal rollout, plant): short dependent chain
+__device__ __forceinline__ double tg_tyre_val(const double *__restrict__ tab, double alpha, double ma, double scale)
+{
+    double s_;
+    const double *row = tg_tab_row(tab, fma(alpha, scale, ma * scale), s_);
+    return tg_tab_val(row, s_);
 }
 
 // 1 / x for x > 0 to ~1 ulp without the IEEE division sequence: hardware seed + two Newton steps
@@ -209,19 +240,9 @@ __device__ __forceinline__ double tg_rcp_pos(double x)
 // atan(t) for |t| <= TG_ATAN_T0 from the table (1e-16; nearest singularities of atan are at +-i, far from every interval)
 __device__ __forceinline__ double tg_atan_tab(const double *__restrict__ tab, double t)
 {
-    const double u = (t + TG_ATAN_T0) * (TG_ATAN_NI / (2.0 * TG_ATAN_T0));
-    int i = (int)u;
-    i = i < 0 ? 0 : (i > TG_ATAN_NI - 1 ? TG_ATAN_NI - 1 : i);
-    const double s_ = 2.0 * (u - (double)i) - 1.0;
-    const double2 *c2 = reinterpret_cast<const double2 *>(tab + i * TG_TAB_NC);
-    const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3), c89 = __ldg(c2 + 4);
-    // two interleaved Horner chains in s^2 (even / odd coefficients): half the dependent depth of a plain Horner
-    const double s2 = s_ * s_;
-    double ev = fma(c89.x, s2, c67.x), od = fma(c89.y, s2, c67.y);
-    ev = fma(ev, s2, c45.x); od = fma(od, s2, c45.y);
-    ev = fma(ev, s2, c23.x); od = fma(od, s2, c23.y);
-    ev = fma(ev, s2, c01.x); od = fma(od, s2, c01.y);
-    return fma(od, s_, ev);
+    double s_;
+    const double *row = tg_tab_row(tab, fma(t, TG_ATAN_NI / (2.0 * TG_ATAN_T0), TG_ATAN_NI / 2.0), s_);
+    return tg_tab_val(row, s_);
 }
 
 // atan2(y, x) for the slip angles: x = vx_eff.  With x > 0 (always for the generator variants, and for the MPC variant
@@ -269,7 +290,7 @@ __device__ __forceinline__ void tg_f_cont_tab(const DevCfg &c, int variant, cons
     const double alpha_raw = rear ? at : (-at + delta);
     const double alpha = tg_clamp(alpha_raw, -p[P_maxAlpha], p[P_maxAlpha]);
     double g, dg;
-    tg_tyre_tab(c.tyre_tab + rear * (TG_TAB_NI * TG_TAB_NC), alpha, p[P_maxAlpha], c.tab_scale, g, dg);
+    tg_tyre_tab(c.tyre_tab + rear * (TG_TAB_ROWS * TG_TAB_NC), alpha, p[P_maxAlpha], c.tab_scale, g, dg);
     const double F = (rear ? p[P_Dr] : p[P_Df]) * g;
     if (aux && lane < 2) { aux[rear] = alpha_raw; aux[2 + rear] = rear ? cp : sp; }
     const double Fyf = __shfl_sync(0xffffffffu, F, base), Fyr = __shfl_sync(0xffffffffu, F, base + 1);
@@ -305,7 +326,7 @@ __device__ __forceinline__ void tg_f_vel_tab(const DevCfg &c, int variant, doubl
     const double alpha_raw = rear ? at : (-at + delta);
     const double alpha = tg_clamp(alpha_raw, -p[P_maxAlpha], p[P_maxAlpha]);
     double g, dg;
-    tg_tyre_tab(c.tyre_tab + rear * (TG_TAB_NI * TG_TAB_NC), alpha, p[P_maxAlpha], c.tab_scale, g, dg);
+    tg_tyre_tab(c.tyre_tab + rear * (TG_TAB_ROWS * TG_TAB_NC), alpha, p[P_maxAlpha], c.tab_scale, g, dg);
     const double F = (rear ? p[P_Dr] : p[P_Df]) * g;
     if (aux && lane < 2) aux[rear] = alpha_raw;
     const double Fyf = __shfl_sync(0xffffffffu, F, base), Fyr = __shfl_sync(0xffffffffu, F, base + 1);
@@ -321,6 +342,72 @@ __device__ __forceinline__ void tg_f_vel_tab(const DevCfg &c, int variant, doubl
         f4 = (Fyr + Fyf * cd - m * vx * om) / m;
         f5 = (Fyf * p[P_lf] * cd - Fyr * p[P_lr]) / p[P_Iz];
     }
+}
+
+// One Euler stage of the velocity recurrence (vx, vy, omega) <- (vx, vy, omega) + Ts f_{3..5} by a lane pair (lane & 1:
+// 0 = front tyre, 1 = rear tyre), written for the SHORTEST dependent chain: this recurrence is the longest sequential chain
+// of an MPC step (N stages, nothing else of the step can start before it ends).  Per-step constants are hoisted into
+// TgRoll; the tables are indexed without F2I / I2F; clamps are compare-selects; the force exchange is one xor-shuffle; the
+// sums are re-associated so that two FMAs follow the tyre force (results differ from tg_f_vel_tab in the last bit only).
+// Variants MPC / GEN2 (both slip angles clamped).  aux (optional, shared memory) receives the slip angle before the clamp.
+struct TgRoll {
+    double L, svy, sa, da, D, ma, tscale, toff, Ts_im, Ts_iI5f, Ts_iI5r, cdm, d, sd;
+    const double *tyre;
+    int rear;
+};
+__device__ __forceinline__ TgRoll tg_roll_setup(const DevCfg &c, double d, double delta, double sd, double cd, int lane)
+{
+    const double *__restrict__ p = c.p;
+    TgRoll k;
+    k.rear = lane & 1;
+    k.L = k.rear ? p[P_lr] : p[P_lf];
+    k.svy = k.rear ? -1.0 : 1.0;                       // n = omega L + svy vy
+    k.sa = k.rear ? 1.0 : -1.0; k.da = k.rear ? 0.0 : delta;   // alpha = sa atan(n / vx_eff) + da
+    k.D = k.rear ? p[P_Dr] : p[P_Df];
+    k.ma = p[P_maxAlpha]; k.tscale = c.tab_scale; k.toff = p[P_maxAlpha] * c.tab_scale;
+    k.tyre = c.tyre_tab + k.rear * (TG_TAB_ROWS * TG_TAB_NC);
+    k.Ts_im = c.Ts * c.inv_m;
+    k.Ts_iI5f = c.Ts * c.inv_Iz * p[P_lf] * cd; k.Ts_iI5r = c.Ts * c.inv_Iz * p[P_lr];
+    k.cdm = cd; k.d = d; k.sd = sd;
+    return k;
+}
+__device__ __forceinline__ void tg_roll_stage(const DevCfg &c, const TgRoll &k, int variant, double &vx, double &vy, double &om,
+                                              int lane, double *aux)
+{
+    const double *__restrict__ p = c.p;
+    const double vz = p[P_vx_zero];
+    double veff = vx;                                    // sign(vx) max(|vx|, vx_zero) = vx while vx >= vx_zero
+    if (!(vx >= vz)) {
+        const double vmag = fmax(fabs(vx), vz);
+        veff = (variant == TG_MODEL_MPC) ? (double)((vx > 0.0) - (vx < 0.0)) * vmag : vmag;
+    }
+    const double n = fma(om, k.L, k.svy * vy);
+    double at;
+    {
+        const double t = n * tg_rcp_pos(veff);
+        if (c.atan_tab && veff > 0.0 && fabs(t) <= TG_ATAN_T0) at = tg_atan_tab(c.atan_tab, t);
+        else at = tg_atan2(n, veff);
+    }
+    const double araw = fma(k.sa, at, k.da);
+    double al = araw > k.ma ? k.ma : araw;
+    al = al < -k.ma ? -k.ma : al;
+    double s_;
+    const double *row = tg_tab_row(k.tyre, fma(al, k.tscale, k.toff), s_);
+    const double F = k.D * tg_tab_val(row, s_);
+    if (aux && lane < 2) aux[k.rear] = araw;
+    // everything that does not wait for the tyre force
+    const double vl = (variant == TG_MODEL_MPC) ? vx : veff;
+    const double Frx = (p[P_Cm1] - p[P_Cm2] * vl) * k.d - p[P_Cr0] - p[P_Cr2] * (vl * vl);
+    const double m = p[P_m];
+    const double b3 = fma(m * vy, om, Frx), b4 = -m * vx * om;
+    const double vx0 = fma(k.Ts_im, b3, vx), vy0 = fma(k.Ts_im, b4, vy);
+    const double Fo = __shfl_xor_sync(0xffffffffu, F, 1);
+    const double Fyf = k.rear ? Fo : F, Fyr = k.rear ? F : Fo;
+    // vx' = vx + Ts/m (Frx - Fyf sin(delta) + m vy om);  vy' = vy + Ts/m (Fyr + Fyf cos(delta) - m vx om);
+    // om' = om + Ts/Iz (Fyf lf cos(delta) - Fyr lr)
+    vx = fma(-k.Ts_im * k.sd, Fyf, vx0);
+    vy = fma(k.Ts_im, fma(Fyf, k.cdm, Fyr), vy0);
+    om = fma(k.Ts_iI5f, Fyf, fma(-k.Ts_iI5r, Fyr, om));
 }
 
 // plant step by a whole warp (see tg_f_cont_lanes)
@@ -359,7 +446,7 @@ __device__ __forceinline__ void tg_plant_step_gen(const DevCfg &c, double x[6], 
     double gf, gr, dg;
     if (c.tyre_tab) {
         tg_tyre_tab(c.tyre_tab, af, ma, c.tab_scale, gf, dg);
-        if (fabs(ar) <= ma) tg_tyre_tab(c.tyre_tab + TG_TAB_NI * TG_TAB_NC, ar, ma, c.tab_scale, gr, dg);
+        if (fabs(ar) <= ma) tg_tyre_tab(c.tyre_tab + TG_TAB_ROWS * TG_TAB_NC, ar, ma, c.tab_scale, gr, dg);
         else gr = tg_sin(p[P_Cr] * tg_atan(p[P_Br] * ar));
     } else {
         gf = tg_sin(p[P_Cf] * tg_atan(p[P_Bf] * af));
@@ -386,11 +473,12 @@ __device__ __forceinline__ void tg_plant_step_gen(const DevCfg &c, double x[6], 
 // ------------------------------------------------------------------------------------------------
 // Compact linearisation record of one stage.  For every variant and both Jacobian modes the full
 // 6x6 / 6x2 matrices have this sparsity exactly (f does not depend on X,Y; phi enters rows 0,1 only;
-// rows 0-2 do not depend on u), so nothing is lost:
+// rows 0-2 do not depend on u; rows 4,5 do not depend on d), so nothing is lost:
 //   [0..2]  A[0][2],A[0][3],A[0][4]   [3..5] A[1][2],A[1][3],A[1][4]   [6] A[2][5]
-//   [7..15] A[3..5][3..5] row-major   [16..21] B[3..5][0..1] row-major [22..27] g[0..5]
-//   A[i][i] = 1 for i<3, everything else 0.
-__device__ __forceinline__ void tg_lin_expand(const double *__restrict__ r, double *A, double *Bm, double *g)
+//   [7..15] A[3..5][3..5] row-major   [16] B[3][0]  [17] B[3][1]  [18] B[4][1]  [19] B[5][1]
+//   A[i][i] = 1 for i<3, everything else 0.   g[0..5] goes to a separate array (only the taps / X_opt need it:
+//   the nominal rollout IS the affine recursion, x_k = xbar_k + sum_j G_kj dU_j).
+__device__ __forceinline__ void tg_lin_expand(const double *__restrict__ r, const double *__restrict__ gv, double *A, double *Bm, double *g)
 {
     if (A) {
         for (int i = 0; i < 36; ++i) A[i] = 0.0;
@@ -402,11 +490,11 @@ __device__ __forceinline__ void tg_lin_expand(const double *__restrict__ r, doub
             for (int j = 0; j < 3; ++j) A[(3 + i) * 6 + 3 + j] = r[7 + 3 * i + j];
     }
     if (Bm) {
-        for (int i = 0; i < 6; ++i) Bm[i] = 0.0;
-        for (int i = 0; i < 6; ++i) Bm[6 + i] = r[16 + i];
+        for (int i = 0; i < 12; ++i) Bm[i] = 0.0;
+        Bm[6] = r[16]; Bm[7] = r[17]; Bm[9] = r[18]; Bm[11] = r[19];
     }
-    if (g)
-        for (int i = 0; i < 6; ++i) g[i] = r[22 + i];
+    if (g && gv)
+        for (int i = 0; i < 6; ++i) g[i] = gv[i];
 }
 
 // Analytic linearisation at (x, u): Ad = I + Ts df/dx, Bd = Ts df/du, g = Ts (f - Jx x - Ju u).
@@ -415,9 +503,16 @@ __device__ __forceinline__ void tg_lin_expand(const double *__restrict__ r, doub
 // this point, so the two atan2, two atan and one sincos of the linearisation are not recomputed.
 // With `tab_aux` = {alpha_f, alpha_r before the clamp, sin(phi), cos(phi)} (table path) the tyre force and its slope
 // come from the table and no transcendental is evaluated at all.
-__device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double d, double delta, double sd,
-                                      double cd, double *__restrict__ rec, const double *__restrict__ aux = nullptr,
-                                      const double *__restrict__ tab_aux = nullptr)
+// Returns true when the reference's central-difference stencil (MPC/mpc_6stati.py:73-97, eps = 1e-5 on every state and
+// input) straddles a CONTINUOUS kink of f -- |vx| = vx_zero or a slip-angle clamp -- where the reference's Jacobian is a
+// blend of the two one-sided slopes.  The caller re-evaluates such a stage with tg_linearize_fd: parity is with what the
+// reference computes.  NOT covered, on purpose: stencils that straddle a JUMP of f (the atan2 branch cut behind
+// vx_eff < 0, the sign flip at vx = 0; a nominal rollout that brakes through standstill ends up there with n ~ 0).  The
+// reference then returns jump / (2 eps) -- entries of ~2e5 in Ad, cond(H) 1e13..1e15 after condensing -- which no
+// condensed solver can carry in fp64; the closed form keeps the one-sided derivative there.
+__device__ bool tg_linearize_analytic(const DevCfg &c, const double x[6], double d, double delta, double sd,
+                                      double cd, double *__restrict__ rec, double *__restrict__ gout,
+                                      const double *__restrict__ aux = nullptr, const double *__restrict__ tab_aux = nullptr)
 {
     const double *p = c.p;
     const int variant = c.model;
@@ -438,6 +533,13 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
     // partials of the slip angles (zero where the clamp is active)
     double af_vx = (nf / denf) * dveff, af_vy = -vx_eff / denf, af_om = -lf * vx_eff / denf, af_de = 1.0;
     double ar_vx = -(nr / denr) * dveff, ar_vy = -vx_eff / denr, ar_om = lr * vx_eff / denr;
+    bool near_kink;
+    {
+        const double eps = 1e-5;                                   // the reference's eps_x = eps_u
+        const double da = 1.0001 * eps * fmax(1.0, 1.0 / vmag);    // first-order reach of a slip angle over the stencil
+        near_kink = fabs(avx - p[P_vx_zero]) <= eps || fabs(fabs(af) - ma) <= da ||
+                    (variant != TG_MODEL_GEN1 && fabs(fabs(ar) - ma) <= da);
+    }
     if (af > ma || af < -ma) { af = tg_clamp(af, -ma, ma); af_vx = af_vy = af_om = af_de = 0.0; }
     if (variant != TG_MODEL_GEN1 && (ar > ma || ar < -ma)) { ar = tg_clamp(ar, -ma, ma); ar_vx = ar_vy = ar_om = 0.0; }
     double Fyf, Fyr, dFf, dFr;   // forces and dF / d alpha
@@ -445,7 +547,7 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
         double g, dg;
         tg_tyre_tab(c.tyre_tab, af, ma, c.tab_scale, g, dg);
         Fyf = p[P_Df] * g; dFf = p[P_Df] * dg;
-        tg_tyre_tab(c.tyre_tab + TG_TAB_NI * TG_TAB_NC, ar, ma, c.tab_scale, g, dg);
+        tg_tyre_tab(c.tyre_tab + TG_TAB_ROWS * TG_TAB_NC, ar, ma, c.tab_scale, g, dg);
         Fyr = p[P_Dr] * g; dFr = p[P_Dr] * dg;
     } else {
         double s1, c1, s2, c2;
@@ -487,21 +589,22 @@ __device__ void tg_linearize_analytic(const DevCfg &c, const double x[6], double
     rec[7] = 1.0 + Ts * j33; rec[8] = Ts * j34;        rec[9] = Ts * j35;
     rec[10] = Ts * j43;      rec[11] = 1.0 + Ts * j44; rec[12] = Ts * j45;
     rec[13] = Ts * j53;      rec[14] = Ts * j54;       rec[15] = 1.0 + Ts * j55;
-    rec[16] = Ts * b30; rec[17] = Ts * b31;
-    rec[18] = 0.0;      rec[19] = Ts * b41;
-    rec[20] = 0.0;      rec[21] = Ts * b51;
-    // g = x + Ts f - Ad x - Bd u = Ts f - (Ad - I) x - Bd u
-    rec[22] = Ts * f[0] - (rec[0] * phi + rec[1] * vx + rec[2] * vy);
-    rec[23] = Ts * f[1] - (rec[3] * phi + rec[4] * vx + rec[5] * vy);
-    rec[24] = Ts * f[2] - rec[6] * om;
-    rec[25] = Ts * f[3] - (Ts * j33 * vx + Ts * j34 * vy + Ts * j35 * om) - (rec[16] * d + rec[17] * delta);
-    rec[26] = Ts * f[4] - (Ts * j43 * vx + Ts * j44 * vy + Ts * j45 * om) - (rec[19] * delta);
-    rec[27] = Ts * f[5] - (Ts * j53 * vx + Ts * j54 * vy + Ts * j55 * om) - (rec[21] * delta);
+    const double B30 = Ts * b30, B31 = Ts * b31, B41 = Ts * b41, B51 = Ts * b51;
+    rec[16] = B30; rec[17] = B31; rec[18] = B41; rec[19] = B51;
+    if (gout) {   // g = x + Ts f - Ad x - Bd u = Ts f - (Ad - I) x - Bd u
+        gout[0] = Ts * f[0] - (rec[0] * phi + rec[1] * vx + rec[2] * vy);
+        gout[1] = Ts * f[1] - (rec[3] * phi + rec[4] * vx + rec[5] * vy);
+        gout[2] = Ts * f[2] - rec[6] * om;
+        gout[3] = Ts * f[3] - (Ts * j33 * vx + Ts * j34 * vy + Ts * j35 * om) - (B30 * d + B31 * delta);
+        gout[4] = Ts * f[4] - (Ts * j43 * vx + Ts * j44 * vy + Ts * j45 * om) - (B41 * delta);
+        gout[5] = Ts * f[5] - (Ts * j53 * vx + Ts * j54 * vy + Ts * j55 * om) - (B51 * delta);
+    }
+    return near_kink;
 }
 
 // Central-difference linearisation, the reference's arithmetic verbatim (mpc_6stati.py:73-109):
 // 12 + 4 + 1 evaluations of f_cont, eps = 1e-5, g = xbar + Ts f - Ad xbar - Bd ubar.
-__device__ __noinline__ void tg_linearize_fd(const DevCfg &c, const double x[6], double d, double delta, double *__restrict__ rec)
+__device__ __noinline__ void tg_linearize_fd(const DevCfg &c, const double x[6], double d, double delta, double *__restrict__ rec, double *__restrict__ gout)
 {
     const double eps = 1e-5;
     double Jx[6][6], Ju[6][2], f0[6], fp[6], fm[6], xx[6];
@@ -544,8 +647,9 @@ __device__ __noinline__ void tg_linearize_fd(const DevCfg &c, const double x[6],
     rec[6] = Ad[2][5];
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) rec[7 + 3 * i + j] = Ad[3 + i][3 + j];
-    for (int i = 0; i < 3; ++i) { rec[16 + 2 * i] = Bd[3 + i][0]; rec[17 + 2 * i] = Bd[3 + i][1]; }
-    for (int i = 0; i < 6; ++i) rec[22 + i] = g[i];
+    rec[16] = Bd[3][0]; rec[17] = Bd[3][1]; rec[18] = Bd[4][1]; rec[19] = Bd[5][1];   // Bd[4][0] = Bd[5][0] = 0 exactly (f4, f5 do not see d)
+    if (gout)
+        for (int i = 0; i < 6; ++i) gout[i] = g[i];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -38,7 +38,7 @@ __device__ long long g_tg_phase[16];
 
 // shared-memory layout (offsets in doubles), identical on host and device
 struct SmemLayout {
-    int x0, uprev, misc, spec, xbar, lin, aux, Xr, Yr, Pr, sn, cs, vref, rr, w, v, dsc, q, x, xt, dH, z, y, l, u, rho, rinv, zt, dy, Gs, red;
+    int x0, uprev, misc, spec, xbar, lin, gl, aux, Xr, Yr, Pr, sn, cs, vref, rr, w, v, dsc, q, x, xt, dH, z, y, l, u, rho, rinv, zt, dy, Gs, red;
     int total;
 };
 
@@ -49,7 +49,7 @@ __host__ __device__ inline SmemLayout tg_make_layout(int N, int ms, int NP, int 
     const int n = 2 * N, m = 4 * N + ms;
     auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };  // keep 16-byte alignment
     L.x0 = take(6); L.uprev = take(2); L.misc = take(24); L.spec = take(12);
-    L.xbar = take(6 * (N + 1)); L.lin = take(TG_LIN * N); L.aux = take(6 * N);
+    L.xbar = take(6 * (N + 1)); L.lin = take(TG_LIN * N); L.gl = take(6 * N); L.aux = take(6 * N);
     L.Xr = take(N + 1); L.Yr = take(N + 1); L.Pr = take(N + 1); L.sn = take(N + 1); L.cs = take(N + 1); L.vref = take(N + 1);
     L.rr = take(3 * (N + 1));
     L.w = take(2 * TG_KB * 3 * NPP); L.v = take(2 * (NPP + 2)); L.dsc = take(NPP);
@@ -80,6 +80,7 @@ struct FusedCtx {   // closed-loop extras handled inside the step body while war
 struct StepResult {
     int status, iters;
     double objective;
+    bool free_end;              // (warp-per-problem body) the solve ended with every dual at zero
 };
 
 // Block-wide max of NRED non-negative values.  The norms only feed the termination / rho tests, so they are
@@ -381,7 +382,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     const int br = br_, bc = bc_, R0 = br * BS, C0 = bc * BS;           // tile block of this thread (NT == TG*TG)
     const int jpad = jpad_;                                                // block-padded position of vector entry `tid`
     StepResult res;
-    res.status = TG_STATUS_NAN; res.iters = 0; res.objective = 0.0;
+    res.status = TG_STATUS_NAN; res.iters = 0; res.objective = 0.0; res.free_end = false;
 
     double *misc = sm + L.misc, *xbar = sm + L.xbar, *lin = sm + L.lin;
     double *sn = sm + L.sn, *cs = sm + L.cs;
@@ -481,12 +482,14 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
 #pragma unroll
             for (int i = 0; i < 6; ++i) xs[i] = xbar[6 * k + i];
             if (c.jacobian == TG_JAC_FD) {
-                tg_linearize_fd(c, xs, ud, udel, lin + TG_LIN * k);
+                tg_linearize_fd(c, xs, ud, udel, lin + TG_LIN * k, sm + L.gl + 6 * k);
             } else {
                 double sd, cd;
                 TG_SINCOS(udel, sd, cd);
-                if (c.tyre_tab && c.model != TG_MODEL_GEN1) tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k, nullptr, sm + L.aux + 6 * k);
-                else tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k, sm + L.aux + 6 * k);
+                bool kink;
+                if (c.tyre_tab && c.model != TG_MODEL_GEN1) kink = tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k, sm + L.gl + 6 * k, nullptr, sm + L.aux + 6 * k);
+                else kink = tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k, sm + L.gl + 6 * k, sm + L.aux + 6 * k);
+                if (kink) tg_linearize_fd(c, xs, ud, udel, lin + TG_LIN * k, sm + L.gl + 6 * k);   // rare: the reference's own arithmetic at a kink
             }
         }
         // stage costs at xbar: threads of the LAST warp, so that they overlap the linearisation in warp 0
@@ -508,7 +511,7 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
     tg_psync<MULTI>(bar, NT);
     if (tap.A || tap.Bm || tap.g || tap.xbar) {
         for (int k = tid; k < N; k += NT)
-            tg_lin_expand(lin + TG_LIN * k, tap.A ? tap.A + 36 * k : nullptr, tap.Bm ? tap.Bm + 12 * k : nullptr,
+            tg_lin_expand(lin + TG_LIN * k, sm + L.gl + 6 * k, tap.A ? tap.A + 36 * k : nullptr, tap.Bm ? tap.Bm + 12 * k : nullptr,
                           tap.g ? tap.g + 6 * k : nullptr);
         if (tap.xbar)
             for (int i = tid; i < 6 * (N + 1); i += NT) tap.xbar[i] = xbar[i];
@@ -538,11 +541,11 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                 // gradient term and the stores hang off it, and with the stages of a block unrolled the scheduler overlaps
                 // them with the next stage's recursion (a rolled, branchy loop cost ~900 cycles per stage).
                 auto stage = [&](int k, int s_i) {
-                    double r[22];
+                    double r[20];
                     {
                         const double2 *r2 = reinterpret_cast<const double2 *>(lin + TG_LIN * k);
 #pragma unroll
-                        for (int i = 0; i < 11; ++i) { const double2 t = r2[i]; r[2 * i] = t.x; r[2 * i + 1] = t.y; }
+                        for (int i = 0; i < 10; ++i) { const double2 t = r2[i]; r[2 * i] = t.x; r[2 * i + 1] = t.y; }
                     }
                     double *wb = wblk + s_i * 3 * NPP;
                     const double n0 = G0 + r[0] * G2 + r[1] * G3 + r[2] * G4;   // G_{k+1} = A_k G_k
@@ -554,8 +557,8 @@ __device__ StepResult tg_mpc_step_body(const DevCfg &c, const SmemLayout &L, dou
                     const bool born = (j >> 1) == k, c1 = (j & 1) != 0;            // new block column: B_k
                     G0 = born ? 0.0 : n0; G1 = born ? 0.0 : n1; G2 = born ? 0.0 : n2;
                     G3 = born ? (c1 ? r[17] : r[16]) : n3;
-                    G4 = born ? (c1 ? r[19] : r[18]) : n4;
-                    G5 = born ? (c1 ? r[21] : r[20]) : n5;
+                    G4 = born ? (c1 ? r[18] : 0.0) : n4;
+                    G5 = born ? (c1 ? r[19] : 0.0) : n5;
                     const int kk = k + 1;
                     const double wc = sqc * (sn[kk] * G0 - cs[kk] * G1), wp = sqp * G2, wv = sqv * G3;
                     wb[jpad] = wc; wb[NPP + jpad] = wp; wb[2 * NPP + jpad] = wv;

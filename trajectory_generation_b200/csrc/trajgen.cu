@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "tg_solver.cuh"
+#include "tw_solver.cuh"
 #include "tg_openloop.cuh"
 #include "tg_estimator.cuh"
 
@@ -125,15 +126,15 @@ tg_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Sme
             double xs[6];
             for (int i = 0; i < 6; ++i) { xs[i] = sm[L.x0 + i]; X[i] = ok ? xs[i] : nan(""); }
             for (int k = 0; k < N; ++k) {
-                const double *r_ = sm + L.lin + TG_LIN * k;
+                const double *r_ = sm + L.lin + TG_LIN * k, *g_ = sm + L.gl + 6 * k;
                 const double u0 = ud + sm[L.xt + 2 * k], u1 = udel + sm[L.xt + 2 * k + 1];
                 double nx[6];
-                nx[0] = xs[0] + r_[0] * xs[2] + r_[1] * xs[3] + r_[2] * xs[4] + r_[22];
-                nx[1] = xs[1] + r_[3] * xs[2] + r_[4] * xs[3] + r_[5] * xs[4] + r_[23];
-                nx[2] = xs[2] + r_[6] * xs[5] + r_[24];
-                nx[3] = r_[7] * xs[3] + r_[8] * xs[4] + r_[9] * xs[5] + r_[16] * u0 + r_[17] * u1 + r_[25];
-                nx[4] = r_[10] * xs[3] + r_[11] * xs[4] + r_[12] * xs[5] + r_[18] * u0 + r_[19] * u1 + r_[26];
-                nx[5] = r_[13] * xs[3] + r_[14] * xs[4] + r_[15] * xs[5] + r_[20] * u0 + r_[21] * u1 + r_[27];
+                nx[0] = xs[0] + r_[0] * xs[2] + r_[1] * xs[3] + r_[2] * xs[4] + g_[0];
+                nx[1] = xs[1] + r_[3] * xs[2] + r_[4] * xs[3] + r_[5] * xs[4] + g_[1];
+                nx[2] = xs[2] + r_[6] * xs[5] + g_[2];
+                nx[3] = r_[7] * xs[3] + r_[8] * xs[4] + r_[9] * xs[5] + r_[16] * u0 + r_[17] * u1 + g_[3];
+                nx[4] = r_[10] * xs[3] + r_[11] * xs[4] + r_[12] * xs[5] + r_[18] * u1 + g_[4];
+                nx[5] = r_[13] * xs[3] + r_[14] * xs[4] + r_[15] * xs[5] + r_[19] * u1 + g_[5];
                 for (int i = 0; i < 6; ++i) { xs[i] = nx[i]; X[6 * (k + 1) + i] = ok ? xs[i] : nan(""); }
             }
         }
@@ -294,6 +295,217 @@ tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ warp-per-problem kernels
+// tw_solver.cuh: W warps per problem (W = 1 for N <= 20), P problems per CTA side by side, each with its own shared-memory
+// block (and, for W > 1, its own named barrier).  Problems of a CTA are re-aligned at every step boundary (barrier 15) so that
+// they fetch the same instruction lines at the same time (the step body is ~100 KB of mostly straight-line code).
+#define TW_CTA_THREADS 512
+// register budget: S = 2 tiles take 64 registers -> 128-register kernels; S = 1 tiles take 32 -> TW_REGS_S1 registers
+#ifndef TW_REGS_S1
+#define TW_REGS_S1 128
+#endif
+#define TW_REGS(S) ((S) == 1 ? TW_REGS_S1 : 128)
+
+template <int W, int S, int NC>
+__global__ void __launch_bounds__(TW_CTA_THREADS) __maxnreg__(TW_REGS(S))
+tw_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ WLayout L, const __grid_constant__ StepArgs a)
+{
+    extern __shared__ __align__(16) double sm_all[];
+    constexpr int NT = 32 * W;
+    const int P = a.ppc;
+    int prob = threadIdx.x / NT, tid = threadIdx.x % NT;
+    unsigned sm_off = (unsigned)prob * (unsigned)((L.total + 1) & ~1) * 8u;
+    asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));   // kept in registers instead of being re-derived at every use
+    const int bar = 1 + prob;
+    double *sm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm_all) + sm_off);
+    const int N = NC > 0 ? NC : c.N, n = 2 * N, ms = c.ms;
+    if (prob >= P) return;
+    const TwMap<S> mp = tw_make_map<W, S>(LF(nb), tid);
+    for (int b0 = blockIdx.x * P; b0 < a.B; b0 += gridDim.x * P) {
+        const int b = b0 + prob;
+        if (b >= a.B) break;
+        tw_sync<W>(bar);
+        if (tid < 6) sm[LF(x0) + tid] = a.x0[6 * (size_t)b + tid];
+        if (tid < 2) sm[LF(uprev) + tid] = a.u_prev[2 * (size_t)b + tid];
+        const double vx0 = a.x0[6 * (size_t)b + 3];
+        for (int k = tid; k <= N; k += NT) {
+            if (a.path_ref) {
+                const double *pr = a.path_ref + 3 * ((size_t)b * (N + 1) + k);
+                sm[LF(Xr) + k] = pr[0]; sm[LF(Yr) + k] = pr[1]; sm[LF(Pr) + k] = pr[2];
+            } else { sm[LF(Xr) + k] = 0.0; sm[LF(Yr) + k] = 0.0; sm[LF(Pr) + k] = 0.0; }
+            sm[LF(vref) + k] = a.vref ? a.vref[(size_t)b * (N + 1) + k] : vx0;
+        }
+        bool warm = false, warm_free = false;
+        if (a.ws_valid && c.warm_start && a.ws_valid[b]) {
+            warm = true; warm_free = a.ws_valid[b] == 2;
+            const size_t m = 2 * (size_t)n + ms;
+            for (int i = tid; i < n; i += NT) sm[LF(x) + i] = a.ws_x[(size_t)b * n + i];
+            for (int i = tid; i < 2 * n; i += NT) sm[LF(y) + i] = a.ws_y[b * m + i];
+            for (int i = tid; i < ms; i += NT) sm[L.ys + i] = a.ws_y[b * m + 2 * n + i];
+        }
+        tw_sync<W>(bar);
+        StepTaps tap;
+        tap.A = a.A ? a.A + (size_t)b * N * 36 : nullptr;
+        tap.Bm = a.Bm ? a.Bm + (size_t)b * N * 12 : nullptr;
+        tap.g = a.g ? a.g + (size_t)b * N * 6 : nullptr;
+        tap.xbar = a.xbar ? a.xbar + (size_t)b * (N + 1) * 6 : nullptr;
+        tap.H = a.H ? a.H + (size_t)b * n * n : nullptr;
+        tap.q = a.q ? a.q + (size_t)b * n : nullptr;
+        tap.c0 = a.c0 ? a.c0 + b : nullptr;
+        tap.l = a.l ? a.l + (size_t)b * (2 * n + ms) : nullptr;
+        tap.u = a.u ? a.u + (size_t)b * (2 * n + ms) : nullptr;
+        tap.Gs = a.Gs ? a.Gs + (size_t)b * c.ms * n : nullptr;
+        tap.stop = a.stop;
+        const StepResult r = tw_step_body<W, S, NC>(c, L, sm, mp, warm, warm_free, tap, nullptr, tid, bar);
+        if (a.stop) continue;
+        const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);  // :261
+        const double ud = sm[LF(uprev)], udel = sm[LF(uprev) + 1];
+        if (tid == 0) {
+            a.u_cmd[2 * (size_t)b] = ok ? ud + sm[LF(xt)] : ud;          // :265 / fallback :262
+            a.u_cmd[2 * (size_t)b + 1] = ok ? udel + sm[LF(xt) + 1] : udel;
+            if (a.status) a.status[b] = r.status;
+            if (a.iters) a.iters[b] = r.iters;
+            if (a.objective) a.objective[b] = ok ? r.objective : nan("");
+        }
+        if (a.U_opt)
+            for (int i = tid; i < n; i += NT) a.U_opt[(size_t)b * n + i] = ok ? ((i & 1) ? udel : ud) + sm[LF(xt) + i] : nan("");
+        if (a.y_opt) {
+            const size_t m = 2 * (size_t)n + ms;
+            for (int i = tid; i < 2 * n; i += NT) a.y_opt[b * m + i] = ok ? sm[LF(y) + i] : nan("");
+            for (int i = tid; i < ms; i += NT) a.y_opt[b * m + 2 * n + i] = ok ? sm[L.ys + i] : nan("");
+        }
+        if (a.X_opt && tid == 0) {
+            // X_k of the QP (x_{k+1} = A_k x_k + B_k u_k + g_k, :189-192).  The nominal rollout satisfies the same recursion
+            // with u = u_prev, so X_k = xbar_k + dx_k with dx_{k+1} = A_k dx_k + B_k dU_k, dx_0 = 0.
+            double *X = a.X_opt + (size_t)b * (N + 1) * 6;
+            double dx[6] = {0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < 6; ++i) X[i] = ok ? sm[LF(xbar) + i] : nan("");
+            for (int k = 0; k < N; ++k) {
+                const double *r_ = sm + LF(lin) + TG_LIN * k;
+                const double d0 = sm[LF(xt) + 2 * k], d1 = sm[LF(xt) + 2 * k + 1];
+                double nx[6];
+                nx[0] = dx[0] + r_[0] * dx[2] + r_[1] * dx[3] + r_[2] * dx[4];
+                nx[1] = dx[1] + r_[3] * dx[2] + r_[4] * dx[3] + r_[5] * dx[4];
+                nx[2] = dx[2] + r_[6] * dx[5];
+                nx[3] = r_[7] * dx[3] + r_[8] * dx[4] + r_[9] * dx[5] + r_[16] * d0 + r_[17] * d1;
+                nx[4] = r_[10] * dx[3] + r_[11] * dx[4] + r_[12] * dx[5] + r_[18] * d1;
+                nx[5] = r_[13] * dx[3] + r_[14] * dx[4] + r_[15] * dx[5] + r_[19] * d1;
+                for (int i = 0; i < 6; ++i) { dx[i] = nx[i]; X[6 * (k + 1) + i] = ok ? sm[LF(xbar) + 6 * (k + 1) + i] + dx[i] : nan(""); }
+            }
+        }
+        if (a.ws_valid && c.warm_start) {
+            const size_t m = 2 * (size_t)n + ms;
+            for (int i = tid; i < n; i += NT) a.ws_x[(size_t)b * n + i] = sm[LF(xt) + i];
+            for (int i = tid; i < 2 * n; i += NT) a.ws_y[b * m + i] = sm[LF(y) + i];
+            for (int i = tid; i < ms; i += NT) a.ws_y[b * m + 2 * n + i] = sm[L.ys + i];
+            if (tid == 0) a.ws_valid[b] = ok ? (r.free_end ? 2 : 1) : 0;
+        }
+    }
+}
+
+template <int W, int S, int NC>
+__global__ void __launch_bounds__(TW_CTA_THREADS) __maxnreg__(TW_REGS(S))
+tw_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ WLayout L, const __grid_constant__ LoopArgs a)
+{
+    extern __shared__ __align__(16) double sm_all[];
+    constexpr int NT = 32 * W;
+    const int P = a.ppc;
+    int prob = threadIdx.x / NT, tid = threadIdx.x % NT;
+    unsigned sm_off = (unsigned)prob * (unsigned)((L.total + 1) & ~1) * 8u;
+    asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));
+    const int bar = 1 + prob;
+    double *sm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm_all) + sm_off);
+    const int N = NC > 0 ? NC : c.N, n = 2 * N, ms = c.ms, ns = c.ns, T = a.T;
+    if (prob >= P) return;
+    const TwMap<S> mp = tw_make_map<W, S>(LF(nb), tid);
+    const StepTaps tap = {};
+    int *cnt = reinterpret_cast<int *>(sm + LF(misc) + M_CNT);                 // 6 status counters
+    long long *itsum = reinterpret_cast<long long *>(sm + LF(misc) + M_CNT + 3);
+    const bool my = tid < N;
+    const int j0 = 2 * tid;
+    // Trajectories are dealt round-robin over the CTAs: slot `prob` of CTA c takes b = c + G (round P + prob), G = gridDim.x;
+    // `active` (the busy slots of this CTA in this round) is what the step barrier counts.
+    const int G = gridDim.x;
+    for (int round = 0; blockIdx.x + (long long)G * round * P < a.B; ++round) {
+        const long long bfirst = blockIdx.x + (long long)G * round * P;
+        const long long left = (a.B - 1 - bfirst) / G + 1;                   // slots with a trajectory, >= 1
+        const int active = left < P ? (int)left : P;
+        const bool lockstep = active > 1;
+        if (prob >= active) break;                                           // later rounds have no work for this slot either
+        const int b = (int)(bfirst + (long long)G * prob);
+        tw_sync<W>(bar);
+        if (tid < 12) sm[LF(spec) + tid] = reinterpret_cast<const double *>(a.spec + b)[tid];   // scenario -> shared memory
+        if (tid < 6) { const double v_ = a.x0[6 * (size_t)b + tid]; sm[LF(x0) + tid] = v_; a.clean[(size_t)b * (T + 1) * 6 + tid] = v_; }
+        if (tid < 2) sm[LF(uprev) + tid] = a.u0[2 * (size_t)b + tid];
+        if (tid < TG_NUM_STATUS) cnt[tid] = 0;
+        if (tid == 0) *itsum = 0;
+        bool warm = false, warm_free = false;
+        tw_sync<W>(bar);
+#pragma unroll 1
+        for (int t = 0; t <= T; ++t) {
+            FusedCtx fx;
+            fx.brk = a.brk; fx.coef = a.coef;
+            fx.noisy_row = a.noisy + ((size_t)b * (T + 1) + t) * 6;
+            fx.seed = c.seed_base + (unsigned long long)(a.traj_id0 + b);
+            fx.t_index = t;
+            if (t == T) {   // last row: only its noisy copy remains to be written
+                if (tid < 3) {
+                    uint32_t r4[4];
+                    tg_philox4x32_10((uint32_t)t, (uint32_t)(tid >> 1), 0u, 0u, (uint32_t)fx.seed, (uint32_t)(fx.seed >> 32), r4);
+                    double n0, n1;
+                    tg_box_muller(r4[(tid & 1) * 2], r4[(tid & 1) * 2 + 1], n0, n1);
+                    fx.noisy_row[2 * tid] = sm[LF(x0) + 2 * tid] + c.noise_std[2 * tid] * n0;
+                    fx.noisy_row[2 * tid + 1] = sm[LF(x0) + 2 * tid + 1] + c.noise_std[2 * tid + 1] * n1;
+                }
+                break;
+            }
+            const StepResult r = tw_step_body<W, S, NC>(c, L, sm, mp, warm, warm_free, tap, &fx, tid, bar);
+            const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);
+            if (tid == 0) { cnt[r.status] += 1; *itsum += r.iters; }
+            // shifted warm start for the next step, in the next step's dU coordinates
+            double2 nx = make_double2(0.0, 0.0), nyb = nx, nyr = nx;
+            if (my) {
+                const double2 d0 = tw_ld2(sm + LF(xt));
+                const double2 xs_ = tw_ld2(sm + LF(xt) + ((tid + 1 < N) ? j0 + 2 : j0));
+                nx = make_double2(xs_.x - d0.x, xs_.y - d0.y);
+                if (tid + 1 < N) { nyb = tw_ld2(sm + LF(y) + j0 + 2); nyr = tw_ld2(sm + LF(y) + n + j0 + 2); }
+            }
+            if (tid < 32) {   // plant (MPC/main.py:97) + outputs, warp 0 (lane-parallel f_cont)
+                const double ud = sm[LF(uprev)], udel = sm[LF(uprev) + 1];
+                const double u0 = ok ? ud + sm[LF(xt)] : ud, u1 = ok ? udel + sm[LF(xt) + 1] : udel;
+                double xs[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) xs[i] = sm[LF(x0) + i];
+                tg_plant_step_lanes(c, xs, u0, u1, tid);
+                if (tid == 0) {
+                    double *clean = a.clean + ((size_t)b * (T + 1) + t + 1) * 6;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { sm[LF(misc) + M_XNEXT + i] = xs[i]; clean[i] = xs[i]; }
+                    a.U[((size_t)b * T + t) * 2] = u0; a.U[((size_t)b * T + t) * 2 + 1] = u1;
+                    sm[LF(misc) + M_UCMD] = u0; sm[LF(misc) + M_UCMD + 1] = u1;
+                }
+            }
+            tw_sync<W>(bar);
+            // commit the new state / warm start
+            if (tid < 6) sm[LF(x0) + tid] = sm[LF(misc) + M_XNEXT + tid];
+            if (tid < 2) sm[LF(uprev) + tid] = sm[LF(misc) + M_UCMD + tid];
+            if (my) { tw_st2(sm + LF(x) + j0, nx.x, nx.y); tw_st2(sm + LF(y) + j0, nyb.x, nyb.y); tw_st2(sm + LF(y) + n + j0, nyr.x, nyr.y); }
+            if (ms > 0) {   // shift the state-row duals by one stage (ns rows), in place: ascending order, one thread
+                if (tid == 0) {
+                    for (int i = 0; i + ns < ms; ++i) sm[L.ys + i] = sm[L.ys + i + ns];
+                    for (int i = (ms > ns ? ms - ns : 0); i < ms; ++i) sm[L.ys + i] = 0.0;
+                }
+            }
+            warm = ok && c.warm_start;
+            warm_free = warm && r.free_end;
+            if (lockstep) tg_sync(15, NT * active); else tw_sync<W>(bar);
+        }
+        tw_sync<W>(bar);
+        if (tid < TG_NUM_STATUS && a.status_counts) a.status_counts[(size_t)b * TG_NUM_STATUS + tid] = cnt[tid];
+        if (tid == 0 && a.iters_total) a.iters_total[b] = *itsum;
+    }
+}
+
 __global__ void tg_ref_window_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, int B,
                                      const double *x0, const tg_ref_spec *spec, const double *brk, const double *coef,
                                      int t_index, double *path_ref, double *vref)
@@ -383,8 +595,10 @@ static bool pick_shape(int N, Shape &s)
 // deviation from libm on a dense check grid (value and slope) so the caller can refuse a table that is not at
 // rounding level for unusual B, C.
 static double build_cheb_table(const std::function<long double(long double)> &fun, const std::function<long double(long double)> &dfun,
-                               long double lo, long double hi, int NI, double *tab /*[NI][NC]*/, double *slope_err)
+                               long double lo, long double hi, int NI, double *tab /*[NI + 1][NC]*/, double *slope_err)
 {
+    // NI + 1 intervals of width h = (hi - lo) / NI, interval i centred on lo + i h (tg_tab_row): the end intervals reach half
+    // an interval beyond [lo, hi], where fun is still analytic
     const int NC = TG_TAB_NC;
     const long double PI = 3.141592653589793238462643383279502884L;
     long double T[TG_TAB_NC][TG_TAB_NC] = {};   // T[k][i] = coefficient of s^i in T_k(s)
@@ -394,8 +608,8 @@ static double build_cheb_table(const std::function<long double(long double)> &fu
         for (int i = 0; i < NC; ++i) T[k][i] = (i > 0 ? 2.0L * T[k - 1][i - 1] : 0.0L) - T[k - 2][i];
     const long double hw = (hi - lo) / (2 * NI);
     double worst = 0.0, worst_d = 0.0;
-    for (int it = 0; it < NI; ++it) {
-        const long double ctr = lo + (2 * it + 1) * hw;
+    for (int it = 0; it <= NI; ++it) {
+        const long double ctr = lo + 2 * it * hw;
         long double fv[TG_TAB_NC], a[TG_TAB_NC];
         for (int j = 0; j < NC; ++j) {
             const long double sj = cosl(PI * (j + 0.5L) / NC);
@@ -424,7 +638,7 @@ static double build_cheb_table(const std::function<long double(long double)> &fu
     return worst;
 }
 
-static double build_tyre_table(double B, double C, double ma, double *tab /*[NI][NC]*/, double *slope_err)
+static double build_tyre_table(double B, double C, double ma, double *tab /*[TG_TAB_ROWS][NC]*/, double *slope_err)
 {
     auto f = [=](long double al) { return sinl((long double)C * atanl((long double)B * al)); };
     auto df = [=](long double al) { const long double ba = (long double)B * al; return cosl((long double)C * atanl(ba)) * C * B / (1.0L + ba * ba); };
@@ -432,7 +646,7 @@ static double build_tyre_table(double B, double C, double ma, double *tab /*[NI]
 }
 
 // atan on [-TG_ATAN_T0, TG_ATAN_T0] (the slip-angle argument n / vx_eff of the sequential nominal rollout): same form
-static double build_atan_table(double *tab /*[TG_ATAN_NI][NC]*/)
+static double build_atan_table(double *tab /*[TG_ATAN_ROWS][NC]*/)
 {
     auto f = [](long double t) { return atanl(t); };
     auto df = [](long double t) { return 1.0L / (1.0L + t * t); };
@@ -446,6 +660,10 @@ struct tg_handle {
     Shape shape;
     int device, num_sms, grid_cap;
     int ppc_max, ppc_env;     // closed-loop kernel: most problems per CTA that fit / TRAJGEN_PPC override (0 = automatic)
+    // warp-per-problem kernels (tw_solver.cuh): W warps per problem, S tile blocks per thread
+    int use_tw, W, S;
+    WLayout WL;
+    SmemLayout Lref;          // small layout of the reference-window tap kernel
     size_t smem_optin;
     size_t smem_bytes;
     cudaStream_t stream;
@@ -495,6 +713,44 @@ static int dispatch_step(const Shape &s, bool multi, F &&f)
     });
 }
 
+
+// (W, S) of the warp-per-problem kernels for a horizon: the lower triangle of the n x n matrix in 4 x 4 blocks must fit the
+// 32 W S slots, and a thread owns at most one stage (N <= 32 W)
+static bool pick_tw_shape(int N, int &W, int &S)
+{
+    if (const char *e = getenv("TRAJGEN_SHAPE")) {   // development knob: "W,S" (must fit the horizon)
+        int w = 0, s_ = 0;
+        if (sscanf(e, "%d,%d", &w, &s_) == 2 && w >= 1 && s_ >= 1) {
+            const int nb = (2 * N + 3) / 4;
+            if (nb * (nb + 1) / 2 <= 32 * w * s_ && N <= 32 * w && 2 * N <= 64 * w) { W = w; S = s_; return true; }
+        }
+    }
+    if (N <= 14) { W = 1; S = 1; }          // 28 blocks on one warp
+    else if (N <= 20) { W = 2; S = 1; }     // 55 blocks on two warps
+    else if (N <= 30) { W = 4; S = 1; }     // 120 blocks
+    else if (N <= 44) { W = 8; S = 1; }     // 253 blocks
+    else if (N <= 56) { W = 8; S = 2; }     // 406 blocks on 512 slots
+    else return false;
+    return true;
+}
+// kernel instances: (W, S) for a run-time horizon, plus the horizons of the BASELINE configurations compiled in (NC = N:
+// shared-memory offsets become immediates, horizon loops get constant trip counts)
+template <typename F>
+static int dispatch_tw(int W, int S, int N, F &&f)
+{
+    using std::integral_constant;
+    if (W == 2 && S == 1 && N == 20 && !getenv("TRAJGEN_DYNAMIC_N")) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 20>());
+    if (W == 1 && S == 1) return f(integral_constant<int, 1>(), integral_constant<int, 1>(), integral_constant<int, 0>());
+    if (W == 2 && S == 1) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 0>());
+#ifndef TG_ONLY_SHAPE_5_8
+    if (W == 4 && S == 1) return f(integral_constant<int, 4>(), integral_constant<int, 1>(), integral_constant<int, 0>());
+    if (W == 8 && S == 1) return f(integral_constant<int, 8>(), integral_constant<int, 1>(), integral_constant<int, 0>());
+    if (W == 8 && S == 2) return f(integral_constant<int, 8>(), integral_constant<int, 2>(), integral_constant<int, 0>());
+#endif
+    return fail(TG_ERR_UNSUPPORTED, "no kernel shape for this horizon");
+}
+static size_t tw_stride(const tg_handle *h) { return (((size_t)h->WL.total + 1) & ~(size_t)1) * sizeof(double); }
+
 extern "C" {
 
 const char *tg_last_error(void) { return g_err.c_str(); }
@@ -513,7 +769,7 @@ void tg_default_config(tg_config *c)
     c->u_lo[0] = -1.0; c->u_hi[0] = 1.0; c->u_lo[1] = -0.6; c->u_hi[1] = 0.6;
     c->du_lo[0] = -0.5; c->du_hi[0] = 0.5; c->du_lo[1] = -0.3; c->du_hi[1] = 0.3;
     for (int i = 0; i < 6; ++i) { c->x_lo[i] = -TG_INF; c->x_hi[i] = TG_INF; }
-    c->rho = 0.1; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-5; c->eps_rel = 1e-5; c->eps_prim_inf = 1e-4;
+    c->rho = 0.1; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-6; c->eps_rel = 1e-6; c->eps_prim_inf = 1e-4;   // eps: one decade tighter than CVXPY's OSQP setting (1e-5), DESIGN.md 2
     c->adaptive_rho_tol = 5.0; c->alpha_warm = 1.2; c->max_iter = 10000; c->check_every = 5; c->adaptive_rho = 1; c->adaptive_rho_min_iter = 20;
     c->warm_start = 0; c->vref_advance = 0;
     const double sd[6] = {0.05, 0.05, 0.003, 0.010, 0.003, 0.030};
@@ -559,18 +815,18 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     d.inv_m = 1.0 / d.p[P_m]; d.inv_Iz = 1.0 / d.p[P_Iz];
     d.tyre_tab = nullptr; d.tab_scale = 0.0;
     if (d.p[P_maxAlpha] > 0.0 && !getenv("TRAJGEN_NO_TYRE_TABLE")) {
-        std::vector<double> tab(2 * TG_TAB_NI * TG_TAB_NC + TG_ATAN_NI * TG_TAB_NC);
+        std::vector<double> tab(2 * TG_TAB_ROWS * TG_TAB_NC + TG_ATAN_ROWS * TG_TAB_NC);
         double se_f = 0.0, se_r = 0.0;
         const double e_f = build_tyre_table(d.p[P_Bf], d.p[P_Cf], d.p[P_maxAlpha], tab.data(), &se_f);
-        const double e_r = build_tyre_table(d.p[P_Br], d.p[P_Cr], d.p[P_maxAlpha], tab.data() + TG_TAB_NI * TG_TAB_NC, &se_r);
-        const double e_at = build_atan_table(tab.data() + 2 * TG_TAB_NI * TG_TAB_NC);
+        const double e_r = build_tyre_table(d.p[P_Br], d.p[P_Cr], d.p[P_maxAlpha], tab.data() + TG_TAB_ROWS * TG_TAB_NC, &se_r);
+        const double e_at = build_atan_table(tab.data() + 2 * TG_TAB_ROWS * TG_TAB_NC);
         h->tab_err[0] = fmax(e_f, e_r); h->tab_err[1] = fmax(se_f, se_r);
         if (h->tab_err[0] <= 4e-16 && h->tab_err[1] <= 1e-12) {
             CK(cudaMalloc(&h->tyre_tab, tab.size() * sizeof(double)));
             CK(cudaMemcpy(h->tyre_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
             d.tyre_tab = h->tyre_tab;
             d.tab_scale = TG_TAB_NI / (2.0 * d.p[P_maxAlpha]);
-            if (e_at <= 4e-16) d.atan_tab = h->tyre_tab + 2 * TG_TAB_NI * TG_TAB_NC;
+            if (e_at <= 4e-16) d.atan_tab = h->tyre_tab + 2 * TG_TAB_ROWS * TG_TAB_NC;
         }
     }
     d.q_c = cfg->q_c; d.q_phi = cfg->q_phi; d.q_vx = cfg->q_vx;
@@ -587,6 +843,43 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     memcpy(d.noise_std, cfg->noise_std, 48);
     d.seed_base = cfg->noise_seed_base;
 
+    d.free_mode = (cfg->solver_flags & 1) ? 0 : 1;
+    h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+    h->Lref = tg_make_layout(d.N, 0, d.NP, d.NPP);
+    CK(cudaFuncSetAttribute(tg_ref_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+    // Which body: the warp-per-problem kernels (tw_solver.cuh) for every horizon they are enabled for, else the legacy
+    // CTA-per-problem kernels.  TRAJGEN_TW = 0 forces the legacy kernels, = all enables the W > 1 shapes (development knobs).
+    h->use_tw = 0;
+    if (pick_tw_shape(d.N, h->W, h->S)) {
+        const char *e = getenv("TRAJGEN_TW");
+        h->use_tw = (e && strcmp(e, "0") == 0) ? 0 : ((h->W <= 2 || getenv("TRAJGEN_SHAPE") || (e && strcmp(e, "all") == 0)) ? 1 : 0);
+    }
+    h->ppc_env = 0;   // TRAJGEN_PPC pins the number of problems per CTA (measurement knob)
+    if (h->use_tw) {
+        h->WL = tw_make_layout(d.N, d.ms, h->W);
+        const size_t stride = tw_stride(h);
+        h->smem_bytes = stride;
+        if (stride > h->smem_optin) return fail(TG_ERR_UNSUPPORTED, "state-bound rows x horizon exceed the 227 KB shared memory of one CTA");
+        h->ppc_max = TW_CTA_THREADS / (32 * h->W);
+        if (h->W > 1 && h->ppc_max > 14) h->ppc_max = 14;                  // named barriers 1..14 + the step barrier 15
+        while (h->ppc_max > 1 && (size_t)h->ppc_max * stride > h->smem_optin) h->ppc_max -= 1;
+        if (const char *e = getenv("TRAJGEN_PPC")) { const int v = atoi(e); if (v >= 1 && v <= h->ppc_max) h->ppc_env = v; }
+        int occ = 0;
+        int rc = dispatch_tw(h->W, h->S, d.N, [&](auto W_, auto S_, auto NC_) -> int {
+            constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
+            // the attribute is per kernel function and process-wide: always raise it to the device limit so that handles with
+            // different layouts can be used side by side
+            CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+            CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+            CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tw_closed_loop_kernel<W, S, NC>, 32 * W, stride));
+            return TG_OK;
+        });
+        if (rc != TG_OK) return rc;
+        if (occ < 1) return fail(TG_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration");
+        h->grid_cap = occ * h->num_sms;     // resident problems with one problem per CTA
+    } else {
     h->L = tg_make_layout(d.N, d.ms, d.NP, d.NPP);
     h->smem_bytes = (size_t)h->L.total * sizeof(double);
     if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
@@ -594,19 +887,16 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     }
     int occ = 0;
     const size_t stride = (((size_t)h->L.total + 1) & ~(size_t)1) * sizeof(double);   // shared memory of one problem
-    h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
     h->ppc_max = 1;
     if (sh.NT == 64) {   // several problems per CTA for the 64-thread shapes, as many as fit in shared memory
         h->ppc_max = TG_PPC_MAX;
         while (h->ppc_max > 1 && (size_t)h->ppc_max * stride > h->smem_optin) h->ppc_max -= 1;
     }
-    h->ppc_env = 0;   // TRAJGEN_PPC = 1..8 pins the number of problems per CTA (measurement knob)
     if (const char *e = getenv("TRAJGEN_PPC")) { const int v = atoi(e); if (v >= 1 && v <= h->ppc_max) h->ppc_env = v; }
     int rc = TG_OK;
     for (int multi = 0; multi <= (h->ppc_max > 1 ? 1 : 0) && rc == TG_OK; ++multi) {
-        const size_t bytes = multi ? (size_t)h->ppc_max * stride : h->smem_bytes;
         auto setup = [&](auto kern) -> int {
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             if (!multi) { int o = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, sh.NT, h->smem_bytes)); occ = (occ == 0 || o < occ) ? o : occ; }
             return TG_OK;
@@ -617,8 +907,8 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     if (rc != TG_OK) return rc;
     if (occ < 1) return fail(TG_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration");
     h->grid_cap = occ * h->num_sms;
-    CK(cudaFuncSetAttribute(tg_ref_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    if (d.adaptive_rho) {
+    }
+    if (d.adaptive_rho && !h->use_tw) {   // (the warp-per-problem body rebuilds H from the stage records instead of keeping a copy)
         const size_t slots = std::max((size_t)h->grid_cap, (size_t)h->num_sms * TG_PPC_MAX);   // resident problems, either kernel
         h->Hws_elems = slots * d.NP * d.NP;
         CK(cudaMalloc(&h->Hws, h->Hws_elems * sizeof(double)));
@@ -645,7 +935,7 @@ int tg_info(tg_handle *h, int32_t *ctas_per_sm, int32_t *threads_per_cta, int32_
 {
     if (!h) return fail(TG_ERR_INVALID, "null handle");
     if (ctas_per_sm) *ctas_per_sm = h->grid_cap / h->num_sms;
-    if (threads_per_cta) *threads_per_cta = h->shape.NT;
+    if (threads_per_cta) *threads_per_cta = h->use_tw ? 32 * h->W : h->shape.NT;
     if (smem_bytes) *smem_bytes = (int32_t)h->smem_bytes;
     if (num_sms) *num_sms = h->num_sms;
     return TG_OK;
@@ -689,10 +979,45 @@ static int choose_ppc(const tg_handle *h, int B)
     return best;
 }
 
+// warp-per-problem kernels: problems per CTA.  Resident problems per SM are bounded by registers (512 threads x 128) and
+// shared memory either way; larger CTAs share more instruction fetches, smaller ones spread a small batch over more SMs.
+static int choose_tw_ppc(const tg_handle *h, int B)
+{
+    if (h->ppc_env) return h->ppc_env;
+    int p = h->ppc_max < 8 ? h->ppc_max : 8;
+    while (p > 1 && (B + p - 1) / p < h->num_sms) p >>= 1;   // every SM gets a CTA before CTAs get wider
+    return p < 1 ? 1 : p;
+}
+
+extern "C++" {
+template <typename Kern, typename Args>
+static int launch_tw(tg_handle *h, Kern kern, Args &a, int B, int W)
+{
+    const int ppc = choose_tw_ppc(h, B);
+    a.ppc = ppc;
+    const size_t smem = (size_t)ppc * tw_stride(h);
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * W * ppc, smem));
+    if (per_sm < 1) return fail(TG_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration");
+    const int cap = per_sm * h->num_sms, ctas = (B + ppc - 1) / ppc;
+    int grid = ctas < cap ? ctas : cap;
+    if (const char *e = getenv("TRAJGEN_GRID")) { const int v = atoi(e); if (v >= 1 && v <= cap) grid = v; }   // measurement knob
+    kern<<<grid, 32 * W * ppc, smem, h->stream>>>(h->dc, h->WL, a);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+}  // extern "C++"
+
 static int launch_step(tg_handle *h, StepArgs &a)
 {
     if (a.B <= 0) return TG_OK;   // empty batch: nothing to do
     CK(cudaSetDevice(h->device));
+    if (h->use_tw)
+        return dispatch_tw(h->W, h->S, h->dc.N, [&](auto W_, auto S_, auto NC_) -> int {
+            constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
+            return launch_tw(h, tw_mpc_step_kernel<W, S, NC>, a, a.B, W);
+        });
     a.Hws = h->Hws;
     // a batch that is resident at once starts in phase on every SM anyway (one step does not drift), and single-problem CTAs
     // spread it more evenly (p50 of a 1024-problem call: 0.232 ms vs 0.250 ms with 4 per CTA); larger batches run in rounds
@@ -772,7 +1097,7 @@ int tg_ref_window(tg_handle *h, int B, const double *x0, const tg_ref_spec *spec
     if (B == 0) return TG_OK;
     CK(cudaSetDevice(h->device));
     const int grid = B < 8 * h->num_sms ? B : 8 * h->num_sms;
-    tg_ref_window_kernel<<<grid, 64, h->smem_bytes, h->stream>>>(h->dc, h->L, B, x0, spec, brk, coef, t_index, path_ref, vref);
+    tg_ref_window_kernel<<<grid, 64, (size_t)h->Lref.total * sizeof(double), h->stream>>>(h->dc, h->Lref, B, x0, spec, brk, coef, t_index, path_ref, vref);
     h->launches += 1;
     CK(cudaGetLastError());
     return TG_OK;
@@ -789,6 +1114,11 @@ int tg_closed_loop(tg_handle *h, int B, int T, const double *x0, const double *u
     memset(&a, 0, sizeof(a));
     a.B = B; a.T = T; a.x0 = x0; a.u0 = u0; a.spec = spec; a.brk = brk; a.coef = coef; a.traj_id0 = traj_id0;
     a.clean = clean; a.noisy = noisy; a.U = U; a.status_counts = status_counts; a.iters_total = (long long *)iters_total;
+    if (h->use_tw)
+        return dispatch_tw(h->W, h->S, h->dc.N, [&](auto W_, auto S_, auto NC_) -> int {
+            constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
+            return launch_tw(h, tw_closed_loop_kernel<W, S, NC>, a, B, W);
+        });
     a.Hws = h->Hws;
     const int ppc = choose_ppc(h, B);
     a.ppc = ppc;
