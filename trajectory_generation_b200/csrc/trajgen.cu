@@ -848,11 +848,11 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     h->Lref = tg_make_layout(d.N, 0, d.NP, d.NPP);
     CK(cudaFuncSetAttribute(tg_ref_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
     // Which body: the warp-per-problem kernels (tw_solver.cuh) for every horizon they are enabled for, else the legacy
-    // CTA-per-problem kernels.  TRAJGEN_TW = 0 forces the legacy kernels, = all enables the W > 1 shapes (development knobs).
+    // CTA-per-problem kernels.  TRAJGEN_TW = 0 forces the legacy kernels (development knob).
     h->use_tw = 0;
     if (pick_tw_shape(d.N, h->W, h->S)) {
         const char *e = getenv("TRAJGEN_TW");
-        h->use_tw = (e && strcmp(e, "0") == 0) ? 0 : ((h->W <= 2 || getenv("TRAJGEN_SHAPE") || (e && strcmp(e, "all") == 0)) ? 1 : 0);
+        h->use_tw = (e && strcmp(e, "0") == 0) ? 0 : 1;
     }
     h->ppc_env = 0;   // TRAJGEN_PPC pins the number of problems per CTA (measurement knob)
     if (h->use_tw) {
@@ -984,7 +984,12 @@ static int choose_ppc(const tg_handle *h, int B)
 static int choose_tw_ppc(const tg_handle *h, int B)
 {
     if (h->ppc_env) return h->ppc_env;
-    int p = h->ppc_max < 8 ? h->ppc_max : 8;
+    // problems with state-bound rows have long, unequal solves (tens to hundreds of ADMM iterations): free-running
+    // single-problem CTAs beat problems that wait for one another at every step boundary
+    if (h->dc.ms > 0) return 1;
+    // measured at N = 20 (two warps per problem): 4 problems per CTA 2.65e7 steps/s (B = 2368), 8 per CTA 2.37e7 (B = 4736),
+    // 2 per CTA 2.24e7 and 1 per CTA 1.43e7 (B = 1024): sharing instruction fetches matters, waiting for 7 neighbours costs more
+    int p = h->ppc_max < 4 ? h->ppc_max : 4;
     while (p > 1 && (B + p - 1) / p < h->num_sms) p >>= 1;   // every SM gets a CTA before CTAs get wider
     return p < 1 ? 1 : p;
 }

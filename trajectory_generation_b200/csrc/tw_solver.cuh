@@ -93,6 +93,28 @@ __device__ __forceinline__ void tw_st4(double *p, double a, double b, double c, 
     p2[0] = make_double2(a, b); p2[1] = make_double2(c, d);
 }
 __device__ __forceinline__ double2 tw_ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+// Explicit shared-space accesses for the innermost loops.  The compiler re-derives the CTA's shared-memory window base
+// (S2R SR_CgaCtaId + LEA, tens of cycles) next to ordinary shared accesses inside loops instead of keeping it in a register,
+// which put it on the dependent chain of every sweep pivot; a 32-bit shared address computed once avoids that.
+__device__ __forceinline__ unsigned tw_saddr(const double *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tw_lds4(unsigned a, double (&o)[4])
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%4];\n\tld.shared.v2.f64 {%2, %3}, [%4+16];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "r"(a));
+}
+__device__ __forceinline__ double tw_lds1(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void tw_sts4(unsigned a, double x0, double x1, double x2, double x3)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n\tst.shared.v2.f64 [%0+16], {%3, %4};" ::"r"(a), "d"(x0), "d"(x1), "d"(x2), "d"(x3) : "memory");
+}
+__device__ __forceinline__ void tw_sts1(unsigned a, double x0) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(x0) : "memory"); }
+// 1 / x for x > 0: hardware seed (~2^-22) + one cubic step, e = 1 - x r, r <- r (1 + e + e^2): ~2^-66, three dependent FMAs
+__device__ __forceinline__ double tw_rcp3(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    return fma(r, fma(e, e, e), r);
+}
 __device__ __forceinline__ void tw_st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
 
 // max of NRED non-negative values over the threads of a problem.  The norms only feed the termination / rho tests, so they
@@ -427,7 +449,12 @@ __device__ __forceinline__ void tw_sweep_invert(const DevCfg &c, const WLayout &
     double rp_next = 0.0;
 #pragma unroll
     for (int s = 0; s < S; ++s)
-        if (mp.act[s] && mp.ro[s] == 0 && mp.co[s] == 0) rp_next = tg_rcp_pos(a[s][0][0]);
+        if (mp.act[s] && mp.ro[s] == 0 && mp.co[s] == 0) rp_next = tw_rcp3(a[s][0][0]);
+    // shared-space addresses of this thread's operands in the two pivot-row buffers (buffer = pivot parity)
+    const unsigned vb_a = tw_saddr(vb), stride_a = (unsigned)(NV + 2) * 8u;
+    unsigned ro_a[S], co_a[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { ro_a[s] = vb_a + 8u * (unsigned)mp.ro[s]; co_a[s] = vb_a + 8u * (unsigned)mp.co[s]; }
 #pragma unroll 1
     for (int K = 0; K < nb; ++K) {
         const int K4 = 4 * K;
@@ -435,32 +462,32 @@ __device__ __forceinline__ void tw_sweep_invert(const DevCfg &c, const WLayout &
         for (int kr = 0; kr < 4; ++kr) {
             const int k = K4 + kr;
             if (k < n) {   // uniform
-                double *v = vb + (k & 1) * (NV + 2);
+                const unsigned boff = (kr & 1) ? stride_a : 0u;   // k & 1 == kr & 1 (K4 is even)
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     if (mp.act[s]) {
                         if (mp.ro[s] == K4) {          // block row K: row kr of the block is a_{k, co..co+3}
-                            tw_st4(v + mp.co[s], a[s][kr][0], a[s][kr][1], a[s][kr][2], a[s][kr][3]);
-                            if (mp.co[s] == K4) { v[k] = a[s][kr][kr] - 1.0; v[NV] = rp_next; }
+                            tw_sts4(co_a[s] + boff, a[s][kr][0], a[s][kr][1], a[s][kr][2], a[s][kr][3]);
+                            if (mp.co[s] == K4) { tw_sts1(vb_a + boff + 8u * (unsigned)k, a[s][kr][kr] - 1.0); tw_sts1(vb_a + boff + 8u * (unsigned)NV, rp_next); }
                         } else if (mp.co[s] == K4) {   // block column K below the diagonal: column kr is a_{ro..ro+3, k}
-                            tw_st4(v + mp.ro[s], a[s][0][kr], a[s][1][kr], a[s][2][kr], a[s][3][kr]);
+                            tw_sts4(ro_a[s] + boff, a[s][0][kr], a[s][1][kr], a[s][2][kr], a[s][3][kr]);
                         }
                     }
                 }
                 tw_sync<W>(bar);
-                const double p = v[NV];
+                const double p = tw_lds1(vb_a + boff + 8u * (unsigned)NV);
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     double vr[4], vc[4];
-                    tw_ld4(v + mp.ro[s], vr);
-                    tw_ld4(v + mp.co[s], vc);
+                    tw_lds4(ro_a[s] + boff, vr);
+                    tw_lds4(co_a[s] + boff, vc);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) vr[r] *= p;
                     if (mp.ro[s] == K4) vr[kr] = 1.0 - p;
                     {   // next pivot first
                         const int nx = (kr + 1) & 3;                   // static after unrolling
                         const int nK4 = (kr == 3) ? K4 + 4 : K4;
-                        if (mp.act[s] && mp.ro[s] == nK4 && mp.co[s] == nK4) rp_next = tg_rcp_pos(fma(-vr[nx], vc[nx], a[s][nx][nx]));   // K is SPD: pivots > 0
+                        if (mp.act[s] && mp.ro[s] == nK4 && mp.co[s] == nK4) rp_next = tw_rcp3(fma(-vr[nx], vc[nx], a[s][nx][nx]));   // K is SPD: pivots > 0
                     }
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
