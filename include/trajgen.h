@@ -59,6 +59,7 @@ extern "C" {
 #define TG_PATH_PARABOLA 0 /* y = p0 x^2 + p1 x + p2 */
 #define TG_PATH_SINE 1     /* y = p0 sin(p1 x + p2) + p3 */
 #define TG_PATH_SPLINE 2   /* piecewise cubic y(x): breaks/coef table, scipy PPoly layout */
+#define TG_PATH_ARC 3      /* arclength-parameterised path (x(s), y(s)): two cubic-spline tables over s, see tg_ref_spec */
 /* velocity-reference kinds (MPC/mpc_6stati.py:158-163, MPC/main.py:28-47) */
 #define TG_VREF_HOLD 0      /* vref=None -> x0[3] */
 #define TG_VREF_CONST 1     /* v[0] */
@@ -261,7 +262,8 @@ int tg_fma_peak(tg_handle *h, int dtype, double *tflops);
 
 /* host<->device helpers so a ctypes caller needs no other CUDA binding */
 int tg_device_count(int *n);
-int tg_malloc(void **dptr, int64_t bytes);
+int tg_malloc(void **dptr, int64_t bytes);                  /* on the calling thread's current device */
+int tg_malloc_on(tg_handle *h, void **dptr, int64_t bytes); /* on the handle's device (use this one when several GPUs are in play) */
 int tg_free(void *dptr);
 int tg_memcpy_h2d(tg_handle *h, void *dst, const void *src, int64_t bytes);
 int tg_memcpy_d2h(tg_handle *h, void *dst, const void *src, int64_t bytes);

@@ -397,3 +397,25 @@ def test_tyre_table_is_verified_and_optional(golden_physics, monkeypatch):
     ug, sg, ig = tg.mpc_step(x, up, pr, vref=v, params=stiff, solver_opts=TIGHT)
     uo, so, io = ompc.mpc_step(x, up, pr, vref=v, params=stiff, solver="ipm")
     assert sg == so == "optimal" and np.abs(ig["U_opt"] - io["U_opt"]).max() < TOL_U
+
+
+def test_handles_with_different_layouts_side_by_side():
+    """Handles whose kernels need different amounts of dynamic shared memory, used alternately (the per-kernel shared-memory
+    limit is process-wide: a later, smaller handle must not lower it under an earlier, larger one), including the
+    reference-window tap and the open-loop / estimator handles that are built with N = 1."""
+    N, Ts = 20, 0.02
+    big = tg.BatchedMPC(N=N, Ts=Ts, x_lo=[-10, -10, -10, -1, -3, -20], x_hi=[10, 10, 10, 5, 3, 20])   # six bounded states: 100+ KB
+    x0 = np.array([[0.0, 0.5, 0.0, 1.0, 0.0, 0.0]]); u0 = np.array([[R.d_steady_state(1.0), 0.0]])
+    v = R.vref_profile(R.VREF_RAMP, (0.8, 2.0, 2.0), N, Ts); pr = R.ref_window(0.0, N, Ts, v)
+    first = big.step(x0, u0, pr[None], v[None])
+    small = tg.BatchedMPC(N=N, Ts=Ts)                                    # same kernels, 14 KB layout
+    gen = tg.ClosedLoopGenerator(N=N, Ts=Ts)
+    ol = tg.OpenLoopGenerator("type2", Ts=0.01)                          # N = 1 handle
+    for _ in range(2):
+        s = small.step(x0, u0, pr[None], v[None])
+        b = big.step(x0, u0, pr[None], v[None])
+        assert np.array_equal(b["u_cmd"], first["u_cmd"]) and s["status"][0] == 0 and b["status"][0] == 0
+        assert np.abs(s["u_cmd"] - b["u_cmd"]).max() < 1e-5               # the wide state box is inactive
+        pr_g, v_g = gen.ref_window(x0, tg.Scenarios(1))
+        np.testing.assert_allclose(pr_g[0], pr, atol=1e-14)
+        ol.generate(ol.sample_x0(2), 5)

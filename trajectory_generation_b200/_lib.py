@@ -79,7 +79,7 @@ EXPORTS = (
     "tg_closed_loop", "tg_closed_loop_host", "tg_default_type1_rules", "tg_default_type2_rules", "tg_openloop_type1",
     "tg_openloop_type2", "tg_openloop_type1_host", "tg_openloop_type2_host", "tg_write_csv", "tg_merge_csv", "tg_estimator_step", "tg_estimator_step_vjp",
     "tg_estimator_rollout", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
-    "tg_device_count", "tg_malloc", "tg_free", "tg_memcpy_h2d", "tg_memcpy_d2h", "tg_malloc_host", "tg_free_host",
+    "tg_device_count", "tg_malloc", "tg_malloc_on", "tg_free", "tg_memcpy_h2d", "tg_memcpy_d2h", "tg_malloc_host", "tg_free_host",
 )
 
 _lib = None
@@ -148,6 +148,7 @@ def load():
     L.tg_fma_peak.argtypes = [vp, ctypes.c_int, ctypes.POINTER(d)]
     L.tg_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
     L.tg_malloc.argtypes = [ctypes.POINTER(vp), i64]
+    L.tg_malloc_on.argtypes = [vp, ctypes.POINTER(vp), i64]
     L.tg_free.argtypes = [vp]
     L.tg_memcpy_h2d.argtypes = [vp, vp, vp, i64]
     L.tg_memcpy_d2h.argtypes = [vp, vp, vp, i64]
@@ -179,10 +180,13 @@ def ptr(a):
 class DeviceBuffer:
     """A cudaMalloc'ed block owned by Python (used by tests / bench to keep data resident in HBM)."""
 
-    def __init__(self, nbytes):
+    def __init__(self, nbytes, handle=None):
         self.nbytes = int(nbytes)
         p = vp()
-        check(load().tg_malloc(ctypes.byref(p), self.nbytes))
+        if handle is not None:                       # on the owning handle's device, whatever the thread's current device is
+            check(load().tg_malloc_on(handle, ctypes.byref(p), self.nbytes))
+        else:
+            check(load().tg_malloc(ctypes.byref(p), self.nbytes))
         self.ptr = p.value
 
     def free(self):

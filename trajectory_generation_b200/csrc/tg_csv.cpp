@@ -7,6 +7,7 @@
 #include <charconv>
 #include <cmath>
 #include <cstdint>
+#include <cerrno>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -14,6 +15,8 @@
 #include <vector>
 
 #include "../../include/trajgen.h"
+
+void tg_internal_set_error(const char *msg);   // trajgen.cu
 
 namespace {
 
@@ -93,11 +96,18 @@ void format_traj(std::string &out, bool with_phi, int T, double Ts, long long id
     out.resize(p - &out[0]);
 }
 
+static int io_fail(const char *what, const char *path)
+{
+    const std::string msg = std::string("tg_write_csv: ") + what + " '" + path + "': " + strerror(errno);
+    tg_internal_set_error(msg.c_str());
+    return TG_ERR_INVALID;
+}
+
 int write_one(const char *path, bool with_phi, int B, int T, double Ts, long long id0, const double *X, const double *U,
               int append, int nthreads)
 {
     FILE *f = fopen(path, append ? "ab" : "wb");
-    if (!f) return TG_ERR_INVALID;
+    if (!f) return io_fail("cannot open", path);
     if (!append) fputs(with_phi ? "t,X,Y,phi,vx,vy,omega,d,delta,trajectory_id\n" : "t,X,Y,vx,vy,omega,d,delta,trajectory_id\n", f);
     const int wave = nthreads * 8;
     std::vector<std::string> bufs(wave);
@@ -111,9 +121,9 @@ int write_one(const char *path, bool with_phi, int B, int T, double Ts, long lon
             });
         for (auto &t : th) t.join();
         for (int i = 0; i < nb; ++i)
-            if (fwrite(bufs[i].data(), 1, bufs[i].size(), f) != bufs[i].size()) { fclose(f); return TG_ERR_INVALID; }
+            if (fwrite(bufs[i].data(), 1, bufs[i].size(), f) != bufs[i].size()) { const int rc_ = io_fail("write failed on", path); fclose(f); return rc_; }
     }
-    return fclose(f) == 0 ? TG_OK : TG_ERR_INVALID;
+    return fclose(f) == 0 ? TG_OK : io_fail("close failed on", path);
 }
 
 // ---- merge (generation_traj/merge_datasets.py)
@@ -166,8 +176,6 @@ inline bool parse_id(const char *s, size_t n, long long &v)
 }
 
 }  // namespace
-
-void tg_internal_set_error(const char *msg);   // trajgen.cu
 
 static int merge_fail(const std::string &msg) { tg_internal_set_error(msg.c_str()); return TG_ERR_INVALID; }
 
@@ -228,7 +236,7 @@ extern "C" int tg_merge_csv(const char *first_path, const char *second_path, con
 extern "C" int tg_write_csv(const char *clean_path, const char *noisy_path, int B, int T, double Ts, int64_t traj_id0,
                             const double *clean, const double *noisy, const double *U, int append, int n_threads)
 {
-    if (B < 0 || T < 0 || !(Ts > 0) || (B > 0 && (!U && T > 0))) return TG_ERR_INVALID;
+    if (B < 0 || T < 0 || !(Ts > 0) || (B > 0 && (!U && T > 0))) { tg_internal_set_error("tg_write_csv: bad argument (B, T >= 0, Ts > 0, U required when T > 0)"); return TG_ERR_INVALID; }
     if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
     if (n_threads <= 0) n_threads = 1;
     int rc = TG_OK;

@@ -27,8 +27,6 @@ struct DevCfg {
     int ns;           // number of state components with a finite bound
     int sidx[6];      // their indices
     int ms, m;        // ns*N state rows, 4N + ms rows in total
-    int NP;           // padded matrix width TG*BS
-    int NPP;          // length of a block-padded vector, TG*BSP
     int max_iter, check_every, adaptive_rho, adaptive_rho_min_iter, warm_start, vref_advance;
     int free_mode;    // start solves that have no active row with rho = 1e-6, alpha = 1 (tw_solver.cuh)
     double Ts;
@@ -311,44 +309,11 @@ __device__ __forceinline__ void tg_f_cont_tab(const DevCfg &c, int variant, cons
     }
 }
 
-// The velocity part of f_cont by a lane pair with the tables (see tg_f_cont_tab).  (vx, vy, omega) do not depend on the
-// pose, so the nominal rollout integrates them alone along its sequential chain and recovers heading and position
-// afterwards (tg_solver.cuh, K1a).  aux (optional, lanes 0/1) receives the slip angle before the clamp.
-__device__ __forceinline__ void tg_f_vel_tab(const DevCfg &c, int variant, double vx, double vy, double om, double d, double delta,
-                                             double sd, double cd, int lane, double &f3, double &f4, double &f5, double *aux = nullptr)
-{
-    const double *__restrict__ p = c.p;
-    const int rear = lane & 1, base = lane & ~1;
-    const double vmag = fmax(fabs(vx), p[P_vx_zero]);
-    const double vx_eff = (variant == TG_MODEL_MPC) ? (double)((vx > 0.0) - (vx < 0.0)) * vmag : vmag;
-    const double nl = rear ? (om * p[P_lr] - vy) : (om * p[P_lf] + vy);
-    const double at = tg_slip_atan(c.atan_tab, nl, vx_eff);
-    const double alpha_raw = rear ? at : (-at + delta);
-    const double alpha = tg_clamp(alpha_raw, -p[P_maxAlpha], p[P_maxAlpha]);
-    double g, dg;
-    tg_tyre_tab(c.tyre_tab + rear * (TG_TAB_ROWS * TG_TAB_NC), alpha, p[P_maxAlpha], c.tab_scale, g, dg);
-    const double F = (rear ? p[P_Dr] : p[P_Df]) * g;
-    if (aux && lane < 2) aux[rear] = alpha_raw;
-    const double Fyf = __shfl_sync(0xffffffffu, F, base), Fyr = __shfl_sync(0xffffffffu, F, base + 1);
-    const double vl = (variant == TG_MODEL_MPC) ? vx : vx_eff;
-    const double Frx = (p[P_Cm1] - p[P_Cm2] * vl) * d - p[P_Cr0] - p[P_Cr2] * (vl * vl);
-    const double m = p[P_m];
-    if (variant == TG_MODEL_MPC) {
-        f3 = c.inv_m * (Frx - Fyf * sd + m * vy * om);       // (1.0/m) * (...), MPC/mpc_6stati.py:67
-        f4 = c.inv_m * (Fyr + Fyf * cd - m * vx * om);
-        f5 = c.inv_Iz * (Fyf * p[P_lf] * cd - Fyr * p[P_lr]);
-    } else {
-        f3 = (Frx - Fyf * sd + m * vy * om) / m;
-        f4 = (Fyr + Fyf * cd - m * vx * om) / m;
-        f5 = (Fyf * p[P_lf] * cd - Fyr * p[P_lr]) / p[P_Iz];
-    }
-}
-
 // One Euler stage of the velocity recurrence (vx, vy, omega) <- (vx, vy, omega) + Ts f_{3..5} by a lane pair (lane & 1:
 // 0 = front tyre, 1 = rear tyre), written for the SHORTEST dependent chain: this recurrence is the longest sequential chain
 // of an MPC step (N stages, nothing else of the step can start before it ends).  Per-step constants are hoisted into
 // TgRoll; the tables are indexed without F2I / I2F; clamps are compare-selects; the force exchange is one xor-shuffle; the
-// sums are re-associated so that two FMAs follow the tyre force (results differ from tg_f_vel_tab in the last bit only).
+// sums are re-associated so that two FMAs follow the tyre force (results differ from tg_f_cont_tab's in the last bit only).
 // Variants MPC / GEN2 (both slip angles clamped).  aux (optional, shared memory) receives the slip angle before the clamp.
 struct TgRoll {
     double L, svy, sa, da, D, ma, tscale, toff, Ts_im, Ts_iI5f, Ts_iI5r, cdm, d, sd;

@@ -19,7 +19,6 @@
 #include <string>
 #include <vector>
 
-#include "tg_solver.cuh"
 #include "tw_solver.cuh"
 #include "tg_openloop.cuh"
 #include "tg_estimator.cuh"
@@ -33,18 +32,6 @@ void tg_internal_set_error(const char *msg) { g_err = msg; }   // for tg_csv.cpp
         if (e_ != cudaSuccess) return fail(TG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-// A shape is (BS, TG): TG x TG threads, each owning a BS x BS block of the n x n matrix (n <= BS*TG).
-// TG_MINB = resident CTAs per SM the register allocator must allow (65536 / (threads * MINB) registers/thread):
-// 64 threads x 8 CTAs -> 128 registers for N <= 20, which leaves room to keep operand loads in flight.
-#define TG_NT(BS, TG) ((TG) * (TG))
-#ifndef TG_MINB8
-#define TG_MINB8 8
-#endif
-#define TG_MINB(BS, TG) ((TG) == 8 ? TG_MINB8 : ((BS) <= 5 ? 2 : 1))
-#define TG_KATTR(BS, TG) __launch_bounds__(TG_NT(BS, TG), TG_MINB(BS, TG))
-#define TG_PPC_MAX 8       // most problems one CTA of the closed-loop kernel holds (64-thread shapes): 512 threads
-
-// ------------------------------------------------------------------------------------------------ kernels
 struct StepArgs {
     int B;
     const double *x0, *u_prev, *path_ref, *vref;
@@ -53,122 +40,8 @@ struct StepArgs {
     double *A, *Bm, *g, *xbar, *H, *q, *c0, *l, *u, *Gs;
     int stop;
     double *ws_x, *ws_y; int *ws_valid;   // per-problem warm-start state (step API), may be null
-    double *Hws;                          // per-problem-slot H workspace, may be null
     int ppc;                              // problems per CTA
 };
-
-// a.ppc problems per CTA, side by side (see tg_closed_loop_kernel): problem slot = threadIdx.x / NT
-template <int BS, int TG, bool MULTI>
-__global__ void __launch_bounds__(TG_NT(BS, TG) * (MULTI ? TG_PPC_MAX : 1), MULTI ? 1 : TG_MINB(BS, TG))
-tg_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, const __grid_constant__ StepArgs a)
-{
-    extern __shared__ __align__(16) double sm_all[];
-    constexpr int NT = TG_NT(BS, TG);
-    const int P = MULTI ? a.ppc : 1;
-    int prob = MULTI ? threadIdx.x / NT : 0, tid = MULTI ? threadIdx.x % NT : threadIdx.x;
-    unsigned sm_off = (unsigned)prob * (unsigned)((L.total + 1) & ~1) * 8u;
-    asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));   // see tg_closed_loop_kernel
-    const int bar = 1 + prob;
-    double *sm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm_all) + sm_off);
-    const int N = c.N, n = c.n, m = c.m;
-    double *Hws = a.Hws ? a.Hws + ((size_t)blockIdx.x * P + prob) * c.NP * c.NP : nullptr;
-    for (int b0 = blockIdx.x * P; b0 < a.B; b0 += gridDim.x * P) {
-        const int b = b0 + prob;
-        if (MULTI && P > 1 && a.B - b0 >= P) tg_sync(15, NT * P);   // all slots busy: start the round together
-        if (b >= a.B) continue;
-        tg_psync<MULTI>(bar, NT);
-        if (tid < 6) sm[L.x0 + tid] = a.x0[6 * (size_t)b + tid];
-        if (tid < 2) sm[L.uprev + tid] = a.u_prev[2 * (size_t)b + tid];
-        const double vx0 = a.x0[6 * (size_t)b + 3];
-        for (int k = tid; k <= N; k += NT) {
-            if (a.path_ref) {
-                const double *pr = a.path_ref + 3 * ((size_t)b * (N + 1) + k);
-                sm[L.Xr + k] = pr[0]; sm[L.Yr + k] = pr[1]; sm[L.Pr + k] = pr[2];
-            } else { sm[L.Xr + k] = 0.0; sm[L.Yr + k] = 0.0; sm[L.Pr + k] = 0.0; }
-            sm[L.vref + k] = a.vref ? a.vref[(size_t)b * (N + 1) + k] : vx0;
-        }
-        bool warm = false;
-        if (a.ws_valid && c.warm_start && a.ws_valid[b]) {
-            warm = true;
-            for (int i = tid; i < n; i += NT) sm[L.x + i] = a.ws_x[(size_t)b * n + i];
-            for (int i = tid; i < m; i += NT) sm[L.y + i] = a.ws_y[(size_t)b * m + i];
-        }
-        tg_psync<MULTI>(bar, NT);
-        StepTaps tap;
-        tap.A = a.A ? a.A + (size_t)b * N * 36 : nullptr;
-        tap.Bm = a.Bm ? a.Bm + (size_t)b * N * 12 : nullptr;
-        tap.g = a.g ? a.g + (size_t)b * N * 6 : nullptr;
-        tap.xbar = a.xbar ? a.xbar + (size_t)b * (N + 1) * 6 : nullptr;
-        tap.H = a.H ? a.H + (size_t)b * n * n : nullptr;
-        tap.q = a.q ? a.q + (size_t)b * n : nullptr;
-        tap.c0 = a.c0 ? a.c0 + b : nullptr;
-        tap.l = a.l ? a.l + (size_t)b * m : nullptr;
-        tap.u = a.u ? a.u + (size_t)b * m : nullptr;
-        tap.Gs = a.Gs ? a.Gs + (size_t)b * c.ms * n : nullptr;
-        tap.stop = a.stop;
-        const StepResult r = tg_mpc_step_body<BS, TG, MULTI>(c, L, sm, warm, Hws, tap, nullptr, tid, bar);
-        if (a.stop) continue;
-        const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);  // :261
-        const double ud = sm[L.uprev], udel = sm[L.uprev + 1];
-        if (tid == 0) {
-            a.u_cmd[2 * (size_t)b] = ok ? ud + sm[L.xt] : ud;          // :265 / fallback :262
-            a.u_cmd[2 * (size_t)b + 1] = ok ? udel + sm[L.xt + 1] : udel;
-            if (a.status) a.status[b] = r.status;
-            if (a.iters) a.iters[b] = r.iters;
-            if (a.objective) a.objective[b] = ok ? r.objective : nan("");
-        }
-        if (a.U_opt)
-            for (int i = tid; i < n; i += NT) a.U_opt[(size_t)b * n + i] = ok ? ((i & 1) ? udel : ud) + sm[L.xt + i] : nan("");
-        if (a.y_opt)
-            for (int i = tid; i < m; i += NT) a.y_opt[(size_t)b * m + i] = ok ? sm[L.y + i] : nan("");
-        if (a.X_opt && tid == 0) {   // X_k of the QP: x_{k+1} = A_k x_k + B_k u_k + g_k  (:189-192)
-            double *X = a.X_opt + (size_t)b * (N + 1) * 6;
-            double xs[6];
-            for (int i = 0; i < 6; ++i) { xs[i] = sm[L.x0 + i]; X[i] = ok ? xs[i] : nan(""); }
-            for (int k = 0; k < N; ++k) {
-                const double *r_ = sm + L.lin + TG_LIN * k, *g_ = sm + L.gl + 6 * k;
-                const double u0 = ud + sm[L.xt + 2 * k], u1 = udel + sm[L.xt + 2 * k + 1];
-                double nx[6];
-                nx[0] = xs[0] + r_[0] * xs[2] + r_[1] * xs[3] + r_[2] * xs[4] + g_[0];
-                nx[1] = xs[1] + r_[3] * xs[2] + r_[4] * xs[3] + r_[5] * xs[4] + g_[1];
-                nx[2] = xs[2] + r_[6] * xs[5] + g_[2];
-                nx[3] = r_[7] * xs[3] + r_[8] * xs[4] + r_[9] * xs[5] + r_[16] * u0 + r_[17] * u1 + g_[3];
-                nx[4] = r_[10] * xs[3] + r_[11] * xs[4] + r_[12] * xs[5] + r_[18] * u1 + g_[4];
-                nx[5] = r_[13] * xs[3] + r_[14] * xs[4] + r_[15] * xs[5] + r_[19] * u1 + g_[5];
-                for (int i = 0; i < 6; ++i) { xs[i] = nx[i]; X[6 * (k + 1) + i] = ok ? xs[i] : nan(""); }
-            }
-        }
-        if (a.ws_valid && c.warm_start) {
-            for (int i = tid; i < n; i += NT) a.ws_x[(size_t)b * n + i] = sm[L.xt + i];
-            for (int i = tid; i < m; i += NT) a.ws_y[(size_t)b * m + i] = sm[L.y + i];
-            if (tid == 0) a.ws_valid[b] = ok ? 1 : 0;
-        }
-    }
-}
-
-// reference window into shared memory (MPC/main.py:87-90)
-__device__ __forceinline__ void tg_ref_window_dev(const DevCfg &c, const SmemLayout &L, double *sm, const tg_ref_spec &sp,
-                                                  const double *brk, const double *coef, int t_index)
-{
-    const int tid = threadIdx.x, NT = blockDim.x, N = c.N;
-    const double t0 = c.vref_advance ? (double)t_index * c.Ts : 0.0;
-    const double vx0 = sm[L.x0 + 3];
-    for (int k = tid; k <= N; k += NT) sm[L.vref + k] = tg_vref_at(sp.vref_kind, sp.vref, t0 + (double)k * c.Ts, vx0);
-    __syncthreads();
-    if (tid == 0) {
-        double xs = sm[L.x0];
-        sm[L.Xr] = xs;
-        for (int k = 0; k < N; ++k) { xs = xs + sm[L.vref + k] * c.Ts; sm[L.Xr + k + 1] = xs; }   // :59-61
-    }
-    __syncthreads();
-    for (int k = tid; k <= N; k += NT) {
-        double y, dy;
-        tg_path_at(sp, brk, coef, sm[L.Xr + k], y, dy);
-        sm[L.Yr + k] = y;
-        sm[L.Pr + k] = tg_atan(dy);   // :66
-    }
-    __syncthreads();
-}
 
 struct LoopArgs {
     int B, T;
@@ -179,121 +52,8 @@ struct LoopArgs {
     double *clean, *noisy, *U;
     int *status_counts;
     long long *iters_total;
-    double *Hws;
     int ppc;   // problems per CTA
 };
-
-// P problems per CTA, side by side: problem p = threadIdx.x / NT owns its own shared-memory block and named barrier 1 + p.
-// The step body is ~110 KB of code that every trajectory walks through once per step; with one problem per CTA the 7
-// CTAs of an SM drift into different phases and the instruction caches thrash (ncu: L1 instruction hit rate 70 %, the
-// GPC instruction cache at 87 % of its request peak).  Problems of one CTA are re-aligned at every step boundary
-// (barrier 15), so they fetch the same lines at the same time.
-// P = a.ppc is a launch parameter (1..TG_PPC_MAX for the 64-thread shapes, 1 otherwise): the register budget is that of
-// the largest CTA (512 threads x 128 registers = one full register file), which is also what 8 single-problem CTAs get.
-template <int BS, int TG, bool MULTI>
-__global__ void __launch_bounds__(TG_NT(BS, TG) * (MULTI ? TG_PPC_MAX : 1), MULTI ? 1 : TG_MINB(BS, TG))
-tg_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, const __grid_constant__ LoopArgs a)
-{
-    extern __shared__ __align__(16) double sm_all[];
-    constexpr int NT = TG_NT(BS, TG);
-    const int P = MULTI ? a.ppc : 1;
-    int prob = MULTI ? threadIdx.x / NT : 0, tid = MULTI ? threadIdx.x % NT : threadIdx.x;
-    unsigned sm_off = (unsigned)prob * (unsigned)((L.total + 1) & ~1) * 8u;
-    // opaque to the compiler: under register pressure it otherwise re-reads %tid.x and redoes this arithmetic at every use
-    // (45 S2R sites, 7 % of the executed instructions in the several-problems-per-CTA kernel)
-    asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));
-    const int bar = 1 + prob;
-    double *sm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm_all) + sm_off);
-    const int n = c.n, ms = c.ms, ns = c.ns, T = a.T;
-    double *Hws = a.Hws ? a.Hws + ((size_t)blockIdx.x * P + prob) * c.NP * c.NP : nullptr;
-    const StepTaps tap = {};
-    int *cnt = reinterpret_cast<int *>(sm + L.misc + M_CNT);                 // 6 status counters
-    long long *itsum = reinterpret_cast<long long *>(sm + L.misc + M_CNT + 3);
-    // Trajectories are dealt round-robin over the CTAs: slot `prob` of CTA c takes b = c + G (round P + prob), G = gridDim.x;
-    // `active` (the busy slots of this CTA in this round) is what the step barrier counts.
-    const int G = gridDim.x;
-    for (int round = 0; blockIdx.x + (long long)G * round * P < a.B; ++round) {
-        const long long bfirst = blockIdx.x + (long long)G * round * P;
-        const long long left = (a.B - 1 - bfirst) / G + 1;                   // slots with a trajectory, >= 1
-        const int active = left < P ? (int)left : P;
-        const bool lockstep = MULTI && active > 1;
-        if (prob >= active) break;                                           // later rounds have no work for this slot either
-        const int b = (int)(bfirst + (long long)G * prob);
-        tg_psync<MULTI>(bar, NT);
-        if (tid < 12) sm[L.spec + tid] = reinterpret_cast<const double *>(a.spec + b)[tid];   // scenario -> shared memory
-        if (tid < 6) { const double v_ = a.x0[6 * (size_t)b + tid]; sm[L.x0 + tid] = v_; a.clean[(size_t)b * (T + 1) * 6 + tid] = v_; }
-        if (tid < 2) sm[L.uprev + tid] = a.u0[2 * (size_t)b + tid];
-        if (tid < TG_NUM_STATUS) cnt[tid] = 0;
-        if (tid == 0) *itsum = 0;
-        bool warm = false;
-        tg_psync<MULTI>(bar, NT);
-#pragma unroll 1
-        for (int t = 0; t <= T; ++t) {
-            FusedCtx fx;
-            fx.brk = a.brk; fx.coef = a.coef;
-            fx.noisy_row = a.noisy + ((size_t)b * (T + 1) + t) * 6;
-            fx.seed = c.seed_base + (unsigned long long)(a.traj_id0 + b);
-            fx.t_index = t;
-            if (t == T) {   // last row: only its noisy copy remains to be written
-                const int nbase = (NT >= 96) ? 64 : 32;
-                if (tid >= nbase && tid < nbase + 3) {
-                    const int pr = tid - nbase;
-                    uint32_t r4[4];
-                    tg_philox4x32_10((uint32_t)t, (uint32_t)(pr >> 1), 0u, 0u, (uint32_t)fx.seed, (uint32_t)(fx.seed >> 32), r4);
-                    double n0, n1;
-                    tg_box_muller(r4[(pr & 1) * 2], r4[(pr & 1) * 2 + 1], n0, n1);
-                    fx.noisy_row[2 * pr] = sm[L.x0 + 2 * pr] + c.noise_std[2 * pr] * n0;
-                    fx.noisy_row[2 * pr + 1] = sm[L.x0 + 2 * pr + 1] + c.noise_std[2 * pr + 1] * n1;
-                }
-                break;
-            }
-            const StepResult r = tg_mpc_step_body<BS, TG, MULTI>(c, L, sm, warm, Hws, tap, &fx, tid, bar);
-            const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);
-            if (tid == 0) { cnt[r.status] += 1; *itsum += r.iters; }
-            // shifted warm start for the next step, in the next step's dU coordinates
-            double nx = 0.0, nyb = 0.0, nyr = 0.0;
-            if (tid < n) {
-                const double d0 = sm[L.xt + (tid & 1)];
-                nx = ((tid + 2 < n) ? sm[L.xt + tid + 2] : sm[L.xt + tid]) - d0;
-                if (tid + 2 < n) { nyb = sm[L.y + tid + 2]; nyr = sm[L.y + n + tid + 2]; }
-            }
-            if (tid < 32) {   // plant (MPC/main.py:97) + outputs, warp 0 (quad-parallel f_cont)
-                const double ud = sm[L.uprev], udel = sm[L.uprev + 1];
-                const double u0 = ok ? ud + sm[L.xt] : ud, u1 = ok ? udel + sm[L.xt + 1] : udel;
-                double xs[6];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) xs[i] = sm[L.x0 + i];
-                tg_plant_step_lanes(c, xs, u0, u1, tid);
-                if (tid == 0) {
-                    double *clean = a.clean + ((size_t)b * (T + 1) + t + 1) * 6;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) { sm[L.misc + M_XNEXT + i] = xs[i]; clean[i] = xs[i]; }
-                    a.U[((size_t)b * T + t) * 2] = u0; a.U[((size_t)b * T + t) * 2 + 1] = u1;
-                    sm[L.misc + M_UCMD] = u0; sm[L.misc + M_UCMD + 1] = u1;
-                }
-            }
-            double tmp[4];   // ms <= 6 N <= 4 NT for every supported shape
-            if (ms > 0) {
-#pragma unroll
-                for (int r_ = 0; r_ < 4; ++r_) { const int i = tid + r_ * NT; tmp[r_] = (i + ns < ms) ? sm[L.y + 2 * n + i + ns] : 0.0; }
-            }
-            tg_psync<MULTI>(bar, NT);
-            // commit the new state / warm start
-            if (tid < 6) sm[L.x0 + tid] = sm[L.misc + M_XNEXT + tid];
-            if (tid < 2) sm[L.uprev + tid] = sm[L.misc + M_UCMD + tid];
-            if (tid < n) { sm[L.x + tid] = nx; sm[L.y + tid] = nyb; sm[L.y + n + tid] = nyr; }
-            if (ms > 0) {
-#pragma unroll
-                for (int r_ = 0; r_ < 4; ++r_) { const int i = tid + r_ * NT; if (i < ms) sm[L.y + 2 * n + i] = tmp[r_]; }
-            }
-            warm = ok && c.warm_start;
-            if (lockstep) tg_sync(15, NT * active); else tg_psync<MULTI>(bar, NT);
-        }
-        tg_psync<MULTI>(bar, NT);
-        if (tid < TG_NUM_STATUS && a.status_counts) a.status_counts[(size_t)b * TG_NUM_STATUS + tid] = cnt[tid];
-        if (tid == 0 && a.iters_total) a.iters_total[b] = *itsum;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------ warp-per-problem kernels
 // tw_solver.cuh: W warps per problem (W = 1 for N <= 20), P problems per CTA side by side, each with its own shared-memory
@@ -506,19 +266,21 @@ tw_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
     }
 }
 
-__global__ void tg_ref_window_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ SmemLayout L, int B,
+// a10 tap: the reference window of tw_ref_window_warp for B states, one warp per problem
+__global__ void tg_ref_window_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ WLayout L, int B,
                                      const double *x0, const tg_ref_spec *spec, const double *brk, const double *coef,
                                      int t_index, double *path_ref, double *vref)
 {
     extern __shared__ __align__(16) double sm[];
-    const int tid = threadIdx.x, NT = blockDim.x, N = c.N;
+    const int lane = threadIdx.x, N = c.N;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        __syncthreads();
-        if (tid < 6) sm[L.x0 + tid] = x0[6 * (size_t)b + tid];
-        __syncthreads();
+        __syncwarp();
+        if (lane < 6) sm[L.x0 + lane] = x0[6 * (size_t)b + lane];
+        __syncwarp();
         const tg_ref_spec sp = spec[b];
-        tg_ref_window_dev(c, L, sm, sp, brk, coef, t_index);
-        for (int k = tid; k <= N; k += NT) {
+        tw_ref_window_warp<0, 1>(c, L, sm, sp, brk, coef, t_index, lane);
+        __syncwarp();
+        for (int k = lane; k <= N; k += 32) {
             double *pr = path_ref + 3 * ((size_t)b * (N + 1) + k);
             pr[0] = sm[L.Xr + k]; pr[1] = sm[L.Yr + k]; pr[2] = sm[L.Pr + k];
             vref[(size_t)b * (N + 1) + k] = sm[L.vref + k];
@@ -573,23 +335,6 @@ __global__ void tg_fma_peak_kernel(T *out, int iters)
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-struct Shape { int BS, TG, NP, NPP, NT; };
-
-static bool pick_shape(int N, Shape &s)
-{
-    const int n = 2 * N;
-    if (n <= 24) { s.BS = 3; s.TG = 8; }
-    else if (n <= 40) { s.BS = 5; s.TG = 8; }
-    else if (n <= 64) { s.BS = 4; s.TG = 16; }
-    else if (n <= 80) { s.BS = 5; s.TG = 16; }
-    else if (n <= 112) { s.BS = 7; s.TG = 16; }
-    else return false;
-    s.NP = s.BS * s.TG;
-    s.NPP = ((s.BS + 1) & ~1) * s.TG;
-    s.NT = s.TG * s.TG;
-    return true;
-}
-
 // Tyre-curve table (tg_device.cuh: tg_tyre_tab): per interval the degree-(NC-1) Chebyshev interpolant of
 // g(alpha) = sin(C atan(B alpha)) in long double, converted to monomials of s in [-1, 1].  Returns the largest
 // deviation from libm on a dense check grid (value and slope) so the caller can refuse a table that is not at
@@ -656,19 +401,16 @@ static double build_atan_table(double *tab /*[TG_ATAN_ROWS][NC]*/)
 struct tg_handle {
     tg_config cfg;
     DevCfg dc;
-    SmemLayout L;
-    Shape shape;
     int device, num_sms, grid_cap;
     int ppc_max, ppc_env;     // closed-loop kernel: most problems per CTA that fit / TRAJGEN_PPC override (0 = automatic)
     // warp-per-problem kernels (tw_solver.cuh): W warps per problem, S tile blocks per thread
-    int use_tw, W, S;
+    int W, S;
     WLayout WL;
-    SmemLayout Lref;          // small layout of the reference-window tap kernel
+    WLayout Lref;             // layout of the reference-window tap kernel (no state rows, one warp)
     size_t smem_optin;
     size_t smem_bytes;
     cudaStream_t stream;
     long long launches;
-    double *Hws; size_t Hws_elems;
     double *tyre_tab;   // device copy of the tyre-curve table, or null (fit not at rounding level -> atan/sin path)
     double tab_err[2];  // max |table - libm| of value and slope on the check grid
     // warm-start state for the step API
@@ -678,44 +420,6 @@ struct tg_handle {
     void *hstage; size_t hstage_bytes;
 };
 
-template <typename F>
-static int dispatch_shape(const Shape &s, F &&f)
-{
-#ifndef TG_ONLY_SHAPE_5_8
-    if (s.BS == 3 && s.TG == 8) return f(std::integral_constant<int, 3>(), std::integral_constant<int, 8>());
-#endif
-    if (s.BS == 5 && s.TG == 8) return f(std::integral_constant<int, 5>(), std::integral_constant<int, 8>());
-#ifndef TG_ONLY_SHAPE_5_8
-    if (s.BS == 4 && s.TG == 16) return f(std::integral_constant<int, 4>(), std::integral_constant<int, 16>());
-    if (s.BS == 5 && s.TG == 16) return f(std::integral_constant<int, 5>(), std::integral_constant<int, 16>());
-    if (s.BS == 7 && s.TG == 16) return f(std::integral_constant<int, 7>(), std::integral_constant<int, 16>());
-#endif
-    return fail(TG_ERR_UNSUPPORTED, "no kernel shape for this horizon");
-}
-
-// kernel instance for a shape: `multi` = several problems per CTA (64-thread shapes only)
-template <typename F>
-static int dispatch_loop(const Shape &s, bool multi, F &&f)
-{
-    return dispatch_shape(s, [&](auto BS_, auto TG_) -> int {
-        constexpr int BS = decltype(BS_)::value, TG = decltype(TG_)::value;
-        if constexpr (TG == 8) { if (multi) return f(tg_closed_loop_kernel<BS, TG, true>); }
-        return f(tg_closed_loop_kernel<BS, TG, false>);
-    });
-}
-template <typename F>
-static int dispatch_step(const Shape &s, bool multi, F &&f)
-{
-    return dispatch_shape(s, [&](auto BS_, auto TG_) -> int {
-        constexpr int BS = decltype(BS_)::value, TG = decltype(TG_)::value;
-        if constexpr (TG == 8) { if (multi) return f(tg_mpc_step_kernel<BS, TG, true>); }
-        return f(tg_mpc_step_kernel<BS, TG, false>);
-    });
-}
-
-
-// (W, S) of the warp-per-problem kernels for a horizon: the lower triangle of the n x n matrix in 4 x 4 blocks must fit the
-// 32 W S slots, and a thread owns at most one stage (N <= 32 W)
 static bool pick_tw_shape(int N, int &W, int &S)
 {
     if (const char *e = getenv("TRAJGEN_SHAPE")) {   // development knob: "W,S" (must fit the horizon)
@@ -742,7 +446,7 @@ static int dispatch_tw(int W, int S, int N, F &&f)
     if (W == 2 && S == 1 && N == 20 && !getenv("TRAJGEN_DYNAMIC_N")) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 20>());
     if (W == 1 && S == 1) return f(integral_constant<int, 1>(), integral_constant<int, 1>(), integral_constant<int, 0>());
     if (W == 2 && S == 1) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 0>());
-#ifndef TG_ONLY_SHAPE_5_8
+#ifndef TG_DEV_SHAPES_ONLY
     if (W == 4 && S == 1) return f(integral_constant<int, 4>(), integral_constant<int, 1>(), integral_constant<int, 0>());
     if (W == 8 && S == 1) return f(integral_constant<int, 8>(), integral_constant<int, 1>(), integral_constant<int, 0>());
     if (W == 8 && S == 2) return f(integral_constant<int, 8>(), integral_constant<int, 2>(), integral_constant<int, 0>());
@@ -786,8 +490,8 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     if (!(cfg->Ts > 0)) return fail(TG_ERR_INVALID, "Ts must be > 0");
     if (cfg->max_iter < 1 || cfg->check_every < 1) return fail(TG_ERR_INVALID, "max_iter and check_every must be >= 1");
     if (!(cfg->rho > 0) || !(cfg->sigma > 0) || !(cfg->alpha > 0 && cfg->alpha < 2)) return fail(TG_ERR_INVALID, "rho, sigma > 0 and 0 < alpha < 2 required");
-    Shape sh;
-    if (!pick_shape(cfg->N, sh)) return fail(TG_ERR_UNSUPPORTED, "horizon N > 56 is not supported");
+    int W_ = 0, S_ = 0;
+    if (!pick_tw_shape(cfg->N, W_, S_)) return fail(TG_ERR_UNSUPPORTED, "horizon N > 56 is not supported");
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (ndev == 0) return fail(TG_ERR_CUDA, "no CUDA device: libtrajgen has no CPU fallback");
@@ -800,14 +504,14 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
     tg_handle *h = new (std::nothrow) tg_handle();
     if (!h) return fail(TG_ERR_NOMEM, "out of host memory");
     memset(h, 0, sizeof(*h));
-    struct Guard { tg_handle *p; ~Guard() { if (p) { cudaFree(p->Hws); cudaFree(p->tyre_tab); delete p; } } } guard{h};   // released on success
-    h->cfg = *cfg; h->shape = sh; h->device = device; h->num_sms = prop.multiProcessorCount;
+    struct Guard { tg_handle *p; ~Guard() { if (p) { cudaFree(p->tyre_tab); delete p; } } } guard{h};   // released on success
+    h->cfg = *cfg; h->W = W_; h->S = S_; h->device = device; h->num_sms = prop.multiProcessorCount;
     DevCfg &d = h->dc;
     d.N = cfg->N; d.n = 2 * cfg->N; d.model = cfg->model; d.plant = cfg->plant; d.jacobian = cfg->jacobian;
     d.ns = 0;
     for (int i = 0; i < 6; ++i)
         if (cfg->x_lo[i] > -TG_INF || cfg->x_hi[i] < TG_INF) d.sidx[d.ns++] = i;
-    d.ms = d.ns * d.N; d.m = 4 * d.N + d.ms; d.NP = sh.NP; d.NPP = sh.NPP;
+    d.ms = d.ns * d.N; d.m = 4 * d.N + d.ms;
     d.max_iter = cfg->max_iter; d.check_every = cfg->check_every; d.adaptive_rho = cfg->adaptive_rho;
     d.adaptive_rho_min_iter = cfg->adaptive_rho_min_iter; d.warm_start = cfg->warm_start; d.vref_advance = cfg->vref_advance;
     d.Ts = cfg->Ts;
@@ -845,17 +549,10 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
 
     d.free_mode = (cfg->solver_flags & 1) ? 0 : 1;
     h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
-    h->Lref = tg_make_layout(d.N, 0, d.NP, d.NPP);
+    h->Lref = tw_make_layout(d.N, 0, 1);
     CK(cudaFuncSetAttribute(tg_ref_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-    // Which body: the warp-per-problem kernels (tw_solver.cuh) for every horizon they are enabled for, else the legacy
-    // CTA-per-problem kernels.  TRAJGEN_TW = 0 forces the legacy kernels (development knob).
-    h->use_tw = 0;
-    if (pick_tw_shape(d.N, h->W, h->S)) {
-        const char *e = getenv("TRAJGEN_TW");
-        h->use_tw = (e && strcmp(e, "0") == 0) ? 0 : 1;
-    }
     h->ppc_env = 0;   // TRAJGEN_PPC pins the number of problems per CTA (measurement knob)
-    if (h->use_tw) {
+    {
         h->WL = tw_make_layout(d.N, d.ms, h->W);
         const size_t stride = tw_stride(h);
         h->smem_bytes = stride;
@@ -879,39 +576,6 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
         if (rc != TG_OK) return rc;
         if (occ < 1) return fail(TG_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration");
         h->grid_cap = occ * h->num_sms;     // resident problems with one problem per CTA
-    } else {
-    h->L = tg_make_layout(d.N, d.ms, d.NP, d.NPP);
-    h->smem_bytes = (size_t)h->L.total * sizeof(double);
-    if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
-        return fail(TG_ERR_UNSUPPORTED, "state-bound rows x horizon exceed the 227 KB shared memory of one CTA");
-    }
-    int occ = 0;
-    const size_t stride = (((size_t)h->L.total + 1) & ~(size_t)1) * sizeof(double);   // shared memory of one problem
-    h->ppc_max = 1;
-    if (sh.NT == 64) {   // several problems per CTA for the 64-thread shapes, as many as fit in shared memory
-        h->ppc_max = TG_PPC_MAX;
-        while (h->ppc_max > 1 && (size_t)h->ppc_max * stride > h->smem_optin) h->ppc_max -= 1;
-    }
-    if (const char *e = getenv("TRAJGEN_PPC")) { const int v = atoi(e); if (v >= 1 && v <= h->ppc_max) h->ppc_env = v; }
-    int rc = TG_OK;
-    for (int multi = 0; multi <= (h->ppc_max > 1 ? 1 : 0) && rc == TG_OK; ++multi) {
-        auto setup = [&](auto kern) -> int {
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            if (!multi) { int o = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, sh.NT, h->smem_bytes)); occ = (occ == 0 || o < occ) ? o : occ; }
-            return TG_OK;
-        };
-        rc = dispatch_step(sh, multi != 0, setup);
-        if (rc == TG_OK) rc = dispatch_loop(sh, multi != 0, setup);
-    }
-    if (rc != TG_OK) return rc;
-    if (occ < 1) return fail(TG_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration");
-    h->grid_cap = occ * h->num_sms;
-    }
-    if (d.adaptive_rho && !h->use_tw) {   // (the warp-per-problem body rebuilds H from the stage records instead of keeping a copy)
-        const size_t slots = std::max((size_t)h->grid_cap, (size_t)h->num_sms * TG_PPC_MAX);   // resident problems, either kernel
-        h->Hws_elems = slots * d.NP * d.NP;
-        CK(cudaMalloc(&h->Hws, h->Hws_elems * sizeof(double)));
     }
     h->stream = 0;
     guard.p = nullptr;
@@ -923,7 +587,7 @@ int tg_destroy(tg_handle *h)
 {
     if (!h) return TG_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->Hws); cudaFree(h->tyre_tab); cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_valid); cudaFree(h->dstage);
+    cudaFree(h->tyre_tab); cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_valid); cudaFree(h->dstage);
     if (h->hstage) cudaFreeHost(h->hstage);
     delete h;
     return TG_OK;
@@ -935,7 +599,7 @@ int tg_info(tg_handle *h, int32_t *ctas_per_sm, int32_t *threads_per_cta, int32_
 {
     if (!h) return fail(TG_ERR_INVALID, "null handle");
     if (ctas_per_sm) *ctas_per_sm = h->grid_cap / h->num_sms;
-    if (threads_per_cta) *threads_per_cta = h->use_tw ? 32 * h->W : h->shape.NT;
+    if (threads_per_cta) *threads_per_cta = 32 * h->W;
     if (smem_bytes) *smem_bytes = (int32_t)h->smem_bytes;
     if (num_sms) *num_sms = h->num_sms;
     return TG_OK;
@@ -957,27 +621,6 @@ int tg_tyre_table_info(tg_handle *h, int32_t *in_use, double *max_value_err, dou
     return TG_OK;
 }
 int tg_kernel_launches(tg_handle *h, int64_t *count) { if (!h || !count) return fail(TG_ERR_INVALID, "null argument"); *count = h->launches; return TG_OK; }
-
-// Problems per CTA (64-thread shapes; a 256-thread CTA is one problem): problems of one CTA run in lockstep and share
-// their instruction fetches.
-static int choose_ppc(const tg_handle *h, int B)
-{
-    if (h->ppc_max <= 1) return 1;
-    if (h->ppc_env) return h->ppc_env;
-    // measured on the headline workload (1024 trajectories, 21 KB of shared memory each): 4 per CTA (two CTAs per SM, out
-    // of phase with each other) 1.53e7 steps/s, 8 per CTA 1.49e7, 2 per CTA 1.41e7, 1 per CTA 1.07e7.  Resident problems
-    // come first, though: with state-bound rows a problem needs 40+ KB and long, unequal solves, where 5 free-running
-    // single-problem CTAs per SM beat 4 problems in lockstep (config 4, N = 20: 1.5e6 vs 1.1e6 steps/s).
-    const size_t stride = (((size_t)h->L.total + 1) & ~(size_t)1) * sizeof(double);
-    int best = 1, best_res = 0;
-    for (int p = 1; p <= 4 && p <= h->ppc_max; p *= 2) {
-        if (p > 1 && B < p * h->num_sms) break;                   // small batches keep at least one CTA per SM
-        const int by_regs = TG_PPC_MAX / p, by_smem = (int)(h->smem_optin / ((size_t)p * stride));
-        const int res = p * (by_regs < by_smem ? by_regs : by_smem);
-        if (res >= best_res) { best = p; best_res = res; }
-    }
-    return best;
-}
 
 // warp-per-problem kernels: problems per CTA.  Resident problems per SM are bounded by registers (512 threads x 128) and
 // shared memory either way; larger CTAs share more instruction fetches, smaller ones spread a small batch over more SMs.
@@ -1018,29 +661,10 @@ static int launch_step(tg_handle *h, StepArgs &a)
 {
     if (a.B <= 0) return TG_OK;   // empty batch: nothing to do
     CK(cudaSetDevice(h->device));
-    if (h->use_tw)
-        return dispatch_tw(h->W, h->S, h->dc.N, [&](auto W_, auto S_, auto NC_) -> int {
-            constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
-            return launch_tw(h, tw_mpc_step_kernel<W, S, NC>, a, a.B, W);
-        });
-    a.Hws = h->Hws;
-    // a batch that is resident at once starts in phase on every SM anyway (one step does not drift), and single-problem CTAs
-    // spread it more evenly (p50 of a 1024-problem call: 0.232 ms vs 0.250 ms with 4 per CTA); larger batches run in rounds
-    const int ppc = (a.B <= h->grid_cap && !h->ppc_env) ? 1 : choose_ppc(h, a.B);
-    a.ppc = ppc;
-    const size_t smem = ppc > 1 ? (size_t)ppc * (((size_t)h->L.total + 1) & ~(size_t)1) * sizeof(double) : h->smem_bytes;
-    int per_sm = 0;
-    int rc = dispatch_step(h->shape, ppc > 1, [&](auto kern) -> int {
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, h->shape.NT * ppc, smem));
-        if (per_sm < 1) return fail(TG_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration");
-        const int ctas = (a.B + ppc - 1) / ppc, cap = per_sm * h->num_sms;
-        kern<<<ctas < cap ? ctas : cap, h->shape.NT * ppc, smem, h->stream>>>(h->dc, h->L, a);
-        return TG_OK;
+    return dispatch_tw(h->W, h->S, h->dc.N, [&](auto W_, auto S_, auto NC_) -> int {
+        constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
+        return launch_tw(h, tw_mpc_step_kernel<W, S, NC>, a, a.B, W);
     });
-    if (rc != TG_OK) return rc;
-    h->launches += 1;
-    CK(cudaGetLastError());
-    return TG_OK;
 }
 
 int tg_linearize(tg_handle *h, int B, const double *x0, const double *u_prev, double *A, double *Bm, double *g, double *xbar)
@@ -1102,7 +726,7 @@ int tg_ref_window(tg_handle *h, int B, const double *x0, const tg_ref_spec *spec
     if (B == 0) return TG_OK;
     CK(cudaSetDevice(h->device));
     const int grid = B < 8 * h->num_sms ? B : 8 * h->num_sms;
-    tg_ref_window_kernel<<<grid, 64, (size_t)h->Lref.total * sizeof(double), h->stream>>>(h->dc, h->Lref, B, x0, spec, brk, coef, t_index, path_ref, vref);
+    tg_ref_window_kernel<<<grid, 32, (size_t)h->Lref.total * sizeof(double), h->stream>>>(h->dc, h->Lref, B, x0, spec, brk, coef, t_index, path_ref, vref);
     h->launches += 1;
     CK(cudaGetLastError());
     return TG_OK;
@@ -1119,31 +743,10 @@ int tg_closed_loop(tg_handle *h, int B, int T, const double *x0, const double *u
     memset(&a, 0, sizeof(a));
     a.B = B; a.T = T; a.x0 = x0; a.u0 = u0; a.spec = spec; a.brk = brk; a.coef = coef; a.traj_id0 = traj_id0;
     a.clean = clean; a.noisy = noisy; a.U = U; a.status_counts = status_counts; a.iters_total = (long long *)iters_total;
-    if (h->use_tw)
-        return dispatch_tw(h->W, h->S, h->dc.N, [&](auto W_, auto S_, auto NC_) -> int {
-            constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
-            return launch_tw(h, tw_closed_loop_kernel<W, S, NC>, a, B, W);
-        });
-    a.Hws = h->Hws;
-    const int ppc = choose_ppc(h, B);
-    a.ppc = ppc;
-    const size_t loop_smem = ppc > 1 ? (size_t)ppc * (((size_t)h->L.total + 1) & ~(size_t)1) * sizeof(double) : h->smem_bytes;
-    int per_sm = 0;
-    int rc = dispatch_loop(h->shape, ppc > 1, [&](auto kern) -> int {
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, h->shape.NT * ppc, loop_smem));
-        if (per_sm < 1) return fail(TG_ERR_UNSUPPORTED, "closed-loop kernel does not fit on an SM with this configuration");
-        // full CTAs (every slot busy) measure faster than an even spread with partly filled ones: 1024 trajectories as
-        // 256 CTAs of 4 run at 1.55e7 steps/s, as 296 CTAs of 4 or 3 (7 per SM everywhere) at 1.20e7
-        const int cap = per_sm * h->num_sms, ctas = (B + ppc - 1) / ppc;
-        int grid = ctas < cap ? ctas : cap;
-        if (const char *e = getenv("TRAJGEN_GRID")) { const int v = atoi(e); if (v >= 1 && v <= cap) grid = v; }   // measurement knob
-        kern<<<grid, h->shape.NT * ppc, loop_smem, h->stream>>>(h->dc, h->L, a);
-        return TG_OK;
+    return dispatch_tw(h->W, h->S, h->dc.N, [&](auto W_, auto S_, auto NC_) -> int {
+        constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
+        return launch_tw(h, tw_closed_loop_kernel<W, S, NC>, a, B, W);
     });
-    if (rc != TG_OK) return rc;
-    h->launches += 1;
-    CK(cudaGetLastError());
-    return TG_OK;
 }
 
 int tg_plant_rollout(tg_handle *h, int B, int T, const double *x0, const double *U, double *X)
@@ -1379,6 +982,12 @@ int tg_fma_peak(tg_handle *h, int dtype, double *tflops)
 }
 
 int tg_malloc(void **p, int64_t bytes) { if (!p || bytes < 0) return fail(TG_ERR_INVALID, "bad argument"); *p = nullptr; if (bytes == 0) return TG_OK; CK(cudaMalloc(p, (size_t)bytes)); return TG_OK; }
+int tg_malloc_on(tg_handle *h, void **p, int64_t bytes)
+{
+    if (!h) return fail(TG_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->device));
+    return tg_malloc(p, bytes);
+}
 int tg_free(void *p) { if (p) CK(cudaFree(p)); return TG_OK; }
 int tg_malloc_host(void **p, int64_t bytes) { if (!p || bytes < 0) return fail(TG_ERR_INVALID, "bad argument"); *p = nullptr; if (bytes == 0) return TG_OK; CK(cudaMallocHost(p, (size_t)bytes)); return TG_OK; }
 int tg_free_host(void *p) { if (p) CK(cudaFreeHost(p)); return TG_OK; }
@@ -1386,6 +995,7 @@ int tg_memcpy_h2d(tg_handle *h, void *dst, const void *src, int64_t bytes)
 {
     if (!h || bytes < 0) return fail(TG_ERR_INVALID, "bad argument");
     if (bytes == 0) return TG_OK;
+    CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return TG_OK;
@@ -1394,6 +1004,7 @@ int tg_memcpy_d2h(tg_handle *h, void *dst, const void *src, int64_t bytes)
 {
     if (!h || bytes < 0) return fail(TG_ERR_INVALID, "bad argument");
     if (bytes == 0) return TG_OK;
+    CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return TG_OK;
@@ -1465,6 +1076,18 @@ int tg_closed_loop_host(tg_handle *h, int B, int T, const double *x0, const doub
 {
     if (!h || B < 0 || T < 0 || (B > 0 && (!x0 || !u0 || !spec || !clean || !noisy || (T > 0 && !U)))) return fail(TG_ERR_INVALID, "bad argument");
     if (B == 0) return TG_OK;
+    {   // the scenario table is host memory here: reject what would send the device out of bounds
+        const int64_t n_tab = (brk && coef) ? (n_breaks < n_coef ? n_breaks : n_coef) : 0;
+        for (int b = 0; b < B; ++b) {
+            const tg_ref_spec &sp = spec[b];
+            if (sp.path_kind < TG_PATH_PARABOLA || sp.path_kind > TG_PATH_ARC || sp.vref_kind < TG_VREF_HOLD || sp.vref_kind > TG_VREF_SINE)
+                return fail(TG_ERR_INVALID, "scenario " + std::to_string(b) + ": unknown path_kind / vref_kind");
+            if (sp.path_kind == TG_PATH_SPLINE || sp.path_kind == TG_PATH_ARC) {
+                if (sp.spline_count < 1 || sp.spline_first < 0 || (int64_t)sp.spline_first + sp.spline_count > n_tab)
+                    return fail(TG_ERR_INVALID, "scenario " + std::to_string(b) + ": spline pieces outside the break / coefficient tables");
+            }
+        }
+    }
     CK(cudaSetDevice(h->device));
     const size_t b8 = sizeof(double);
     const size_t s_x0 = (size_t)B * 6 * b8, s_u0 = (size_t)B * 2 * b8, s_sp = (size_t)B * sizeof(tg_ref_spec);

@@ -15,7 +15,45 @@
 // the block partials exchanged through shared memory.  The ADMM vectors live in shared memory, lane t owns stage t (the
 // entries 2t, 2t+1 of dU and its two box and two rate rows).
 #pragma once
-#include "tg_solver.cuh"   // StepTaps, FusedCtx, StepResult, misc slots, phase-timing macros (shared with the legacy CTA-per-problem body)
+#include "tg_device.cuh"
+
+// optional phase timing (development): -DTG_PHASE_TIMING accumulates clock64 deltas of CTA 0 / thread 0 per phase
+#ifdef TG_PHASE_TIMING
+__device__ long long g_tg_phase[16];
+#define TG_TICK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t__ = clock64(); g_tg_phase[i] += t__ - tg_last_tick; tg_last_tick = t__; } } while (0)
+#define TG_TICK_DECL long long tg_last_tick = clock64()
+#else
+#define TG_TICK(i) do { } while (0)
+#define TG_TICK_DECL do { } while (0)
+#endif
+
+// misc slots (doubles): 0 c0, 2 rho scale, 8..13 next state, 14..15 applied input, 16..19 counters (as 32/64-bit ints)
+enum { M_C0 = 0, M_RHOSCALE = 2, M_XNEXT = 8, M_UCMD = 14, M_CNT = 16 };
+
+struct StepTaps {   // optional debug/parity outputs of this problem (global memory, may be null)
+    double *A, *Bm, *g, *xbar;          // tg_linearize
+    double *H, *q, *c0, *l, *u, *Gs;    // tg_assemble
+    int stop;                           // 0 = full step, 1 = stop after linearisation, 2 = stop after assembly
+};
+
+struct FusedCtx {   // closed-loop extras handled inside the step body
+    const double *brk, *coef;   // spline tables (global)
+    double *noisy_row;          // where the noisy copy of the CURRENT state goes (global), or null
+    unsigned long long seed;
+    int t_index;
+};
+
+struct StepResult {
+    int status, iters;
+    double objective;
+    bool free_end;              // the solve ended with every dual at zero (no active row)
+};
+
+// barrier of a thread group of the CTA
+__device__ __forceinline__ void tg_sync(int bar, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads) : "memory");
+}
 
 #define TW_KB 4                  // horizon stages condensed per synchronisation in K2
 #define TW_WARM_RESTART_ITER 300

@@ -38,6 +38,7 @@ class _StepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, u, model):
         x, u = _cuda_contig(x, "x"), _cuda_contig(u, "u")
+        model._check_device(x, u)
         out = torch.empty_like(x)
         model._call("tg_estimator_step", x, x.shape[0], _dtype_code(x), x.data_ptr(), u.data_ptr(), model._limits(), out.data_ptr())
         ctx.save_for_backward(x, u)
@@ -84,6 +85,12 @@ class VehicleModel:
             lim.lo[i], lim.hi[i] = float(self.Params[a]), float(self.Params[b])
         return ctypes.byref(lim)
 
+    def _check_device(self, *tensors):
+        for t in tensors:
+            if t.device.index != self._device:
+                raise _lib.TrajgenError(f"tensor on cuda:{t.device.index}, but this VehicleModel is bound to cuda:{self._device} "
+                                        "(pass device= at construction)")
+
     def _call(self, name, like, *args):
         L, h = _lib.load(), self._handle()
         _lib.check(L.tg_set_stream(h, torch.cuda.current_stream(like.device).cuda_stream))
@@ -105,6 +112,9 @@ class VehicleModel:
         """x_t = f(x_{t-1}, u_t): [B,6,1], [B,2,1] -> [B,6,1]   (vehicle_model.py:109-134)"""
         x = torch.squeeze(x_batch_in, 2)
         u = torch.squeeze(u_batch_in, 2)
+        if u.dtype != x.dtype:                                # the reference's torch code type-promotes; the kernel takes one
+            dt = torch.promote_types(x.dtype, u.dtype)        # dtype (the cast stays in the autograd graph)
+            x, u = x.to(dt), u.to(dt)
         return torch.unsqueeze(_StepFn.apply(x, u, self), 2)
 
     def h(self, x_batch_in):
@@ -115,7 +125,8 @@ class VehicleModel:
     def rollout_open_loop(self, x0_real, u, t_start_state, H):
         """KalmanNet/test_prediction.py:68-87 (there a free function taking the model): x0[B,6,1], u[B,2,T] -> [B,6,Hn]."""
         x0 = _cuda_contig(torch.squeeze(x0_real, 2), "x0")
-        u = _cuda_contig(u, "u").to(x0.dtype)
+        u = _cuda_contig(u.to(x0.dtype), "u")
+        self._check_device(x0, u)
         B, T_u = x0.shape[0], u.shape[2]
         Hn = max(0, min(int(H), T_u - int(t_start_state)))
         if Hn == 0:

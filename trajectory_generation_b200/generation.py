@@ -150,7 +150,7 @@ class ClosedLoopGenerator(BatchedMPC):
         spec = np.ascontiguousarray(scenarios.spec)
         brk, coef = scenarios.tables()
         bufs = self._on_device([x0, spec.view(np.uint8), brk if len(brk) else None, coef if len(coef) else None])
-        op, ov = _lib.DeviceBuffer(B * (N + 1) * 3 * 8), _lib.DeviceBuffer(B * (N + 1) * 8)
+        op, ov = _lib.DeviceBuffer(B * (N + 1) * 3 * 8, self._h), _lib.DeviceBuffer(B * (N + 1) * 8, self._h)
         _lib.check(_lib.load().tg_ref_window(self._h, B, bufs[0].ptr, bufs[1].ptr, bufs[2].ptr if bufs[2] else None,
                                              bufs[3].ptr if bufs[3] else None, int(t_index), op.ptr, ov.ptr))
         return self._from_device(op, (B, N + 1, 3)), self._from_device(ov, (B, N + 1))
@@ -162,18 +162,18 @@ class ClosedLoopGenerator(BatchedMPC):
         U = np.ascontiguousarray(np.asarray(U, float))
         T = U.shape[1]
         bx, bu = self._on_device([x0, U])
-        oX = _lib.DeviceBuffer(B * (T + 1) * 6 * 8)
+        oX = _lib.DeviceBuffer(B * (T + 1) * 6 * 8, self._h)
         _lib.check(_lib.load().tg_plant_rollout(self._h, B, T, bx.ptr, bu.ptr, oX.ptr))
         return self._from_device(oX, (B, T + 1, 6))
 
     def sensor_noise_normals(self, traj_id0, n_traj, n_rows):
         """K4 tap: standard normals [n_traj, n_rows, 6] of seeds noise_seed_base + traj_id0 + i."""
-        o = _lib.DeviceBuffer(max(n_traj * n_rows * 6 * 8, 8))
+        o = _lib.DeviceBuffer(max(n_traj * n_rows * 6 * 8, 8), self._h)
         _lib.check(_lib.load().tg_sensor_noise(self._h, int(traj_id0), int(n_traj), int(n_rows), o.ptr))
         return self._from_device(o, (n_traj, n_rows, 6))
 
     def philox_u32(self, seed, first, block, n):
-        o = _lib.DeviceBuffer(max(n * 16, 16))
+        o = _lib.DeviceBuffer(max(n * 16, 16), self._h)
         _lib.check(_lib.load().tg_philox_u32(self._h, int(seed), int(first), int(block), int(n), o.ptr))
         return self._from_device(o, (n, 4), np.uint32)
 
@@ -247,9 +247,15 @@ def merge_datasets(first_clean, second_clean, out_clean, first_noisy=None, secon
 
 def to_loader_tensors(result, T_steps):
     """The arrays KalmanNet/data_loader.py:33-53 would build from the CSVs, without the CSV round trip:
-    y[B,5,T] noisy (X,Y,vx,vy,omega), u[B,2,T], x[B,6,T] clean; float32."""
+    y[B,5,T] noisy (X,Y,vx,vy,omega), u[B,2,T], x[B,6,T] clean; float32.  Like the loader (:51-53) it takes the first
+    T_steps rows of each trajectory's T+1 rows; the controls of the last row are NaN in the files, so asking for all
+    T+1 rows gives a NaN last column in u, exactly as the loader does."""
     clean, noisy, U = result["clean"], result["noisy"], result["U"]
+    T1 = clean.shape[1]
+    if T_steps > T1:
+        raise ValueError(f"T_steps = {T_steps} exceeds the {T1} rows per trajectory")
+    Upad = np.concatenate([U, np.full((U.shape[0], 1, 2), np.nan)], axis=1)
     y = noisy[:, :T_steps][:, :, [0, 1, 3, 4, 5]].transpose(0, 2, 1).astype(np.float32)
-    u = U[:, :T_steps].transpose(0, 2, 1).astype(np.float32)
+    u = Upad[:, :T_steps].transpose(0, 2, 1).astype(np.float32)
     x = clean[:, :T_steps].transpose(0, 2, 1).astype(np.float32)
     return y, u, x

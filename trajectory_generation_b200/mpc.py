@@ -130,7 +130,7 @@ class BatchedMPC:
             if a is None:
                 bufs.append(None)
                 continue
-            b = _lib.DeviceBuffer(max(a.nbytes, 8))
+            b = _lib.DeviceBuffer(max(a.nbytes, 8), self._h)
             _lib.check(L.tg_memcpy_h2d(self._h, b.ptr, _lib.ptr(a), a.nbytes))
             bufs.append(b)
         return bufs
@@ -148,8 +148,8 @@ class BatchedMPC:
         if B == 0:
             return np.zeros((0, N, 6, 6)), np.zeros((0, N, 6, 2)), np.zeros((0, N, 6)), np.zeros((0, N + 1, 6))
         bx, bu = self._on_device([x0, u_prev])
-        oA, oB, og, ox = (_lib.DeviceBuffer(B * N * 36 * 8), _lib.DeviceBuffer(B * N * 12 * 8),
-                          _lib.DeviceBuffer(B * N * 6 * 8), _lib.DeviceBuffer(B * (N + 1) * 6 * 8))
+        oA, oB, og, ox = (_lib.DeviceBuffer(B * N * 36 * 8, self._h), _lib.DeviceBuffer(B * N * 12 * 8, self._h),
+                          _lib.DeviceBuffer(B * N * 6 * 8, self._h), _lib.DeviceBuffer(B * (N + 1) * 6 * 8, self._h))
         _lib.check(_lib.load().tg_linearize(self._h, B, bx.ptr, bu.ptr, oA.ptr, oB.ptr, og.ptr, ox.ptr))
         return (self._from_device(oA, (B, N, 6, 6)), self._from_device(oB, (B, N, 6, 2)),
                 self._from_device(og, (B, N, 6)), self._from_device(ox, (B, N + 1, 6)))
@@ -162,9 +162,9 @@ class BatchedMPC:
         path_ref = self._arr(path_ref, (B, N + 1, 3))
         vref = None if vref is None else self._arr(vref, (B, N + 1))
         bx, bu, bp, bv = self._on_device([x0, u_prev, path_ref, vref])
-        oH, oq, oc, ol, ou = (_lib.DeviceBuffer(B * n * n * 8), _lib.DeviceBuffer(B * n * 8), _lib.DeviceBuffer(B * 8),
-                              _lib.DeviceBuffer(B * m * 8), _lib.DeviceBuffer(B * m * 8))
-        oG = _lib.DeviceBuffer(max(B * ms * n * 8, 8))
+        oH, oq, oc, ol, ou = (_lib.DeviceBuffer(B * n * n * 8, self._h), _lib.DeviceBuffer(B * n * 8, self._h), _lib.DeviceBuffer(B * 8, self._h),
+                              _lib.DeviceBuffer(B * m * 8, self._h), _lib.DeviceBuffer(B * m * 8, self._h))
+        oG = _lib.DeviceBuffer(max(B * ms * n * 8, 8), self._h)
         _lib.check(_lib.load().tg_assemble(self._h, B, bx.ptr, bu.ptr, bp.ptr, bv.ptr if bv else None,
                                            oH.ptr, oq.ptr, oc.ptr, ol.ptr, ou.ptr, oG.ptr if ms else None))
         return {"H": self._from_device(oH, (B, n, n)), "q": self._from_device(oq, (B, n)),
