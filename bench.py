@@ -6,8 +6,9 @@
 One "step" = one pass of the hot path over one batch: BASELINE config 2 -- B = 1024 trajectories per GPU,
 spline / sinusoidal references, N = 20, Ts = 0.01, T = 1200 closed-loop MPC steps each (1.23 M MPC steps),
 run by ONE launch of the fused closed-loop kernel.  `value` is timed with CUDA events on the kernel's
-stream with inputs resident in HBM; `e2e` goes through the public host-buffer API (pinned host memory,
-H2D + D2H inside the timed region).  For N > 1 the driver launches this file under torchrun: each rank
+stream with inputs resident in HBM; `e2e` goes through the public Python API with host arrays
+(ClosedLoopGenerator.generate: inputs copied host -> device inside the call, result rows stored into page-locked
+host arrays while the kernel runs).  For N > 1 the driver launches this file under torchrun: each rank
 owns its own block of trajectory ids (weak scaling, no collective on the solve path), time = max over
 ranks.  `--impl reference` times the reference's algorithm on the host cores (oracle/ port of
 MPC/main.py's loop with the restated OSQP; cvxpy/osqp are not installable offline).
@@ -164,60 +165,88 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def _cpu_traj(args):
-    """MPC/main.py:85-101 for one trajectory of the workload: oracle port, cold-started restated OSQP each step."""
-    b, n_steps, x0, u0, spec, brk, coef = args
+CPU_CHUNK_STEPS = 40                    # closed-loop steps per chunk
+CPU_CHUNK_STARTS = (0, 300, 600, 900)   # chunks start at these steps of a trajectory: transient, mid-run and late cruise
+# (16 cores x 4 chunks x 40 steps = 2560 MPC steps, about 25 core-seconds)
+
+
+def _cpu_chunk(args):
+    """MPC/main.py:85-101 for CPU_CHUNK_STEPS steps of one trajectory of the workload, started from the oracle's own state at
+    step t0 (tests/golden/oracle_bench_config.npz): oracle port, cold-started restated OSQP each step (the reference builds a
+    fresh cp.Problem per call, so its warm_start=True never takes effect)."""
+    b, t0, n_steps, x, u_prev, spec, brk, coef = args
     from oracle import dynamics as dyn, mpc as ompc, refgen as R
     kind = int(spec["path_kind"])
     spline = None
     if kind == R.PATH_SPLINE:
         f, K = int(spec["spline_first"]), int(spec["spline_count"])
         spline = (np.append(brk[f:f + K], np.inf), coef[f:f + K])
-    t0 = time.perf_counter()
-    X, U, st, its = ompc.closed_loop(x0, u0, n_steps, TS, N_HORIZON, path_kind=kind, path_prm=tuple(spec["path"]), spline=spline,
-                                     vref_kind=int(spec["vref_kind"]), vref_prm=tuple(spec["vref"]), vref_advance=True,
-                                     plant=dyn.PLANT_GEN1, solver="osqp")
-    return time.perf_counter() - t0, int(np.sum(its)), sum(s == "optimal" for s in st)
+    tt = time.perf_counter()
+    its, nopt = 0, 0
+    x = np.array(x, float); u_prev = np.array(u_prev, float)
+    for t in range(t0, t0 + n_steps):
+        vref_seq = R.vref_profile(int(spec["vref_kind"]), tuple(spec["vref"]), N_HORIZON, TS, t * TS, x[3])
+        path_ref = R.ref_window(x[0], N_HORIZON, TS, vref_seq, kind, tuple(spec["path"]), spline)
+        u_cmd, status, info = ompc.mpc_step(x, u_prev, path_ref, Ts=TS, N=N_HORIZON, vref=vref_seq, solver="osqp")
+        x = dyn.plant_step(x, u_cmd, TS, plant=dyn.PLANT_GEN1)
+        u_prev = u_cmd
+        its += info.get("iters", 0) if info else 0
+        nopt += status == "optimal"
+    return time.perf_counter() - tt, its, nopt
 
 
-def cpu_baseline(n_traj, n_steps, cores):
-    """-> (MPC steps/s over all cores, description).  Every worker runs whole trajectories of the bench workload."""
+def cpu_baseline(cores, chunks_per_core=len(CPU_CHUNK_STARTS)):
+    """-> (MPC steps/s over all cores, description).  The sample: `cores` trajectories of the bench workload x the chunk
+    starts above x CPU_CHUNK_STEPS steps, each chunk started from the oracle's state at that step."""
     import multiprocessing as mp
-    x0, u0, sc = make_workload(n_traj)
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "oracle_bench_config.npz"))
+    n_g = int(golden["n_traj"])
+    x0, u0, sc = make_workload(n_g)
     brk, coef = sc.tables()
-    jobs = [(b, n_steps, x0[b], u0[b], sc.spec[b], brk, coef) for b in range(n_traj)]
+    X, U = golden["X_ipm"], golden["U_ipm"]
+    jobs = []
+    for c in range(cores):
+        b = c % n_g
+        for t0 in CPU_CHUNK_STARTS[:chunks_per_core]:
+            up = u0[b] if t0 == 0 else U[b, t0 - 1]
+            jobs.append((b, t0, CPU_CHUNK_STEPS, X[b, t0], up, sc.spec[b], brk, coef))
     if cores > 1:
         with mp.get_context("spawn").Pool(cores) as pool:     # spawn: the parent may hold a CUDA context
-            pool.map(_cpu_traj, [(j[0], 1) + j[2:] for j in jobs[:cores]])   # start-up + imports are not the workload
+            pool.map(_cpu_chunk, [(j[0], j[1], 1) + j[3:] for j in jobs[:cores]])   # start-up + imports are not the workload
             t0 = time.perf_counter()
-            res = pool.map(_cpu_traj, jobs)
+            res = pool.map(_cpu_chunk, jobs, chunksize=1)
     else:
         t0 = time.perf_counter()
-        res = [_cpu_traj(j) for j in jobs]
+        res = [_cpu_chunk(j) for j in jobs]
     wall = time.perf_counter() - t0
-    steps = n_traj * n_steps
+    steps = len(jobs) * CPU_CHUNK_STEPS
+    sample = (f"{len(jobs)} chunks of {CPU_CHUNK_STEPS} closed-loop steps ({cores} trajectories of the config-2 workload, chunks "
+              f"starting at steps {list(CPU_CHUNK_STARTS[:chunks_per_core])} from the oracle's state), one process per core")
     return steps / wall, {"wall_s": wall, "mean_osqp_iters": sum(r[1] for r in res) / steps,
-                          "optimal_frac": sum(r[2] for r in res) / steps}
+                          "optimal_frac": sum(r[2] for r in res) / steps, "sample": sample, "mpc_steps_in_sample": steps}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_traj, n_steps = cores, 60
-    vals = []
+    vals, info = [], {}
     for it in range(args.warmup + args.steps):
-        v, info = cpu_baseline(n_traj, n_steps, cores)
+        v, info = cpu_baseline(cores)
         if it >= args.warmup:
             vals.append(v)
     value = float(np.mean(vals))
-    sample = f"{n_traj} trajectories x {n_steps} closed-loop steps of the config-2 workload per step, one process per core"
+    sample = info.pop("sample")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "MPC steps/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * n_traj * n_steps / value, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * info["mpc_steps_in_sample"] / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2 (generation_type1-style spline/sinusoidal references), N=20, Ts=0.01",
-                       "note": "oracle/ port of MPC/main.py's loop (reference linearisation + restated CVXPY problem + restated OSQP, "
-                               "cold start per step); cvxpy/osqp are not installed and cannot be installed offline"},
+            "config": {"workload": "BASELINE config 2: generation_type1-style spline/sinusoidal references, closed loop",
+                       "horizon_N": N_HORIZON, "Ts": TS, "plant": "generation_type1 (clipped)", "sample": sample,
+                       "note": "CPU port of MPC/main.py's loop under oracle/ (the oracle's restatement of the reference's "
+                               "finite-difference linearisation in plain math.* calls -- faster than the reference's own NumPy "
+                               "code --, the restated CVXPY problem and the restated OSQP algorithm, cold start per step); "
+                               "cvxpy / osqp are not installed and cannot be installed offline, so this stands in for the "
+                               "reference's CVXPY -> OSQP call and is optimistic for it"},
             "cpu_baseline": {"value": value, "unit": "MPC steps/s", "cores": cores, "kind": "port", "sample": sample, **info},
             "e2e": {"value": value, "unit": "MPC steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -262,7 +291,6 @@ def measure_widened_rows(stream, hbm_peak):
 
 
 def run_gpu(args, rank, world, local_rank):
-    import ctypes
     import torch
     import trajectory_generation_b200 as tg
     from trajectory_generation_b200 import _lib
@@ -348,23 +376,14 @@ def run_gpu(args, rank, world, local_rank):
     value = world * steps_per_launch * args.steps / (total_ms_max * 1e-3)
     mean_iters = iters_total / (world * steps_per_launch)
 
-    # ---- e2e: public host API, pinned buffers, H2D + D2H inside the timed region
-    hx0, hu0 = torch.from_numpy(x0).pin_memory(), torch.from_numpy(u0).pin_memory()
-    spec_h = torch.from_numpy(np.ascontiguousarray(sc.spec).view(np.uint8)).pin_memory()
-    out = {"clean": torch.empty((B, T + 1, 6), dtype=torch.float64).pin_memory(), "noisy": torch.empty((B, T + 1, 6), dtype=torch.float64).pin_memory(),
-           "U": torch.empty((B, T, 2), dtype=torch.float64).pin_memory(), "sc": torch.zeros((B, 6), dtype=torch.int32).pin_memory(),
-           "it": torch.zeros(B, dtype=torch.int64).pin_memory()}
-
-    def e2e_call():
-        _lib.check(L.tg_closed_loop_host(gen.handle, B, T, hx0.data_ptr(), hu0.data_ptr(), spec_h.data_ptr(),
-                                         brk.ctypes.data if len(brk) else None, len(brk), coef.ctypes.data if len(coef) else None, len(coef),
-                                         traj_id0, out["clean"].data_ptr(), out["noisy"].data_ptr(), out["U"].data_ptr(),
-                                         out["sc"].data_ptr(), out["it"].data_ptr()))
-    e2e_call()
+    # ---- e2e: the public Python API (ClosedLoopGenerator.generate -> tg_closed_loop_host) with HOST buffers: inputs are
+    # copied host -> device inside the call, the result rows land in page-locked host arrays while the kernel runs
+    out = gen.alloc_result(B, T, pinned=True)
+    gen.generate(x0, u0, sc, T, traj_id0, out=out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e2e_call()
+        gen.generate(x0, u0, sc, T, traj_id0, out=out)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -373,29 +392,39 @@ def run_gpu(args, rank, world, local_rank):
     e2e_value = world * steps_per_launch * args.steps / float(te.item())
     h2d = x0.nbytes + u0.nbytes + sc.spec.nbytes + brk.nbytes + coef.nbytes
     d2h = 2 * B * (T + 1) * 6 * 8 + B * T * 2 * 8 + B * 6 * 4 + B * 8
-    e2e_ok = bool(np.array_equal(out["clean"].numpy(), d_clean.cpu().numpy()))
+    e2e_ok = bool(np.array_equal(out["clean"], d_clean.cpu().numpy()))
+    gpu_launches += args.steps + 1
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- p50 latency of one batched mpc_step call (device-resident, B problems)
-    lat = None
+    # ---- p50 latency of one batched mpc_step call (device-resident, B problems, cold start): on the initial states of the
+    # workload (large offsets: most problems have active rows) and on its states at mid-run (t = T/2: the typical case)
+    lat, lat_mid = None, None
     if rank == 0:
-        pr, vr = gen.ref_window(x0, sc)
         ctl = tg.BatchedMPC(device=local_rank, N=N, Ts=TS)
         ctl.set_stream(stream.cuda_stream)
-        d_pr, d_vr, d_uc = dev_t(pr), dev_t(vr), torch.empty((B, 2), dtype=torch.float64, device=dev)
-        d_st, d_its = torch.zeros(B, dtype=torch.int32, device=dev), torch.zeros(B, dtype=torch.int32, device=dev)
-        ev = []
-        with torch.cuda.stream(stream):
-            for i in range(110):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-                _lib.check(L.tg_mpc_step(ctl.handle, B, d_x0.data_ptr(), d_u0.data_ptr(), d_pr.data_ptr(), d_vr.data_ptr(), d_uc.data_ptr(),
-                                         d_st.data_ptr(), d_its.data_ptr(), None, None, None, None))
-                b.record(stream)
-                ev.append((a, b))
-        torch.cuda.synchronize(dev)
-        lat = float(np.median([a.elapsed_time(b) for a, b in ev[10:]]))
-        gpu_launches += 110
+
+        def p50(x_np, up_np, t_index):
+            nonlocal gpu_launches
+            pr, vr = gen.ref_window(x_np, sc, t_index=t_index)
+            d_x, d_up, d_pr, d_vr = dev_t(x_np), dev_t(up_np), dev_t(pr), dev_t(vr)
+            d_uc = torch.empty((B, 2), dtype=torch.float64, device=dev)
+            d_st, d_its = torch.zeros(B, dtype=torch.int32, device=dev), torch.zeros(B, dtype=torch.int32, device=dev)
+            ev = []
+            with torch.cuda.stream(stream):
+                for i in range(110):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    _lib.check(L.tg_mpc_step(ctl.handle, B, d_x.data_ptr(), d_up.data_ptr(), d_pr.data_ptr(), d_vr.data_ptr(), d_uc.data_ptr(),
+                                             d_st.data_ptr(), d_its.data_ptr(), None, None, None, None))
+                    b.record(stream)
+                    ev.append((a, b))
+            torch.cuda.synchronize(dev)
+            gpu_launches += 111
+            return float(np.median([a.elapsed_time(b) for a, b in ev[10:]])), float(d_its.double().mean().item())
+        lat = p50(x0, u0, 0)
+        tm_ = T // 2
+        if tm_ >= 1:
+            lat_mid = p50(out["clean"][:, tm_].copy(), out["U"][:, tm_ - 1].copy(), tm_)
 
     if rank == 0:
         peaks = {}
@@ -409,11 +438,13 @@ def run_gpu(args, rank, world, local_rank):
         kms = float(np.mean(kern_ms))
         alg_bytes = steps_per_launch * 14 * 8 + B * (6 + 2) * 8 + B * 14 * 8      # 14 fp64 words out per MPC step + x0/u0 in + row 0
         flops = steps_per_launch * algorithmic_flops_per_step(N, mean_iters, gen.cfg.check_every)
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_closed_loop_traffic.json"))).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        parity = None
+        if not args.no_parity:
+            try:
+                parity = parity_vs_golden(device=local_rank)      # outside the timed region
+                gpu_launches += 1
+            except Exception as e:
+                parity = {"error": repr(e)}
         widened = None
         if not args.no_extra:
             try:
@@ -422,8 +453,8 @@ def run_gpu(args, rank, world, local_rank):
             except Exception as e:          # never let a side measurement take the headline line down
                 widened = {"error": repr(e)}
         cores = os.cpu_count() or 1
-        cb_traj, cb_steps = cores, 60
-        cb_val, cb_info = (0.0, {"skipped": True}) if args.no_cpu else cpu_baseline(cb_traj, cb_steps, cores)
+        cb_val, cb_info = (0.0, {"skipped": True, "sample": "skipped"}) if args.no_cpu else cpu_baseline(cores)
+        cb_sample = cb_info.pop("sample")
         line = {
             "metric": METRIC, "value": value, "unit": "MPC steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -432,23 +463,36 @@ def run_gpu(args, rank, world, local_rank):
                        "batch_per_gpu": B, "global_batch": world * B, "horizon_N": N, "Ts": TS, "closed_loop_steps_T": T,
                        "mpc_steps_per_bench_step": world * steps_per_launch, "plant": "generation_type1 (clipped)", "jacobian": "analytic",
                        "solver": {"eps_abs": gen.cfg.eps_abs, "eps_rel": gen.cfg.eps_rel, "rho": gen.cfg.rho, "alpha": gen.cfg.alpha,
-                                  "check_every": gen.cfg.check_every, "warm_start": bool(gen.cfg.warm_start)},
+                                  "check_every": gen.cfg.check_every, "warm_start": bool(gen.cfg.warm_start),
+                                  "free_mode": not (gen.cfg.solver_flags & 1)},
                        "parallelism": f"trajectory-parallel x{world}, no collective on the solve path",
                        "l2": "256 MB buffer zeroed before every timed launch; outputs (138 MB) exceed the 126 MB L2"},
             "mean_admm_iters_per_step": mean_iters, "status_counts": {k: int(v) for k, v in zip(tg.STATUS_STRINGS, status)},
-            "p50_step_latency_ms": lat, "p50_step_latency_note": f"one tg_mpc_step call over {B} problems, cold start, device-resident, CUDA events",
+            "p50_step_latency_ms": lat[0] if lat else None,
+            "p50_step_latency_note": f"one tg_mpc_step call over {B} problems, cold start, device-resident, CUDA events; the workload's initial "
+                                     f"states (mean {lat[1] if lat else 0:.1f} ADMM iterations: most have active rows)",
+            "p50_step_latency_ms_midrun": lat_mid[0] if lat_mid else None,
+            "p50_step_latency_midrun_note": f"same call on the closed loop's states at step {T // 2} (mean {lat_mid[1] if lat_mid else 0:.1f} iterations)",
             "e2e": {"value": e2e_value, "unit": "MPC steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "tg_closed_loop_host (pinned host buffers)", "matches_resident_run": e2e_ok},
+                    "api": "ClosedLoopGenerator.generate (host arrays in, page-locked result arrays out; tg_closed_loop_host)",
+                    "matches_resident_run": e2e_ok},
             "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "tg_closed_loop_kernel", "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "the path is neither HBM- nor tensor-bound (SURVEY.md 8(d)): 112 B leave the SM per MPC step; see roofline_flop"},
-            "roofline_flop": {"bound": "fp64 CUDA-core FMA", "achieved": flops / (kms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                              "frac": flops / (kms * 1e-3) / 1e12 / fp64_peak, "peak_source": "tg_fma_peak micro-benchmark in this run",
-                              "algorithmic_flops_per_mpc_step": flops / steps_per_launch},
-            "cpu_baseline": {"value": cb_val, "unit": "MPC steps/s", "cores": cores, "kind": "port",
-                             "sample": f"{cb_traj} trajectories x {cb_steps} closed-loop steps of the same workload, one process per core", **cb_info},
+            "parity": parity,
+            # the binding roofline of this path is the fp64 CUDA-core FMA rate (neither HBM nor tensor cores;
+            # the only dense contraction is a 40 x 40 SPD inversion per problem); algorithmic flops per MPC step by the
+            # SURVEY's convention at the measured mean iteration count.  HBM is reported beside it.
+            "roofline": {"bound": "fp64 CUDA-core FMA (tensor cores are not applicable: fp64, 40x40 per problem)",
+                         "achieved": flops / (kms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": flops / (kms * 1e-3) / 1e12 / fp64_peak,
+                         "peak_source": "tg_fma_peak micro-benchmark in this run (MEASURED_PEAKS.json has no fp64 entry; nominal 37)",
+                         "traffic": None, "traffic_note": "DRAM bytes are an ncu metric: profiles/r02_closed_loop_ncu.txt",
+                         "kernel": "tw_closed_loop_kernel<2,1,20>", "kernel_ms": kms,
+                         "algorithmic_flops_per_mpc_step": flops / steps_per_launch},
+            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg_bytes,
+                             "note": "112 B leave the SM per MPC step: not the bound"},
+            "cpu_baseline": {"value": cb_val, "unit": "MPC steps/s", "cores": cores, "kind": "port", "sample": cb_sample, **cb_info},
             "clocks": clocks,
             "widened_rows": widened,
         }
@@ -469,6 +513,7 @@ def main():
     ap.add_argument("--check-every", type=int, default=0, help="override the ADMM termination-check interval (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (development runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the side measurements of the widened rows (open-loop generators)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity sample against the golden oracle loops (development runs)")
     ap.add_argument("--solver-opt", action="append", default=[], help="development: key=value override of a tg_config solver field")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

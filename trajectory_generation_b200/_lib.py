@@ -177,6 +177,22 @@ def ptr(a):
     return a.ctypes.data
 
 
+def pinned_empty(shape, dtype=np.float64):
+    """A page-locked (cudaMallocHost) NumPy array, freed when the array (and every view of it) is garbage-collected.
+    The closed-loop kernel stores its rows straight into such buffers (no device-to-host copy after the kernel)."""
+    import weakref
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if nbytes == 0:
+        return np.empty(shape, dtype)
+    p = vp()
+    check(load().tg_malloc_host(ctypes.byref(p), nbytes))
+    buf = (ctypes.c_char * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    weakref.finalize(buf, load().tg_free_host, p.value)     # arr.base keeps buf alive
+    return arr
+
+
 class DeviceBuffer:
     """A cudaMalloc'ed block owned by Python (used by tests / bench to keep data resident in HBM)."""
 

@@ -124,9 +124,20 @@ class ClosedLoopGenerator(BatchedMPC):
     def __init__(self, device=0, warm_start=True, **kwargs):
         super().__init__(device=device, warm_start=warm_start, **kwargs)
 
-    def generate(self, x0, u0, scenarios, T, traj_id0=0):
+    @staticmethod
+    def alloc_result(B, T, pinned=True):
+        """result buffers of one generate() call: dict(clean[B,T+1,6], noisy[B,T+1,6], U[B,T,2], status_counts[B,6],
+        iters_total[B]).  pinned=True: page-locked memory, into which the kernel stores its rows directly."""
+        mk = _lib.pinned_empty if pinned else np.empty
+        return {"clean": mk((B, T + 1, 6)), "noisy": mk((B, T + 1, 6)), "U": mk((B, T, 2)),
+                "status_counts": np.zeros((B, _lib.TG_NUM_STATUS), np.int32), "iters_total": np.zeros(B, np.int64)}
+
+    def generate(self, x0, u0, scenarios, T, traj_id0=0, out=None, pinned=True):
         """x0[B,6], u0[B,2], scenarios (len B), T steps -> dict(clean[B,T+1,6], noisy[B,T+1,6], U[B,T,2],
-        status_counts[B,6], iters_total[B]).  Row 0 of clean is x0; noise seed = base + traj_id0 + i."""
+        status_counts[B,6], iters_total[B]).  Row 0 of clean is x0; noise seed = base + traj_id0 + i.
+        The result arrays are page-locked by default (``pinned``), so the kernel writes its rows straight into them
+        while it runs (112 B per MPC step: far below what PCIe carries) and nothing is copied afterwards; ``out`` re-uses
+        the buffers of an earlier call (see ``alloc_result``)."""
         x0 = np.ascontiguousarray(np.asarray(x0, float).reshape(-1, 6))
         B = x0.shape[0]
         u0 = self._arr(np.asarray(u0, float).reshape(-1, 2), (B, 2))
@@ -134,13 +145,59 @@ class ClosedLoopGenerator(BatchedMPC):
             raise ValueError("one scenario per trajectory required")
         spec = np.ascontiguousarray(scenarios.spec)
         brk, coef = scenarios.tables()
-        out = {"clean": np.empty((B, T + 1, 6)), "noisy": np.empty((B, T + 1, 6)), "U": np.empty((B, T, 2)),
-               "status_counts": np.zeros((B, _lib.TG_NUM_STATUS), np.int32), "iters_total": np.zeros(B, np.int64)}
+        if out is None:
+            out = self.alloc_result(B, int(T), pinned)
+        elif out["clean"].shape != (B, T + 1, 6) or out["U"].shape != (B, T, 2):
+            raise ValueError("`out` was allocated for another batch size / horizon")
         _lib.check(_lib.load().tg_closed_loop_host(
             self._h, B, int(T), _lib.ptr(x0), _lib.ptr(u0), spec.ctypes.data, _lib.ptr(brk) if len(brk) else None,
             len(brk), _lib.ptr(coef) if len(coef) else None, len(coef), int(traj_id0),
             _lib.ptr(out["clean"]), _lib.ptr(out["noisy"]), _lib.ptr(out["U"]), _lib.ptr(out["status_counts"]),
             _lib.ptr(out["iters_total"])))
+        return out
+
+    def generate_to_csv(self, x0, u0, scenarios, T, clean_path, noisy_path, traj_id0=0, chunk=8192, keep=False, n_threads=0):
+        """generate() in chunks of ``chunk`` trajectories with the dataset files written as it goes (the reference holds
+        every DataFrame in RAM and writes once at the end, generation_type2.py:166,216-218,319-322): while the GPU computes
+        chunk k + 1 into one set of pinned buffers, a host thread formats chunk k from the other (tg_write_csv, all cores,
+        appending).  Returns dict(status_counts[B,6], iters_total[B]) (+ the rows if ``keep``)."""
+        import threading
+        x0 = np.ascontiguousarray(np.asarray(x0, float).reshape(-1, 6))
+        u0 = np.ascontiguousarray(np.asarray(u0, float).reshape(-1, 2))
+        B, T = x0.shape[0], int(T)
+        bufs = [self.alloc_result(min(chunk, B), T) for _ in range(2 if B > chunk else 1)]
+        sc_all, it_all, kept = [], [], []
+        writer, err = None, []
+
+        def write(res, nb, first_id, append):
+            try:
+                write_csv({k: v[:nb] for k, v in res.items()}, self.cfg.Ts, clean_path, noisy_path, traj_id0=first_id, append=append,
+                          n_threads=n_threads)
+            except Exception as e:     # surfaced by the caller's thread below
+                err.append(e)
+
+        for k, lo in enumerate(range(0, B, chunk)):
+            hi = min(lo + chunk, B)
+            buf = bufs[k % len(bufs)]
+            res = buf if hi - lo == len(buf["clean"]) else self.alloc_result(hi - lo, T)
+            self.generate(x0[lo:hi], u0[lo:hi], scenarios.slice(lo, hi), T, traj_id0 + lo, out=res)
+            if writer is not None:
+                writer.join()                      # the previous chunk's buffers are free again after this
+            if err:
+                raise err[0]
+            sc_all.append(res["status_counts"].copy()); it_all.append(res["iters_total"].copy())
+            if keep:
+                kept.append({k_: res[k_].copy() for k_ in ("clean", "noisy", "U")})
+            writer = threading.Thread(target=write, args=(res, hi - lo, traj_id0 + lo, lo > 0))
+            writer.start()
+        if writer is not None:
+            writer.join()
+        if err:
+            raise err[0]
+        out = {"status_counts": np.concatenate(sc_all), "iters_total": np.concatenate(it_all)}
+        if keep:
+            for k_ in ("clean", "noisy", "U"):
+                out[k_] = np.concatenate([c[k_] for c in kept])
         return out
 
     def ref_window(self, x0, scenarios, t_index=0):
