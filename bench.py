@@ -30,52 +30,27 @@ N_HORIZON, TS = 20, 0.01
 METRIC = "closed-loop MPC steps/sec (batched QP solves/sec)"
 
 
-def make_workload(B, traj_id0=0, seed=2025):
-    """BASELINE config 2: per trajectory id i (seed 2025 + i): even ids a natural cubic
-    spline y(x) through 27 knots every U(1,3) m (from x = -6 m) with N(0, 0.3^2) m ordinates, odd ids y = A sin(kx + psi) with
-    A~U(0.2,1), k~U(0.3,1), psi~U(0,2pi); vref ramp-cruise 0.8 -> U(0.8,2.0) m/s over 2 s, advancing in time;
-    x0 from generation_type1.py:260-265's ranges with heading / lateral offset relative to the path."""
+def make_workload(gen, B, traj_id0=0):
+    """BASELINE config 2 for trajectory ids traj_id0 .. traj_id0 + B - 1, generated ON THE DEVICE
+    (tg_make_scenarios; oracle/scenarios.py restates it): even ids a natural cubic spline y(x) through 27 knots every
+    U(1,3) m from x = -6 m with N(0, 0.3^2) m ordinates, odd ids y = A sin(kx + psi) with A~U(0.2,1), k~U(0.3,1),
+    psi~U(0,2pi); vref ramp-cruise 0.8 -> U(0.8,2.0) m/s over 2 s, advancing in time; x0 from generation_type1.py:260-265's
+    ranges with heading / lateral offset (+-0.2) relative to the path; u0 = steady-state duty cycle.  Every number is a
+    function of 2025 + trajectory id.  -> (x0[B,6], u0[B,2], Scenarios)"""
+    return gen.make_scenarios(B, traj_id0=traj_id0)
+
+
+def workload_from_golden(golden):
+    """the first n_traj ids of the same workload as the oracle generated them (stored with the golden closed loops)"""
     import trajectory_generation_b200 as tg
-    sc = tg.Scenarios(B)
-    x0 = np.zeros((B, 6))
-    K = 27                                                   # knots per spline: -6 m ... >= 20 m at 1-3 m spacing
-    kxs, kys, sidx = [], [], []
-    ys, dys = np.zeros(B), np.zeros(B)
-    draws = np.zeros((B, 8))
-    for b in range(B):
-        i = traj_id0 + b
-        rng = np.random.default_rng(seed + i)
-        X = rng.uniform(-2.0, 2.0)
-        if i % 2 == 0:
-            kx = -6.0 + np.concatenate([[0.0], np.cumsum(rng.uniform(1.0, 3.0, K - 1))])
-            ky = rng.normal(0.0, 0.3, K)
-            kxs.append(kx); kys.append(ky); sidx.append(b)
-        else:
-            A, k, psi = rng.uniform(0.2, 1.0), rng.uniform(0.3, 1.0), rng.uniform(0.0, 2 * np.pi)
-            sc.set_sine(b, A, k, psi, 0.0)
-            ys[b], dys[b] = A * np.sin(k * X + psi), A * k * np.cos(k * X + psi)
-        sc.set_vref(b, tg.VREF_RAMP, 0.8, rng.uniform(0.8, 2.0), 2.0)
-        draws[b] = [X, rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2), rng.uniform(0.4, 1.5), rng.uniform(-0.05, 0.05),
-                    rng.uniform(-1.0, 1.0), 0.0, 0.0]
-    if sidx:                                                 # all splines in one batched fit
-        sidx = np.array(sidx); kxs = np.array(kxs); kys = np.array(kys)
-        coef = sc.set_splines(sidx, kxs, kys)
-        Xs = draws[sidx, 0]
-        piece = np.clip((kxs[:, :-1] <= Xs[:, None]).sum(1) - 1, 0, K - 2)
-        dx = Xs - kxs[np.arange(len(sidx)), piece]
-        c = coef[np.arange(len(sidx)), piece]
-        ys[sidx] = ((c[:, 0] * dx + c[:, 1]) * dx + c[:, 2]) * dx + c[:, 3]
-        dys[sidx] = (3.0 * c[:, 0] * dx + 2.0 * c[:, 1]) * dx + c[:, 2]
-    x0[:, 0] = draws[:, 0]; x0[:, 1] = ys + draws[:, 1]; x0[:, 2] = np.arctan(dys) + draws[:, 2]
-    x0[:, 3] = draws[:, 3]; x0[:, 4] = draws[:, 4]; x0[:, 5] = draws[:, 5]
-    u0 = np.stack([tg.d_steady_state(x0[:, 3]), np.zeros(B)], axis=1)
-    return x0, u0, sc
+    sc = tg.Scenarios.from_arrays(golden["path_kind"], golden["path"], golden["vref"], golden["breaks"], golden["coef"])
+    return np.ascontiguousarray(golden["x0"]), np.ascontiguousarray(golden["u0"]), sc
 
 
 GEN_KW = dict(N=N_HORIZON, Ts=TS, plant=1, vref_advance=True)   # plant 1 = generation_type1's clipped plant
 
 
-def parity_vs_golden(golden=None, gen_kw=None, device=0):
+def parity_vs_golden(golden=None, gen_kw=None, device=0, exclude_fd_jumps=True):
     """Parity of the benchmarked configuration, measured OUTSIDE the timed region: the first n_traj ids of make_workload
     run through the public generator API for the golden file's full T and compared with the oracle closed loops stored
     in tests/golden/oracle_bench_config.npz (exact per-step optimum, and the restated OSQP at eps 1e-5)."""
@@ -83,15 +58,17 @@ def parity_vs_golden(golden=None, gen_kw=None, device=0):
     if golden is None:
         golden = np.load(os.path.join(ROOT, "tests", "golden", "oracle_bench_config.npz"))
     n, T = int(golden["n_traj"]), int(golden["T"])
-    x0, u0, sc = make_workload(n)
-    assert np.array_equal(x0, golden["x0"]) and np.array_equal(u0, golden["u0"]), "workload generator changed: regenerate the golden file"
+    x0, u0, sc = workload_from_golden(golden)
     gen = tg.ClosedLoopGenerator(device=device, **(gen_kw or GEN_KW))
+    xg, ug, scg = make_workload(gen, n)                      # the device-made workload is the oracle-made one
+    same = (np.abs(xg - x0).max() <= 1e-13 and np.array_equal(ug, u0) and np.array_equal(scg.spec["path_kind"], sc.spec["path_kind"])
+            and np.abs(scg.tables()[1] - sc.tables()[1]).max() == 0.0)
     res = gen.generate(x0, u0, sc, T)
     gen.close()
     # Steps at which the reference's central differences straddle a JUMP of f_cont (golden["fd_jump"])
     # are not comparable: there the reference's Jacobian is the jump divided by 2 eps.  A trajectory is compared up to its
     # first such step; what follows it is reported separately (the loops re-converge within a few steps).
-    jump = golden["fd_jump"]
+    jump = golden["fd_jump"] if exclude_fd_jumps else np.zeros_like(golden["fd_jump"])
     first = np.where(jump.any(1), jump.argmax(1), T)                      # first artefact step per trajectory, T = none
     mU = np.arange(T)[None, :] < first[:, None]                             # U[t] comparable
     mX = np.arange(T + 1)[None, :] <= first[:, None]                        # X[t] comparable (X[first] is still pre-artefact)
@@ -107,6 +84,7 @@ def parity_vs_golden(golden=None, gen_kw=None, device=0):
             "compared_steps": int(mU.sum()), "fd_jump_trajectories": np.nonzero(jump.any(1))[0].tolist(),
             "max_abs_err_X_after_fd_jump": float(dX[~mX].max()) if (~mX).any() else 0.0,
             "max_abs_err_X_last_100_steps": float(dX[:, -100:].max()),
+            "workload_matches_oracle_generator": bool(same),
             "all_steps_accepted": bool(res["status_counts"][:, :2].sum() == n * T),
             "mean_admm_iters": float(res["iters_total"].sum() / (n * T))}
 
@@ -201,7 +179,7 @@ def cpu_baseline(cores, chunks_per_core=len(CPU_CHUNK_STARTS)):
     import multiprocessing as mp
     golden = np.load(os.path.join(ROOT, "tests", "golden", "oracle_bench_config.npz"))
     n_g = int(golden["n_traj"])
-    x0, u0, sc = make_workload(n_g)
+    x0, u0, sc = workload_from_golden(golden)
     brk, coef = sc.tables()
     X, U = golden["X_ipm"], golden["U_ipm"]
     jobs = []
@@ -303,8 +281,6 @@ def run_gpu(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     B, T, N = args.batch, args.horizon_steps, N_HORIZON
     traj_id0 = rank * B
-    x0, u0, sc = make_workload(B, traj_id0)
-    brk, coef = sc.tables()
     kw = dict(GEN_KW)
     so = {}
     if args.check_every:
@@ -315,6 +291,8 @@ def run_gpu(args, rank, world, local_rank):
     if so:
         kw["solver_opts"] = so
     gen = tg.ClosedLoopGenerator(device=local_rank, **kw)
+    x0, u0, sc = make_workload(gen, B, traj_id0)
+    brk, coef = sc.tables()
     stream = torch.cuda.Stream(device=dev)
     gen.set_stream(stream.cuda_stream)
     L = _lib.load()
@@ -442,7 +420,11 @@ def run_gpu(args, rank, world, local_rank):
         if not args.no_parity:
             try:
                 parity = parity_vs_golden(device=local_rank)      # outside the timed region
-                gpu_launches += 1
+                # the same runs with the reference's own central-difference Jacobians: every step comparable, none excluded
+                pfd = parity_vs_golden(device=local_rank, gen_kw=dict(GEN_KW, jacobian=tg.JAC_FD), exclude_fd_jumps=False)
+                parity["with_reference_fd_jacobians"] = {k: pfd[k] for k in ("max_abs_err_X", "max_abs_err_U", "compared_steps",
+                                                                               "all_steps_accepted", "mean_admm_iters")}
+                gpu_launches += 2
             except Exception as e:
                 parity = {"error": repr(e)}
         widened = None

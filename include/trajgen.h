@@ -166,6 +166,30 @@ int tg_closed_loop_host(tg_handle *h, int B, int T, const double *x0, const doub
                         int64_t traj_id0, double *clean, double *noisy, double *U, int32_t *status_counts,
                         int64_t *iters_total);
 
+/* ---- scenario + initial-state generation on the device: x0 from the ranges of
+ * generation_type1.py:260-265 / generation_type2.py:171-174 (Y and phi relative to the reference path), one reference path
+ * per trajectory (natural cubic spline through random knots / sinusoid / parabola, by id mod n_cycle), ramp-cruise speed
+ * profile.  Every number is a function of seed_base + global trajectory id (Philox4x32-10; layout in csrc/tg_scenarios.cuh,
+ * restated by oracle/scenarios.py).  spline tables: spl_knots - 1 pieces per trajectory, trajectory b at [b * (spl_knots - 1)]. */
+typedef struct tg_scenario_rules {
+    double x0_lo[6], x0_hi[6];   /* X, -, -, vx, vy, omega ranges (entries 1, 2 unused: Y, phi follow the path) */
+    double lat_off[2], head_off[2]; /* lateral / heading offset from the path at X */
+    double vref0, vcruise[2], t_ramp; /* vref ramps from vref0 to U(vcruise) over t_ramp seconds (MPC/main.py:28-32) */
+    double sine_A[2], sine_k[2], sine_psi[2]; /* y = A sin(k x + psi), MPC/README.md:75 has A = k = 0.5 */
+    double parab_c[2];           /* y = c x^2, MPC/main.py:64 has c = 0.1 */
+    double spl_x0, spl_dx[2], spl_sigma; /* knots from x = spl_x0 every U(spl_dx) m, ordinates N(0, spl_sigma^2) */
+    int32_t spl_knots;           /* 3 .. 32 */
+    int32_t n_cycle, cycle[4];   /* path kind of trajectory id i = cycle[i mod n_cycle] (TG_PATH_PARABOLA / SINE / SPLINE) */
+    int32_t reserved;
+    uint64_t seed_base;
+} tg_scenario_rules;
+void tg_default_scenario_rules(tg_scenario_rules *r); /* BASELINE config 2: spline / sinusoid by id parity, generation_type1's x0 ranges */
+/* DEVICE pointers: x0[B][6], u0[B][2] (steady-state duty cycle at vx, 0), spec[B], spl_breaks[B][spl_knots-1], spl_coef[B][spl_knots-1][4] */
+int tg_make_scenarios(tg_handle *h, int B, int64_t traj_id0, const tg_scenario_rules *rules, double *x0, double *u0,
+                      tg_ref_spec *spec, double *spl_breaks, double *spl_coef);
+int tg_make_scenarios_host(tg_handle *h, int B, int64_t traj_id0, const tg_scenario_rules *rules, double *x0, double *u0,
+                           tg_ref_spec *spec, double *spl_breaks, double *spl_coef);
+
 /* K4 taps -- plant + noise.  tg_plant_rollout: open-loop Euler integration with the configured plant
  * (generation_type1.py:70-84): x0[B][6], U[B][T][2] -> X[B][T+1][6].
  * tg_sensor_noise: standard normals [n_traj][n_rows][6] for seeds seed_base + traj_id0 + i (Philox4x32-10).

@@ -4,7 +4,7 @@ tests/golden/oracle_bench_config.npz.
 
     python tests/golden/make_bench_golden.py [n_traj=32] [T=1200]
 
-For trajectory ids 0..n_traj-1 of bench.make_workload (plant = generation_type1's clipped plant, spline / sinusoid
+For trajectory ids 0..n_traj-1 of the bench workload (oracle/scenarios.py = what bench.make_workload generates on the device; plant = generation_type1's clipped plant, spline / sinusoid
 references, time-advancing ramp vref, N = 20, Ts = 0.01) this runs the oracle's closed loop (MPC/main.py:85-101
 restated in oracle/mpc.py) twice:
 
@@ -55,13 +55,18 @@ def main():
     n_traj = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     T = int(sys.argv[2]) if len(sys.argv) > 2 else 1200
     import bench
-    x0, u0, sc = bench.make_workload(n_traj)
+    import trajectory_generation_b200 as tg
+    from oracle import scenarios as oscn
+    scn = oscn.make_scenarios(n_traj)                     # the workload bench.make_workload generates on the device
+    x0, u0 = scn["x0"], scn["u0"]
+    sc = tg.Scenarios.from_arrays(scn["path_kind"], scn["path"], scn["vref"], scn["breaks"], scn["coef"])
     brk, coef = sc.tables()
     jobs = [(b, T, x0[b], u0[b], sc.spec[b], brk, coef, s) for s in ("ipm", "osqp") for b in range(n_traj)]
     t0 = time.time()
     with mp.get_context("spawn").Pool(os.cpu_count()) as pool:
         res = pool.map(_one, jobs, chunksize=1)
-    out = {"x0": x0, "u0": u0, "n_traj": n_traj, "T": T}
+    out = {"x0": x0, "u0": u0, "n_traj": n_traj, "T": T, "path_kind": scn["path_kind"], "path": scn["path"], "vref": scn["vref"],
+           "breaks": scn["breaks"], "coef": scn["coef"]}
     for s in ("ipm", "osqp"):
         rs = sorted([r for r in res if r[1] == s], key=lambda r: r[0])
         out[f"X_{s}"] = np.stack([r[2] for r in rs])

@@ -204,3 +204,36 @@ def test_results_do_not_depend_on_problems_per_cta(monkeypatch):
     b = tg.BatchedMPC(N=20, Ts=0.01).step(x0, u0, pr, vr)
     for k in a:
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
+def test_device_scenario_generation_matches_oracle():
+    """tg_make_scenarios vs oracle/scenarios.py: Philox draws, knot tables, spline coefficients, vx / vy / omega, u0 and the
+    scenario table bit for bit; entries that pass through sin / cos / atan (Y, phi of x0) to rounding.  Shard invariance:
+    ids 40..47 generated alone equal rows 40..47 of the batch."""
+    from oracle import scenarios as oscn
+    gen = tg.ClosedLoopGenerator(N=20, Ts=0.01)
+    for kw, okw in (({}, {}),
+                    (dict(cycle=(tg.PATH_PARABOLA, tg.PATH_SINE, tg.PATH_SPLINE), seed_base=42, spl_knots=12, spl_sigma=0.5,
+                          x0_lo=(-1, 0, 0, 0.2, -0.05, -1), x0_hi=(1, 0, 0, 0.6, 0.05, 1)),
+                     dict(cycle=(R.PATH_PARABOLA, R.PATH_SINE, R.PATH_SPLINE), seed_base=42, spl_knots=12, spl_sigma=0.5,
+                          x0_lo=(-1, 0, 0, 0.2, -0.05, -1), x0_hi=(1, 0, 0, 0.6, 0.05, 1)))):
+        B = 96
+        x0, u0, sc = gen.make_scenarios(B, tg.scenario_rules(**kw))
+        o = oscn.make_scenarios(B, **okw)
+        P = o["breaks"].shape[1]
+        brk, coef = sc.tables()
+        assert np.array_equal(sc.spec["path_kind"], o["path_kind"]) and np.array_equal(sc.spec["vref"], o["vref"])
+        assert np.array_equal(brk.reshape(B, P), o["breaks"]) and np.array_equal(coef.reshape(B, P, 4), o["coef"])
+        assert np.array_equal(x0[:, [0, 3, 4, 5]], o["x0"][:, [0, 3, 4, 5]]) and np.array_equal(u0, o["u0"])
+        spl = o["path_kind"] == R.PATH_SPLINE
+        assert np.array_equal(x0[spl, 1], o["x0"][spl, 1])                       # spline ordinates: no libm involved
+        assert np.array_equal(sc.spec["path"][~spl], o["path"][~spl])
+        np.testing.assert_allclose(x0[:, 1:3], o["x0"][:, 1:3], rtol=0, atol=5e-16)
+        assert np.array_equal(sc.spec["spline_first"], np.arange(B) * P) and (sc.spec["spline_count"] == P).all()
+        x1, u1, sc1 = gen.make_scenarios(8, tg.scenario_rules(**kw), traj_id0=40)
+        assert np.array_equal(x1, x0[40:48]) and np.array_equal(u1, u0[40:48]) and np.array_equal(sc1.spec["path"], sc.spec["path"][40:48])
+        assert np.array_equal(sc1.tables()[1], coef.reshape(B, P, 4)[40:48].reshape(-1, 4))
+    # and the generated scenarios drive the closed loop like hand-built ones
+    x0, u0, sc = gen.make_scenarios(16)
+    res = tg.ClosedLoopGenerator(**{"N": 20, "Ts": 0.01, "plant": tg.PLANT_GEN1, "vref_advance": True}).generate(x0, u0, sc, 50)
+    assert res["status_counts"][:, :2].sum() == 16 * 50

@@ -158,3 +158,35 @@ def test_merge_datasets_matches_the_reference_script(tmp_path):
     open(p("lf.csv"), "wb").write(b"t,X,trajectory_id\n0.0,9.5,4\n")
     tg.merge_datasets(p("lf.csv"), p("crlf.csv"), p("m.csv"))
     assert open(p("m.csv")).read() == "t,X,trajectory_id\n0.0,9.5,4\n0.0,1.5,5\n0.01,2.5,6\n"
+
+
+def test_scenario_oracle_spline_is_scipys_natural_spline_and_ranges_hold():
+    """oracle/scenarios.py (what tg_make_scenarios must reproduce): the Thomas-algorithm spline equals scipy's
+    CubicSpline(bc_type="natural") -- the routine generation_type1.py:97 calls --, every draw lies in its range, and a
+    trajectory does not depend on the batch it is generated in (ids are the only key)."""
+    from scipy.interpolate import CubicSpline
+    from oracle import scenarios as oscn, refgen as R
+    o = oscn.make_scenarios(12)
+    ru = oscn.DEFAULT_RULES
+    for b in range(12):
+        x0 = o["x0"][b]
+        assert ru["x0_lo"][0] <= x0[0] <= ru["x0_hi"][0] and ru["x0_lo"][3] <= x0[3] <= ru["x0_hi"][3]
+        assert ru["x0_lo"][4] <= x0[4] <= ru["x0_hi"][4] and ru["x0_lo"][5] <= x0[5] <= ru["x0_hi"][5]
+        assert ru["vcruise"][0] <= o["vref"][b, 1] <= ru["vcruise"][1] and o["path_kind"][b] == ru["cycle"][b % 2]
+        if o["path_kind"][b] == R.PATH_SPLINE:
+            kx = o["breaks"][b]; ky = o["coef"][b, :, 3]
+            assert (np.diff(kx) >= 1.0).all() and (np.diff(kx) <= 3.0).all() and kx[0] == -6.0
+            # rebuild the last knot from the last piece, then compare with scipy on the interior pieces
+            h = kx[-1] - kx[-2]
+            cs = CubicSpline(kx, ky, bc_type="natural")          # natural spline through the first K-1 knots differs from
+            assert cs.c.shape[1] == len(kx) - 1                  # ours only through the (dropped) last knot: compare the fit
+            full = oscn.natural_spline(np.append(kx, kx[-1] + h), np.append(ky, ky[-1]))
+            ref = CubicSpline(np.append(kx, kx[-1] + h), np.append(ky, ky[-1]), bc_type="natural")
+            np.testing.assert_allclose(full, ref.c.T, atol=1e-12)
+            # the lateral / heading offsets are applied at X
+            piece = int(np.clip((kx <= x0[0]).sum() - 1, 0, len(kx) - 1)); dx = x0[0] - kx[piece]
+            c0, c1, c2, c3 = o["coef"][b, piece]
+            assert abs(x0[1] - (((c0 * dx + c1) * dx + c2) * dx + c3)) <= 0.2 + 1e-12
+    shifted = oscn.make_scenarios(4, traj_id0=5)
+    for k in ("x0", "u0", "path", "vref", "breaks", "coef"):
+        assert np.array_equal(shifted[k], o[k][5:9]), k

@@ -5,7 +5,7 @@ import bench
 import trajectory_generation_b200 as tg
 g = np.load(os.path.join(bench.ROOT, "tests", "golden", "oracle_bench_config.npz"))
 n, T = int(g["n_traj"]), int(g["T"])
-x0, u0, sc = bench.make_workload(n)
+x0, u0, sc = bench.workload_from_golden(g)
 kw = dict(bench.GEN_KW)
 for a in sys.argv[1:]:
     k, v = a.split("="); kw.setdefault("solver_opts", {})[k] = float(v)

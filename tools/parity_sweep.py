@@ -13,7 +13,7 @@ for so in ({}, {"eps_abs": 1e-6, "eps_rel": 1e-6}, {"eps_abs": 1e-7, "eps_rel": 
 # where does the default-settings error sit?
 import trajectory_generation_b200 as tg
 n, T = int(golden["n_traj"]), int(golden["T"])
-x0, u0, sc = bench.make_workload(n)
+x0, u0, sc = bench.workload_from_golden(golden)
 gen = tg.ClosedLoopGenerator(**bench.GEN_KW)
 res = gen.generate(x0, u0, sc, T)
 eX = np.abs(res["clean"] - golden["X_ipm"]); eU = np.abs(res["U"] - golden["U_ipm"])

@@ -6,8 +6,8 @@ import bench
 import trajectory_generation_b200 as tg
 from trajectory_generation_b200 import _lib
 B, T = int(sys.argv[1]), int(sys.argv[2])
-x0, u0, sc = bench.make_workload(B)
 gen = tg.ClosedLoopGenerator(**bench.GEN_KW)
+x0, u0, sc = bench.make_workload(gen, B)
 gen.generate(x0, u0, sc, 5)
 L = _lib.load()
 L.tg_debug_phases.argtypes = [ctypes.c_void_p, ctypes.c_int]

@@ -19,30 +19,27 @@ TOTAL = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 T = 1200
 lo, hi = tgd.shard_range(TOTAL, rank, world)
 B = hi - lo
-# scenario table: sinusoid / parabola mix generated vectorised (splines need a per-trajectory fit on the host)
-rng = np.random.default_rng(2025 + rank)
-x0 = tg.sample_x0(1, 42).repeat(B, 0)
-x0[:, 0] = rng.uniform(-2, 2, B); x0[:, 3] = rng.uniform(0.4, 1.5, B); x0[:, 4] = rng.uniform(-0.05, 0.05, B); x0[:, 5] = rng.uniform(-1, 1, B)
-sc = tg.Scenarios(B)
-A, k, psi = rng.uniform(0.2, 1.0, B), rng.uniform(0.3, 1.0, B), rng.uniform(0, 2 * np.pi, B)
-sc.set_sine(slice(0, B), A, k, psi, 0.0)
-par = np.arange(0, B, 3); c2 = rng.uniform(-0.2, 0.2, len(par)); sc.set_parabola(par, c2)
-y = A * np.sin(k * x0[:, 0] + psi); dy = A * k * np.cos(k * x0[:, 0] + psi)
-y[par] = c2 * x0[par, 0] ** 2; dy[par] = 2 * c2 * x0[par, 0]
-x0[:, 1] = y + rng.uniform(-0.2, 0.2, B); x0[:, 2] = np.arctan(dy) + rng.uniform(-0.2, 0.2, B)
-sc.set_vref(slice(0, B), tg.VREF_RAMP, 0.8, rng.uniform(0.8, 2.0, B), 2.0)
-u0 = np.stack([tg.d_steady_state(x0[:, 3]), np.zeros(B)], 1)
-
+# scenarios, initial states and steady-state inputs: generated on the device, resident (tg_make_scenarios), the spline /
+# sinusoid / parabola mix of configs 2 and 3 by id mod 3
 gen = tg.ClosedLoopGenerator(device=lr, N=20, Ts=0.01, plant=tg.PLANT_GEN1, vref_advance=True)
 stream = torch.cuda.Stream(device=dev); gen.set_stream(stream.cuda_stream)
-d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-d_x0, d_u0, d_spec = d(x0), d(u0), torch.from_numpy(np.ascontiguousarray(sc.spec).view(np.uint8)).to(dev)
+rules = tg.scenario_rules(cycle=(tg.PATH_SPLINE, tg.PATH_SINE, tg.PATH_PARABOLA))
+P = rules.spl_knots - 1
+d_x0 = torch.empty((B, 6), dtype=torch.float64, device=dev); d_u0 = torch.empty((B, 2), dtype=torch.float64, device=dev)
+d_spec = torch.empty(B * _lib.REF_SPEC_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+d_brk = torch.empty(B * P, dtype=torch.float64, device=dev); d_coef = torch.empty((B * P, 4), dtype=torch.float64, device=dev)
 clean = torch.empty((B, T + 1, 6), dtype=torch.float64, device=dev); noisy = torch.empty_like(clean)
 U = torch.empty((B, T, 2), dtype=torch.float64, device=dev)
 scnt = torch.zeros((B, 6), dtype=torch.int32, device=dev); its = torch.zeros(B, dtype=torch.int64, device=dev)
 L = _lib.load()
+import ctypes
+t_s = time.perf_counter()
+with torch.cuda.stream(stream):
+    _lib.check(L.tg_make_scenarios(gen.handle, B, lo, ctypes.byref(rules), d_x0.data_ptr(), d_u0.data_ptr(), d_spec.data_ptr(), d_brk.data_ptr(), d_coef.data_ptr()))
+torch.cuda.synchronize(dev)
+t_scen = time.perf_counter() - t_s
 def launch(nb, t):
-    _lib.check(L.tg_closed_loop(gen.handle, nb, t, d_x0.data_ptr(), d_u0.data_ptr(), d_spec.data_ptr(), None, None, lo,
+    _lib.check(L.tg_closed_loop(gen.handle, nb, t, d_x0.data_ptr(), d_u0.data_ptr(), d_spec.data_ptr(), d_brk.data_ptr(), d_coef.data_ptr(), lo,
                                 clean.data_ptr(), noisy.data_ptr(), U.data_ptr(), scnt.data_ptr(), its.data_ptr()))
 with torch.cuda.stream(stream):
     launch(min(B, 2048), 20)          # warm-up
@@ -60,7 +57,7 @@ if rank == 0:
     steps = TOTAL * T
     print(f"config 5  {TOTAL} trajectories x {T} steps on {world} GPU(s): {ms.item()/1e3:.2f} s (max over ranks) = {steps/(ms.item()*1e-3):.3e} MPC steps/s; "
           f"shard {B} trajectories = {(2*clean.numel()+U.numel())*8/1e9:.1f} GB of rows per GPU in HBM; statuses {dict(zip(tg.STATUS_STRINGS, agg[:6].tolist()))}; "
-          f"mean ADMM iterations/step {agg[6].item()/steps:.2f}")
+          f"mean ADMM iterations/step {agg[6].item()/steps:.2f}; scenario generation on the device {t_scen*1e3:.1f} ms per rank")
     n5 = min(5000, B)
     res = {"clean": clean[:n5].cpu().numpy(), "noisy": noisy[:n5].cpu().numpy(), "U": U[:n5].cpu().numpy()}
     t = time.perf_counter(); tg.write_csv(res, 0.01, "/tmp/c5_clean.csv", "/tmp/c5_noisy.csv"); print(f"          CSV of the first {n5} ids: {time.perf_counter()-t:.1f} s")

@@ -31,16 +31,14 @@ print(f"          one mpc_step call through the host API (B=1, cold start): p50 
 
 # ---- config 3: 65536 trajectories, parabola + mixed references, generator plant, clean+noisy CSV (first 5000 ids)
 B, T = 65536, 1200
-t = time.perf_counter(); x0, u0, sc = bench.make_workload(B); t_setup = time.perf_counter() - t
-rng = np.random.default_rng(3)
-par = np.arange(0, B, 3)
-sc.set_parabola(par, rng.uniform(-0.2, 0.2, len(par)))          # every third trajectory: y = c x^2 (MPC/main.py:64 has c = 0.1)
-x0[par, 1] = sc.spec["path"][par, 0] * x0[par, 0] ** 2 + rng.uniform(-0.2, 0.2, len(par)); x0[par, 2] = np.arctan(2 * sc.spec["path"][par, 0] * x0[par, 0])
 gen = tg.ClosedLoopGenerator(N=20, Ts=0.01, plant=tg.PLANT_GEN2, vref_advance=True)
+# parabola / sinusoid / spline by id mod 3, x0 from generation_type2.py:171-174's ranges with the vx floor of SURVEY.md 8(d)
+rules = tg.scenario_rules(cycle=(tg.PATH_PARABOLA, tg.PATH_SINE, tg.PATH_SPLINE), x0_lo=(-2, 0, 0, 0.4, -0.05, -1), x0_hi=(2, 0, 0, 0.6, 0.05, 1), seed_base=42)
+t = time.perf_counter(); x0, u0, sc = gen.make_scenarios(B, rules); t_setup = time.perf_counter() - t
 res, dt = timed(gen, x0, u0, sc, T, reps=1)
 st = res["status_counts"].sum(0)
 print(f"config 3  B={B} N=20 T={T}: {dt:.2f} s end to end (host buffers, {res['clean'].nbytes*2/1e9 + res['U'].nbytes/1e9:.1f} GB out) = {B*T/dt:.3e} MPC steps/s; "
-      f"statuses {dict(zip(tg.STATUS_STRINGS, st.tolist()))}; mean ADMM iterations/step {res['iters_total'].sum()/(B*T):.2f}; scenario setup on host {t_setup:.1f} s")
+      f"statuses {dict(zip(tg.STATUS_STRINGS, st.tolist()))}; mean ADMM iterations/step {res['iters_total'].sum()/(B*T):.2f}; scenario generation on the device + copy to the host {t_setup:.2f} s")
 sub = {k: v[:5000] for k, v in res.items()}
 t = time.perf_counter(); tg.write_csv(sub, 0.01, "/tmp/c3_clean.csv", "/tmp/c3_noisy.csv"); t_csv = time.perf_counter() - t
 import os

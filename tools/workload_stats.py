@@ -8,8 +8,8 @@ import trajectory_generation_b200 as tg
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1200
-x0, u0, sc = bench.make_workload(B)
 gen = tg.ClosedLoopGenerator(**bench.GEN_KW)
+x0, u0, sc = bench.make_workload(gen, B)
 gen.generate(x0[:8], u0[:8], sc.slice(0, 8), 10)
 t0 = time.perf_counter(); res = gen.generate(x0, u0, sc, T); dt = time.perf_counter() - t0
 U = res["U"]

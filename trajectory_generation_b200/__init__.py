@@ -9,7 +9,7 @@ from . import _lib
 from ._lib import TrajgenError, build
 from .mpc import (BatchedMPC, Params, mpc_step, make_config, MODEL_MPC, MODEL_GEN1, MODEL_GEN2, PLANT_MPC,
                   PLANT_GEN1, PLANT_GEN2, JAC_ANALYTIC, JAC_FD)
-from .generation import (ClosedLoopGenerator, Scenarios, d_steady_state, sample_x0, to_frames, write_csv, merge_datasets,
+from .generation import (ClosedLoopGenerator, Scenarios, scenario_rules, PATH_ARC, d_steady_state, sample_x0, to_frames, write_csv, merge_datasets,
                          to_loader_tensors, PATH_PARABOLA, PATH_SINE, PATH_SPLINE, VREF_HOLD, VREF_CONST, VREF_RAMP,
                          VREF_TRAPEZOID, VREF_SINE, X0_RANGES_TYPE1, X0_RANGES_TYPE2, CLEAN_COLS, NOISY_COLS)
 from .openloop import OpenLoopGenerator, type1_rules, type2_rules, TYPE1_MODES, TYPE2_MODES, CTRL_SEED_BASE

@@ -64,6 +64,17 @@ class TgType2Rules(ctypes.Structure):
     ]
 
 
+class TgScenarioRules(ctypes.Structure):
+    """include/trajgen.h::tg_scenario_rules."""
+    _fields_ = [
+        ("x0_lo", d * 6), ("x0_hi", d * 6), ("lat_off", d * 2), ("head_off", d * 2),
+        ("vref0", d), ("vcruise", d * 2), ("t_ramp", d),
+        ("sine_A", d * 2), ("sine_k", d * 2), ("sine_psi", d * 2), ("parab_c", d * 2),
+        ("spl_x0", d), ("spl_dx", d * 2), ("spl_sigma", d),
+        ("spl_knots", i32), ("n_cycle", i32), ("cycle", i32 * 4), ("reserved", i32), ("seed_base", u64),
+    ]
+
+
 class TgStateLimits(ctypes.Structure):
     _fields_ = [("lo", d * 6), ("hi", d * 6)]
 
@@ -76,7 +87,7 @@ assert REF_SPEC_DTYPE.itemsize == 96
 EXPORTS = (
     "tg_last_error", "tg_version", "tg_default_config", "tg_create", "tg_destroy", "tg_set_stream", "tg_synchronize",
     "tg_kernel_launches", "tg_info", "tg_tyre_table_info", "tg_linearize", "tg_assemble", "tg_mpc_step", "tg_mpc_step_host", "tg_ref_window",
-    "tg_closed_loop", "tg_closed_loop_host", "tg_default_type1_rules", "tg_default_type2_rules", "tg_openloop_type1",
+    "tg_closed_loop", "tg_closed_loop_host", "tg_default_scenario_rules", "tg_make_scenarios", "tg_make_scenarios_host", "tg_default_type1_rules", "tg_default_type2_rules", "tg_openloop_type1",
     "tg_openloop_type2", "tg_openloop_type1_host", "tg_openloop_type2_host", "tg_write_csv", "tg_merge_csv", "tg_estimator_step", "tg_estimator_step_vjp",
     "tg_estimator_rollout", "tg_plant_rollout", "tg_sensor_noise", "tg_philox_u32", "tg_fma_peak",
     "tg_device_count", "tg_malloc", "tg_malloc_on", "tg_free", "tg_memcpy_h2d", "tg_memcpy_d2h", "tg_malloc_host", "tg_free_host",
@@ -129,6 +140,10 @@ def load():
     L.tg_ref_window.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp, vp]
     L.tg_closed_loop.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     L.tg_closed_loop_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, vp]
+    L.tg_default_scenario_rules.argtypes = [ctypes.POINTER(TgScenarioRules)]
+    L.tg_default_scenario_rules.restype = None
+    L.tg_make_scenarios.argtypes = [vp, ctypes.c_int, i64, ctypes.POINTER(TgScenarioRules), vp, vp, vp, vp, vp]
+    L.tg_make_scenarios_host.argtypes = [vp, ctypes.c_int, i64, ctypes.POINTER(TgScenarioRules), vp, vp, vp, vp, vp]
     L.tg_default_type1_rules.argtypes = [ctypes.POINTER(TgType1Rules)]
     L.tg_default_type1_rules.restype = None
     L.tg_default_type2_rules.argtypes = [ctypes.POINTER(TgType2Rules)]

@@ -21,6 +21,7 @@
 
 #include "tw_solver.cuh"
 #include "tg_openloop.cuh"
+#include "tg_scenarios.cuh"
 #include "tg_estimator.cuh"
 
 static thread_local std::string g_err;
@@ -772,6 +773,47 @@ int tg_sensor_noise(tg_handle *h, int64_t traj_id0, int n_traj, int n_rows, doub
     return TG_OK;
 }
 
+// ---- scenario generation (tg_scenarios.cuh)
+void tg_default_scenario_rules(tg_scenario_rules *r)
+{
+    memset(r, 0, sizeof(*r));
+    const double lo[6] = {-2.0, 0.0, 0.0, 0.4, -0.05, -1.0}, hi[6] = {2.0, 0.0, 0.0, 1.5, 0.05, 1.0};   // generation_type1.py:260-265
+    memcpy(r->x0_lo, lo, sizeof(lo)); memcpy(r->x0_hi, hi, sizeof(hi));
+    r->lat_off[0] = -0.2; r->lat_off[1] = 0.2; r->head_off[0] = -0.2; r->head_off[1] = 0.2;
+    r->vref0 = 0.8; r->vcruise[0] = 0.8; r->vcruise[1] = 2.0; r->t_ramp = 2.0;                          // MPC/main.py:87
+    r->sine_A[0] = 0.2; r->sine_A[1] = 1.0; r->sine_k[0] = 0.3; r->sine_k[1] = 1.0; r->sine_psi[0] = 0.0; r->sine_psi[1] = 6.283185307179586;
+    r->parab_c[0] = -0.2; r->parab_c[1] = 0.2;
+    r->spl_x0 = -6.0; r->spl_dx[0] = 1.0; r->spl_dx[1] = 3.0; r->spl_sigma = 0.3; r->spl_knots = 27;
+    r->n_cycle = 2; r->cycle[0] = TG_PATH_SPLINE; r->cycle[1] = TG_PATH_SINE;
+    r->seed_base = 2025ull;
+}
+
+static int scenario_check(tg_handle *h, int B, const tg_scenario_rules *r)
+{
+    if (!h || !r || B < 0) return fail(TG_ERR_INVALID, "bad argument");
+    if (r->spl_knots < 3 || r->spl_knots > TG_SCN_MAX_KNOTS) return fail(TG_ERR_INVALID, "scenario rules: 3 <= spl_knots <= 32");
+    if (r->n_cycle < 1 || r->n_cycle > 4) return fail(TG_ERR_INVALID, "scenario rules: 1 <= n_cycle <= 4");
+    for (int i = 0; i < r->n_cycle; ++i)
+        if (r->cycle[i] < TG_PATH_PARABOLA || r->cycle[i] > TG_PATH_SPLINE) return fail(TG_ERR_INVALID, "scenario rules: cycle entries must be parabola / sine / spline");
+    if (!(r->spl_dx[0] > 0) || r->spl_dx[1] < r->spl_dx[0]) return fail(TG_ERR_INVALID, "scenario rules: knot spacing must be positive");
+    if ((long long)B * (r->spl_knots - 1) > 2147483647LL) return fail(TG_ERR_INVALID, "scenario rules: spline table index overflow");
+    return TG_OK;
+}
+
+int tg_make_scenarios(tg_handle *h, int B, int64_t traj_id0, const tg_scenario_rules *rules, double *x0, double *u0,
+                      tg_ref_spec *spec, double *spl_breaks, double *spl_coef)
+{
+    int rc = scenario_check(h, B, rules);
+    if (rc != TG_OK) return rc;
+    if (B == 0) return TG_OK;
+    if (!x0 || !u0 || !spec || !spl_breaks || !spl_coef) return fail(TG_ERR_INVALID, "null output");
+    CK(cudaSetDevice(h->device));
+    tg_scenario_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->dc, *rules, B, (long long)traj_id0, x0, u0, spec, spl_breaks, spl_coef);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+
 // ---- open-loop generators (tg_openloop.cuh)
 void tg_default_type1_rules(tg_type1_rules *r)
 {
@@ -1125,6 +1167,29 @@ int tg_closed_loop_host(tg_handle *h, int B, int T, const double *x0, const doub
     }
     if (status_counts) D2H(status_counts, d_sc, s_sc);
     if (iters_total) D2H(iters_total, d_it, s_it);
+    CK(cudaStreamSynchronize(h->stream));
+    return TG_OK;
+}
+
+int tg_make_scenarios_host(tg_handle *h, int B, int64_t traj_id0, const tg_scenario_rules *rules, double *x0, double *u0,
+                           tg_ref_spec *spec, double *spl_breaks, double *spl_coef)
+{
+    int rc = scenario_check(h, B, rules);
+    if (rc != TG_OK) return rc;
+    if (B == 0) return TG_OK;
+    if (!x0 || !u0 || !spec || !spl_breaks || !spl_coef) return fail(TG_ERR_INVALID, "null output");
+    CK(cudaSetDevice(h->device));
+    const size_t P = (size_t)rules->spl_knots - 1;
+    const size_t s_x0 = (size_t)B * 48, s_u0 = (size_t)B * 16, s_sp = (size_t)B * sizeof(tg_ref_spec), s_bk = (size_t)B * P * 8, s_cf = s_bk * 4;
+    rc = ensure_dstage(h, PAD(s_x0) + PAD(s_u0) + PAD(s_sp) + PAD(s_bk) + PAD(s_cf) + 4096);
+    if (rc != TG_OK) return rc;
+    Arena ar{(char *)h->dstage, 0, h->dstage_bytes};
+    double *d_x0 = (double *)ar.take(s_x0), *d_u0 = (double *)ar.take(s_u0);
+    tg_ref_spec *d_sp = (tg_ref_spec *)ar.take(s_sp);
+    double *d_bk = (double *)ar.take(s_bk), *d_cf = (double *)ar.take(s_cf);
+    rc = tg_make_scenarios(h, B, traj_id0, rules, d_x0, d_u0, d_sp, d_bk, d_cf);
+    if (rc != TG_OK) return rc;
+    D2H(x0, d_x0, s_x0); D2H(u0, d_u0, s_u0); D2H(spec, d_sp, s_sp); D2H(spl_breaks, d_bk, s_bk); D2H(spl_coef, d_cf, s_cf);
     CK(cudaStreamSynchronize(h->stream));
     return TG_OK;
 }

@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib
 from .mpc import BatchedMPC, Params  # noqa: F401
 
-PATH_PARABOLA, PATH_SINE, PATH_SPLINE = 0, 1, 2
+PATH_PARABOLA, PATH_SINE, PATH_SPLINE, PATH_ARC = 0, 1, 2, 3
 VREF_HOLD, VREF_CONST, VREF_RAMP, VREF_TRAPEZOID, VREF_SINE = 0, 1, 2, 3, 4
 
 CLEAN_COLS = ["t", "X", "Y", "phi", "vx", "vy", "omega", "d", "delta", "trajectory_id"]   # generation_type1.py:327
@@ -41,6 +41,24 @@ class Scenarios:
 
     def __len__(self):
         return len(self.spec)
+
+    @classmethod
+    def from_arrays(cls, path_kind, path, vref, breaks=None, coef=None, vref_kind=None):
+        """Scenario table from plain arrays: path_kind[B], path[B,4], vref[B,6] (+ vref_kind[B], default ramp); spline tables
+        breaks[B,P], coef[B,P,4] with trajectory b's pieces at row b (the layout tg_make_scenarios and oracle/scenarios.py use)."""
+        B = len(path_kind)
+        sc = cls(B)
+        sc.spec["path_kind"] = np.asarray(path_kind, np.int32)
+        sc.spec["path"] = np.asarray(path, float).reshape(B, 4)
+        sc.spec["vref"] = np.asarray(vref, float).reshape(B, 6)
+        sc.spec["vref_kind"] = VREF_RAMP if vref_kind is None else np.asarray(vref_kind, np.int32)
+        if breaks is not None:
+            breaks = np.ascontiguousarray(breaks, float); coef = np.ascontiguousarray(coef, float)
+            P = breaks.shape[1]
+            sc._breaks, sc._coef = [breaks.reshape(-1)], [coef.reshape(-1, 4)]
+            sc.spec["spline_first"] = np.arange(B) * P
+            sc.spec["spline_count"] = P
+        return sc
 
     def set_parabola(self, i, c2=0.1, c1=0.0, c0=0.0):
         self.spec["path_kind"][i] = PATH_PARABOLA
@@ -114,6 +132,33 @@ class Scenarios:
         s.spec = self.spec[lo:hi].copy()
         s._breaks, s._coef = self._breaks, self._coef      # spline_first indexes the shared tables
         return s
+
+
+def scenario_rules(**overrides):
+    """tg_scenario_rules with the library defaults (BASELINE config 2: spline / sinusoid references by id parity, x0 from
+    generation_type1.py:260-265's ranges); keyword overrides by field name, e.g. cycle=(PATH_PARABOLA, PATH_SINE, PATH_SPLINE),
+    x0_lo=..., seed_base=...."""
+    r = _lib.TgScenarioRules()
+    _lib.load().tg_default_scenario_rules(ctypes.byref(r))
+    for k, v in overrides.items():
+        if k == "cycle":
+            v = list(v)
+            r.n_cycle = len(v)
+            for i, kind in enumerate(v):
+                r.cycle[i] = int(kind)
+            continue
+        if not hasattr(r, k):
+            raise TypeError(f"unknown scenario rule {k!r}")
+        cur = getattr(r, k)
+        if isinstance(cur, ctypes.Array):
+            v = list(np.asarray(v, float).ravel())
+            if len(v) != len(cur):
+                raise ValueError(f"{k}: expected {len(cur)} values")
+            for i, x in enumerate(v):
+                cur[i] = x
+        else:
+            setattr(r, k, type(cur)(v))
+    return r
 
 
 class ClosedLoopGenerator(BatchedMPC):
@@ -199,6 +244,20 @@ class ClosedLoopGenerator(BatchedMPC):
             for k_ in ("clean", "noisy", "U"):
                 out[k_] = np.concatenate([c[k_] for c in kept])
         return out
+
+    def make_scenarios(self, B, rules=None, traj_id0=0):
+        """Initial states, steady-state inputs and reference scenarios for trajectory ids traj_id0 .. traj_id0 + B - 1, generated
+        on the device (tg_make_scenarios: Philox draws keyed by the global id, natural-spline fits per trajectory) and returned
+        as host arrays: (x0[B,6], u0[B,2], Scenarios)."""
+        rules = rules if rules is not None else scenario_rules()
+        P = rules.spl_knots - 1
+        x0, u0 = np.empty((B, 6)), np.empty((B, 2))
+        sc = Scenarios(B)
+        brk, coef = np.empty(B * P), np.empty((B * P, 4))
+        _lib.check(_lib.load().tg_make_scenarios_host(self._h, int(B), int(traj_id0), ctypes.byref(rules), _lib.ptr(x0), _lib.ptr(u0),
+                                                      sc.spec.ctypes.data, _lib.ptr(brk), _lib.ptr(coef)))
+        sc._breaks, sc._coef = [brk], [coef]
+        return x0, u0, sc
 
     def ref_window(self, x0, scenarios, t_index=0):
         """a10 tap: -> path_ref[B,N+1,3], vref[B,N+1] (MPC/main.py:87-90)."""
