@@ -104,7 +104,13 @@ typedef struct tg_ref_spec {
     int32_t spline_first;  /* first piece of this trajectory in the spline tables */
     int32_t spline_count;  /* number of pieces K: spl_breaks[first+i] = start of piece i, spl_coef[first+i][4] =
                               (c0,c1,c2,c3) of y = ((c0 dx + c1) dx + c2) dx + c3, dx = x - start; either end extrapolates
-                              its end piece (scipy PPoly behaviour) */
+                              its end piece (scipy PPoly behaviour).
+                              TG_PATH_ARC: the path is (x(s), y(s)); x(s) = pieces [first, first + K), y(s) = pieces
+                              [first + K, first + 2K) of spl_coef over the breaks spl_breaks[first .. first + K); path[0] = the
+                              parameter s from which the point closest to the vehicle is searched on the first step (the
+                              closed loop tracks it afterwards).  The window of MPC/main.py:51-68 then advances along the
+                              path by the arclength vref Ts, and phi* = atan2(y', x') is unwrapped along the window, starting
+                              within pi of the vehicle's heading (csrc/tw_solver.cuh tw_ref_window_warp; oracle/refgen.py) */
     double path[4];
     double vref[6];
 } tg_ref_spec;

@@ -61,7 +61,7 @@ def mpc_step(x0, u_prev, path_ref, Ts=0.02, N=20, params=None,
 
 def closed_loop(x0, u_prev, T, Ts, N, path_kind=refgen.PATH_PARABOLA, path_prm=(0.1, 0.0, 0.0, 0.0),
                 spline=None, vref_kind=refgen.VREF_RAMP, vref_prm=(0.8, 2.0, 2.0), vref_advance=False,
-                plant=dyn.PLANT_MPC, solver="ipm", solver_opts=None, **mpc_kwargs):
+                plant=dyn.PLANT_MPC, solver="ipm", solver_opts=None, arc=None, **mpc_kwargs):
     """MPC/main.py:85-101: for t in range(T): vref window (:87), path window anchored at x[0]
     (:90), mpc_step (:94), Euler plant step (:97), u_prev <- u_cmd (:101).
     Returns X[T+1,6] (row 0 = x0), U[T,2], statuses[T], iters[T]."""
@@ -72,7 +72,10 @@ def closed_loop(x0, u_prev, T, Ts, N, path_kind=refgen.PATH_PARABOLA, path_prm=(
     for t in range(T):
         t0 = t * Ts if vref_advance else 0.0
         vref_seq = refgen.vref_profile(vref_kind, vref_prm, N, Ts, t0, x[3])
-        path_ref = refgen.ref_window(x[0], N, Ts, vref_seq, path_kind, path_prm, spline)
+        if path_kind == refgen.PATH_ARC:     # arclength-parameterised path: the anchor s is tracked from step to step
+            path_ref, s_anchor = refgen.ref_window_arc(x, path_prm[0] if t == 0 else s_anchor, N, Ts, vref_seq, arc)
+        else:
+            path_ref = refgen.ref_window(x[0], N, Ts, vref_seq, path_kind, path_prm, spline)
         u_cmd, status, info = mpc_step(x, u_prev, path_ref, Ts=Ts, N=N, vref=vref_seq,
                                        solver=solver, solver_opts=solver_opts, **mpc_kwargs)
         x = dyn.plant_step(x, u_cmd, Ts, plant=plant)

@@ -15,6 +15,8 @@ from .dynamics import PARAMS
 PATH_PARABOLA = 0   # y = c2 x^2 + c1 x + c0           (MPC/main.py:64-66: c2=0.1)
 PATH_SINE = 1       # y = A sin(k x + psi) + c0        (MPC/README.md:75-76: A=0.5,k=0.5)
 PATH_SPLINE = 2     # piecewise cubic y(x), scipy PPoly layout, end pieces extrapolate
+PATH_ARC = 3        # parametric path (x(s), y(s)): two piecewise cubics over one set of breaks
+ARC_PROJECT_ITERS = 4
 
 VREF_HOLD = 0       # vref=None in mpc_step -> x0[3]   (MPC/mpc_6stati.py:158-159)
 VREF_CONST = 1      # scalar vref                      (MPC/mpc_6stati.py:160-161)
@@ -85,6 +87,67 @@ def ref_window(x_start, N, Ts, vref_seq, kind=PATH_PARABOLA, prm=(0.1, 0.0, 0.0,
         xs[k + 1] = xs[k] + vref_seq[k] * Ts
     ys, dydx = path_eval(kind, prm, xs, spline)
     return np.stack([xs, ys, np.arctan(dydx)], axis=1)
+
+
+def arc_eval(arc, s):
+    """(x, y, x', y') of the parametric path at parameter s.  ``arc`` = (breaks[K] piece starts, coef_x[K,4], coef_y[K,4]),
+    scipy PPoly coefficient order; both ends extrapolate their end piece."""
+    breaks, cx, cy = arc
+    K = len(cx)
+    lo = 0
+    while lo + 1 < K and s >= breaks[lo + 1]:
+        lo += 1
+    d = s - breaks[lo]
+    a, b = cx[lo], cy[lo]
+    x = ((a[0] * d + a[1]) * d + a[2]) * d + a[3]
+    y = ((b[0] * d + b[1]) * d + b[2]) * d + b[3]
+    dx = (3.0 * a[0] * d + 2.0 * a[1]) * d + a[2]
+    dy = (3.0 * b[0] * d + 2.0 * b[1]) * d + b[2]
+    return x, y, dx, dy
+
+
+def arc_project(arc, s_guess, X, Y, iters=ARC_PROJECT_ITERS):
+    """Parameter of the path point closest to (X, Y): ``iters`` Gauss-Newton steps s <- s + (P - p(s)).p'(s) / |p'(s)|^2
+    from ``s_guess`` (a fixed count, so that the CUDA path and this restatement do the same arithmetic)."""
+    s = float(s_guess)
+    for _ in range(iters):
+        x, y, dx, dy = arc_eval(arc, s)
+        s = s + ((X - x) * dx + (Y - y) * dy) / (dx * dx + dy * dy)
+    return s
+
+
+def ref_window_arc(x_state, s_guess, N, Ts, vref_seq, arc):
+    """The window of MPC/main.py:51-68 for a path that is NOT a graph over X.  The reference anchors the window at the
+    vehicle's X and advances X by vref Ts (:59-61); here the anchor is the path parameter s0 of the point closest to the
+    vehicle (tracked from step to step through ``s_guess``), the window advances along the path by the arclength vref Ts,
+    ds = vref Ts / |p'(s)|, and phi* = atan2(y', x') is unwrapped so that it is continuous along the window and within pi of
+    the vehicle's (unwrapped) heading -- the cost (phi - phi*)^2 of mpc_6stati.py:233 has no wrap.
+    -> (path_ref[N+1,3], s0)"""
+    vref_seq = np.asarray(vref_seq, dtype=float).reshape(N + 1)
+    s0 = arc_project(arc, s_guess, float(x_state[0]), float(x_state[1]))
+    out = np.zeros((N + 1, 3))
+    s = s0
+    prev = float(x_state[2])
+    two_pi = 2.0 * math.pi
+    for k in range(N + 1):
+        x, y, dx, dy = arc_eval(arc, s)
+        raw = math.atan2(dy, dx)
+        ph = raw + two_pi * np.rint((prev - raw) / two_pi)
+        out[k] = (x, y, ph)
+        prev = ph
+        if k < N:
+            s = s + vref_seq[k] * Ts / math.sqrt(dx * dx + dy * dy)
+    return out, s0
+
+
+def arc_spline_tables(px, py):
+    """Natural cubic splines x(s), y(s) through the way-points (px, py), s = cumulative chord length.
+    -> (breaks[K] piece starts, coef_x[K,4], coef_y[K,4])"""
+    from scipy.interpolate import CubicSpline
+    px = np.asarray(px, float); py = np.asarray(py, float)
+    s = np.concatenate([[0.0], np.cumsum(np.hypot(np.diff(px), np.diff(py)))])
+    sx, sy = CubicSpline(s, px, bc_type="natural"), CubicSpline(s, py, bc_type="natural")
+    return np.ascontiguousarray(s[:-1]), np.ascontiguousarray(sx.c.T), np.ascontiguousarray(sy.c.T)
 
 
 def natural_spline_ppoly(knots_x, knots_y):

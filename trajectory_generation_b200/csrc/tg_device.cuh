@@ -658,6 +658,36 @@ __device__ __forceinline__ void tg_path_at(const tg_ref_spec &s, const double *_
     }
 }
 
+// Parametric path (TG_PATH_ARC): x(s) in pieces [first, first + K), y(s) in pieces [first + K, first + 2K) of the coefficient
+// table, one set of breaks (the first K entries).  `lo` is the caller's running piece index (s mostly advances).
+__device__ __forceinline__ void tg_arc_eval(const tg_ref_spec &s, const double *__restrict__ brk, const double *__restrict__ coef,
+                                            double sv, int &lo, double &x, double &y, double &dx, double &dy)
+{
+    const int K = s.spline_count;
+    const double *b = brk + s.spline_first;
+    if (sv < b[lo]) lo = 0;
+    while (lo + 1 < K && sv >= b[lo + 1]) ++lo;
+    const double *cx = coef + 4 * (size_t)(s.spline_first + lo), *cy = cx + 4 * (size_t)K;
+    const double d = sv - b[lo];
+    x = ((cx[0] * d + cx[1]) * d + cx[2]) * d + cx[3];
+    y = ((cy[0] * d + cy[1]) * d + cy[2]) * d + cy[3];
+    dx = (3.0 * cx[0] * d + 2.0 * cx[1]) * d + cx[2];
+    dy = (3.0 * cy[0] * d + 2.0 * cy[1]) * d + cy[2];
+}
+#define TG_ARC_PROJECT_ITERS 4
+// parameter of the path point closest to (X, Y): a fixed number of Gauss-Newton steps from s_guess (oracle/refgen.py arc_project)
+__device__ __forceinline__ double tg_arc_project(const tg_ref_spec &s, const double *__restrict__ brk, const double *__restrict__ coef,
+                                                 double s_guess, double X, double Y, int &lo)
+{
+    double sv = s_guess;
+    for (int it = 0; it < TG_ARC_PROJECT_ITERS; ++it) {
+        double x, y, dx, dy;
+        tg_arc_eval(s, brk, coef, sv, lo, x, y, dx, dy);
+        sv = sv + ((X - x) * dx + (Y - y) * dy) / (dx * dx + dy * dy);
+    }
+    return sv;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 + Box-Muller with fixed polynomial kernels: bit-identical to oracle/philox_ref.c
 // (same operations in the same order; __d*_rn / __fma_rn keep nvcc from contracting differently).

@@ -1125,7 +1125,8 @@ int tg_closed_loop_host(tg_handle *h, int B, int T, const double *x0, const doub
             if (sp.path_kind < TG_PATH_PARABOLA || sp.path_kind > TG_PATH_ARC || sp.vref_kind < TG_VREF_HOLD || sp.vref_kind > TG_VREF_SINE)
                 return fail(TG_ERR_INVALID, "scenario " + std::to_string(b) + ": unknown path_kind / vref_kind");
             if (sp.path_kind == TG_PATH_SPLINE || sp.path_kind == TG_PATH_ARC) {
-                if (sp.spline_count < 1 || sp.spline_first < 0 || (int64_t)sp.spline_first + sp.spline_count > n_tab)
+                const int64_t need_c = (int64_t)sp.spline_first + (sp.path_kind == TG_PATH_ARC ? 2 : 1) * (int64_t)sp.spline_count;
+                if (sp.spline_count < 1 || sp.spline_first < 0 || (int64_t)sp.spline_first + sp.spline_count > n_tab || need_c > n_coef || !coef)
                     return fail(TG_ERR_INVALID, "scenario " + std::to_string(b) + ": spline pieces outside the break / coefficient tables");
             }
         }

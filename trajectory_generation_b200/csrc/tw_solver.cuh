@@ -246,15 +246,46 @@ __device__ __forceinline__ TwMap<S> tw_make_map(int nb, int tid)
 
 // reference window by ONE warp (MPC/main.py:87-90): vref over the horizon, xs by sequential accumulation (the reference's own
 // summation order), y = path(xs), phi* = atan(path'(xs)), and sin / cos(phi*).
+// TG_PATH_ARC (a path that is not a graph over X): the anchor is the path parameter s0 of the point
+// closest to the vehicle, found from the guess in sp.path[0] and written back to *s_anchor (when given) so that the closed
+// loop tracks it from step to step; the window advances by the arclength vref Ts (ds = vref Ts / |p'(s)|) and
+// phi* = atan2(y', x') is unwrapped along the window, starting within pi of the vehicle's heading (oracle/refgen.py
+// ref_window_arc states the same arithmetic).
 template <int NC, int W>
 __device__ __forceinline__ void tw_ref_window_warp(const DevCfg &c, const WLayout &L, double *sm, const tg_ref_spec &sp,
-                                                   const double *brk, const double *coef, int t_index, int lane)
+                                                   const double *brk, const double *coef, int t_index, int lane,
+                                                   double *s_anchor = nullptr)
 {
     const int N = NC > 0 ? NC : c.N;
     const double t0 = c.vref_advance ? (double)t_index * c.Ts : 0.0;
     const double vx0 = sm[LF(x0) + 3];
     for (int k = lane; k <= N; k += 32) sm[LF(vref) + k] = tg_vref_at(sp.vref_kind, sp.vref, t0 + (double)k * c.Ts, vx0);
     __syncwarp();
+    if (sp.path_kind == TG_PATH_ARC) {
+        if (lane == 0) {
+            int lo = 0;
+            double sv = tg_arc_project(sp, brk, coef, sp.path[0], sm[LF(x0)], sm[LF(x0) + 1], lo);
+            double prev = sm[LF(x0) + 2];
+            const double two_pi = 6.283185307179586;
+            for (int k = 0; k <= N; ++k) {
+                double x, y, dx, dy;
+                tg_arc_eval(sp, brk, coef, sv, lo, x, y, dx, dy);
+                const double raw = atan2(dy, dx);
+                const double ph = raw + two_pi * rint((prev - raw) / two_pi);
+                sm[LF(Xr) + k] = x; sm[LF(Yr) + k] = y; sm[LF(Pr) + k] = ph;
+                prev = ph;
+                if (k == 0 && s_anchor) *s_anchor = sv;
+                if (k < N) sv = sv + sm[LF(vref) + k] * c.Ts / sqrt(dx * dx + dy * dy);
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k <= N; k += 32) {
+            double s_, c_;
+            TG_SINCOS(sm[LF(Pr) + k], s_, c_);
+            sm[LF(sn) + k] = s_; sm[LF(cs) + k] = c_;
+        }
+        return;
+    }
     if (lane == 0) {
         double xs = sm[LF(x0)];
         sm[LF(Xr)] = xs;
@@ -619,7 +650,7 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
     if (wid == ref_warp) {
         if (fx) {
             const tg_ref_spec &sp = *reinterpret_cast<const tg_ref_spec *>(sm + LF(spec));
-            tw_ref_window_warp<NC, W>(c, L, sm, sp, fx->brk, fx->coef, fx->t_index, lane);
+            tw_ref_window_warp<NC, W>(c, L, sm, sp, fx->brk, fx->coef, fx->t_index, lane, sm + LF(spec) + 2);   // + 2: sp.path[0]
         } else {
             for (int i = lane; i <= N; i += 32) { double s_, c_; TG_SINCOS(sm[LF(Pr) + i], s_, c_); sn[i] = s_; cs[i] = c_; }
         }

@@ -117,6 +117,26 @@ class Scenarios:
         self.spec["spline_count"][idx] = K - 1
         return coef
 
+    def set_arc(self, i, px, py, s_start=0.0):
+        """Arclength-parameterised reference path through the way-points (px, py) -- a path that need not be a graph over X
+        (U-turns, loops): natural cubic splines x(s), y(s), s = cumulative chord length.  The window is
+        anchored at the path point closest to the vehicle, searched from ``s_start`` on the first step and tracked afterwards.
+        Table layout: K pieces of x(s) followed by K pieces of y(s) (the breaks are stored twice so that one index serves both
+        tables)."""
+        from scipy.interpolate import CubicSpline
+        px = np.asarray(px, float); py = np.asarray(py, float)
+        sk = np.concatenate([[0.0], np.cumsum(np.hypot(np.diff(px), np.diff(py)))])
+        cx, cy = CubicSpline(sk, px, bc_type="natural"), CubicSpline(sk, py, bc_type="natural")
+        first = sum(len(b) for b in self._breaks)
+        K = cx.c.shape[1]
+        self._breaks.append(np.concatenate([sk[:K], sk[:K]]))
+        self._coef.append(np.ascontiguousarray(np.concatenate([cx.c.T, cy.c.T], axis=0), dtype=float))
+        self.spec["path_kind"][i] = PATH_ARC
+        self.spec["spline_first"][i] = first
+        self.spec["spline_count"][i] = K
+        self.spec["path"][i] = (float(s_start), 0.0, 0.0, 0.0)
+        return sk
+
     def set_vref(self, i, kind, *prm):
         self.spec["vref_kind"][i] = kind
         cols = list(prm) + [0.0] * (6 - len(prm))
@@ -125,7 +145,7 @@ class Scenarios:
     def tables(self):
         if not self._breaks:
             return np.zeros(0), np.zeros((0, 4))
-        return np.concatenate(self._breaks), np.concatenate(self._coef, axis=0)
+        return np.ascontiguousarray(np.concatenate(self._breaks)), np.ascontiguousarray(np.concatenate(self._coef, axis=0))
 
     def slice(self, lo, hi):
         s = Scenarios(0)
