@@ -237,3 +237,31 @@ def test_device_scenario_generation_matches_oracle():
     x0, u0, sc = gen.make_scenarios(16)
     res = tg.ClosedLoopGenerator(**{"N": 20, "Ts": 0.01, "plant": tg.PLANT_GEN1, "vref_advance": True}).generate(x0, u0, sc, 50)
     assert res["status_counts"][:, :2].sum() == 16 * 50
+
+
+def test_streamed_generation_equals_one_launch(tmp_path):
+    """generate() in chunks through the two page-locked chunk buffers (ragged last chunk), the chunk iterator and
+    generate_to_csv give exactly the rows / files of a single launch."""
+    B, T = 100, 60
+    gen = tg.ClosedLoopGenerator(N=20, Ts=0.01, plant=tg.PLANT_GEN2, vref_advance=True)
+    x0, u0, sc = gen.make_scenarios(B, tg.scenario_rules(cycle=(tg.PATH_PARABOLA, tg.PATH_SINE, tg.PATH_SPLINE)))
+    one = gen.generate(x0, u0, sc, T, traj_id0=7)
+    ch = gen.generate(x0, u0, sc, T, traj_id0=7, chunk=32)
+    for k in ("clean", "noisy", "U", "status_counts", "iters_total"):
+        assert np.array_equal(one[k], ch[k]), k
+    seen = []
+    for lo, hi, res in gen.generate_chunks(x0, u0, sc, T, traj_id0=7, chunk=48):
+        assert np.array_equal(res["clean"], one["clean"][lo:hi]) and np.array_equal(res["U"], one["U"][lo:hi])
+        seen.append((lo, hi))
+    assert seen == [(0, 48), (48, 96), (96, 100)]
+    a, b = str(tmp_path / "c1.csv"), str(tmp_path / "n1.csv")
+    tg.write_csv(one, 0.01, a, b, traj_id0=7)
+    a2, b2 = str(tmp_path / "c2.csv"), str(tmp_path / "n2.csv")
+    r = gen.generate_to_csv(x0, u0, sc, T, a2, b2, traj_id0=7, chunk=32, keep=True)
+    assert open(a).read() == open(a2).read() and open(b).read() == open(b2).read()
+    assert np.array_equal(r["clean"], one["clean"]) and np.array_equal(r["status_counts"], one["status_counts"])
+    # CSV for the first ids only (BASELINE config 5), the rest binary
+    a3, b3 = str(tmp_path / "c3.csv"), str(tmp_path / "n3.csv")
+    gen.generate_to_csv(x0, u0, sc, T, a3, b3, traj_id0=7, chunk=32, csv_ids=40)
+    tg.write_csv({k: v[:40] for k, v in one.items()}, 0.01, a, b, traj_id0=7)
+    assert open(a).read() == open(a3).read() and open(b).read() == open(b3).read()

@@ -6,7 +6,10 @@ import bench
 import trajectory_generation_b200 as tg
 from trajectory_generation_b200 import _lib
 B, T = int(sys.argv[1]), int(sys.argv[2])
-gen = tg.ClosedLoopGenerator(**bench.GEN_KW)
+kw = dict(bench.GEN_KW)
+if len(sys.argv) > 3:
+    kw["N"] = int(sys.argv[3])
+gen = tg.ClosedLoopGenerator(**kw)
 x0, u0, sc = bench.make_workload(gen, B)
 gen.generate(x0, u0, sc, 5)
 L = _lib.load()

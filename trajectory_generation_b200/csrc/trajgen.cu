@@ -79,7 +79,7 @@ tw_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ WLa
     asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));   // kept in registers instead of being re-derived at every use
     const int bar = 1 + prob;
     double *sm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm_all) + sm_off);
-    const int N = NC > 0 ? NC : c.N, n = 2 * N, ms = c.ms;
+    const int N = NC > 0 ? NC : c.N, n = 2 * N, ms = NC > 0 ? 0 : c.ms;
     if (prob >= P) return;
     const TwMap<S> mp = tw_make_map<W, S>(LF(nb), tid);
     for (int b0 = blockIdx.x * P; b0 < a.B; b0 += gridDim.x * P) {
@@ -176,7 +176,7 @@ tw_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
     asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));
     const int bar = 1 + prob;
     double *sm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm_all) + sm_off);
-    const int N = NC > 0 ? NC : c.N, n = 2 * N, ms = c.ms, ns = c.ns, T = a.T;
+    const int N = NC > 0 ? NC : c.N, n = 2 * N, ms = NC > 0 ? 0 : c.ms, ns = NC > 0 ? 0 : c.ns, T = a.T;
     if (prob >= P) return;
     const TwMap<S> mp = tw_make_map<W, S>(LF(nb), tid);
     const StepTaps tap = {};
@@ -441,10 +441,10 @@ static bool pick_tw_shape(int N, int &W, int &S)
 // kernel instances: (W, S) for a run-time horizon, plus the horizons of the BASELINE configurations compiled in (NC = N:
 // shared-memory offsets become immediates, horizon loops get constant trip counts)
 template <typename F>
-static int dispatch_tw(int W, int S, int N, F &&f)
+static int dispatch_tw(int W, int S, int N, bool has_state_rows, F &&f)
 {
     using std::integral_constant;
-    if (W == 2 && S == 1 && N == 20 && !getenv("TRAJGEN_DYNAMIC_N")) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 20>());
+    if (W == 2 && S == 1 && N == 20 && !has_state_rows && !getenv("TRAJGEN_DYNAMIC_N")) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 20>());
     if (W == 1 && S == 1) return f(integral_constant<int, 1>(), integral_constant<int, 1>(), integral_constant<int, 0>());
     if (W == 2 && S == 1) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 0>());
 #ifndef TG_DEV_SHAPES_ONLY
@@ -563,7 +563,7 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
         while (h->ppc_max > 1 && (size_t)h->ppc_max * stride > h->smem_optin) h->ppc_max -= 1;
         if (const char *e = getenv("TRAJGEN_PPC")) { const int v = atoi(e); if (v >= 1 && v <= h->ppc_max) h->ppc_env = v; }
         int occ = 0;
-        int rc = dispatch_tw(h->W, h->S, d.N, [&](auto W_, auto S_, auto NC_) -> int {
+        int rc = dispatch_tw(h->W, h->S, d.N, d.ms > 0, [&](auto W_, auto S_, auto NC_) -> int {
             constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
             // the attribute is per kernel function and process-wide: always raise it to the device limit so that handles with
             // different layouts can be used side by side
@@ -662,7 +662,7 @@ static int launch_step(tg_handle *h, StepArgs &a)
 {
     if (a.B <= 0) return TG_OK;   // empty batch: nothing to do
     CK(cudaSetDevice(h->device));
-    return dispatch_tw(h->W, h->S, h->dc.N, [&](auto W_, auto S_, auto NC_) -> int {
+    return dispatch_tw(h->W, h->S, h->dc.N, h->dc.ms > 0, [&](auto W_, auto S_, auto NC_) -> int {
         constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
         return launch_tw(h, tw_mpc_step_kernel<W, S, NC>, a, a.B, W);
     });
@@ -744,7 +744,7 @@ int tg_closed_loop(tg_handle *h, int B, int T, const double *x0, const double *u
     memset(&a, 0, sizeof(a));
     a.B = B; a.T = T; a.x0 = x0; a.u0 = u0; a.spec = spec; a.brk = brk; a.coef = coef; a.traj_id0 = traj_id0;
     a.clean = clean; a.noisy = noisy; a.U = U; a.status_counts = status_counts; a.iters_total = (long long *)iters_total;
-    return dispatch_tw(h->W, h->S, h->dc.N, [&](auto W_, auto S_, auto NC_) -> int {
+    return dispatch_tw(h->W, h->S, h->dc.N, h->dc.ms > 0, [&](auto W_, auto S_, auto NC_) -> int {
         constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
         return launch_tw(h, tw_closed_loop_kernel<W, S, NC>, a, B, W);
     });

@@ -15,6 +15,7 @@
 // the block partials exchanged through shared memory.  The ADMM vectors live in shared memory, lane t owns stage t (the
 // entries 2t, 2t+1 of dU and its two box and two rate rows).
 #pragma once
+#include <type_traits>
 #include "tg_device.cuh"
 
 // optional phase timing (development): -DTG_PHASE_TIMING accumulates clock64 deltas of CTA 0 / thread 0 per phase
@@ -68,11 +69,18 @@ struct WLayout {
     int aux, Xr, Yr, Pr, vref, P;   // inside the wb region (dead before / after K2)
     int dH, dsc;                    // dH aliases v, dsc aliases xt
     int NV, nb, nbuf;
-    int zs, ys, rhos, rinvs, ls, us, zts, dys, Gs;   // tail: state rows (ms each; Gs ms x NV)
+    int zs, ys, rhos, rinvs, ls, us, zts, dys, tv, gt, Gs;   // tail: state rows (ms each; tv ms; gt 3 NV; Gs packed, tw_gs_*)
     int total;
 };
 
 __host__ __device__ constexpr int tw_even(int v) { return (v + 1) & ~1; }   // keep 16-byte alignment
+
+// State-bound rows (mpc_6stati.py:216-221).  Row i = k ns + si is row sidx[si] of G_{k+1} (k = 0 .. N-1); it vanishes in the
+// columns >= 2 (k + 1) (inputs that come later), so the rows are stored PACKED: the ns rows of stage k have length
+// len_k = 4 ceil((k + 1) / 2) (zero-padded to whole 4-blocks of the tile) and start at ns off_k, off_k = sum_{k' < k} len_k'.
+// Half the dense ms x NV block: N = 50 with two bounded states is 41 KB instead of 80 KB.
+__host__ __device__ constexpr int tw_gs_len(int k) { return 4 * ((k >> 1) + 1); }
+__host__ __device__ constexpr int tw_gs_off(int k) { return 4 * (k >> 1) * ((k >> 1) + 1) + ((k & 1) ? 4 * ((k >> 1) + 1) : 0); }
 
 __host__ __device__ constexpr WLayout tw_make_layout(int N, int ms, int W)
 {
@@ -87,7 +95,7 @@ __host__ __device__ constexpr WLayout tw_make_layout(int N, int ms, int W)
     L.q = o; o += NV; L.x = o; o += NV; L.xt = o; o += NV; L.v = o; o += NV;
     L.z = o; o += 2 * NV; L.y = o; o += 2 * NV; L.rho = o; o += 2 * NV + 2; L.rinv = o; o += 2 * NV + 2;   // box rows, then rate rows at + n
     L.dyr = o; o += NV + 2;
-    L.piv = o; o += 2 * (NV + 2);
+    L.piv = o; o += 2 * (4 * NV + 16);   // two panel buffers of the blocked sweep (4 columns of NV + the 4 x 4 inverse)
     int wbn = L.nbuf * TW_KB * 3 * NV;
     if (wbn < nb * nb * 4) wbn = nb * nb * 4;
     const int k1n = tw_even(6 * N) + 4 * tw_even(N + 2);
@@ -100,7 +108,8 @@ __host__ __device__ constexpr WLayout tw_make_layout(int N, int ms, int W)
     const int mse = tw_even(ms);
     L.zs = o; o += mse; L.ys = o; o += mse; L.rhos = o; o += mse; L.rinvs = o; o += mse;
     L.ls = o; o += mse; L.us = o; o += mse; L.zts = o; o += mse; L.dys = o; o += mse;
-    L.Gs = o; o += ms * NV;
+    L.tv = o; o += mse; L.gt = o; o += (ms > 0 ? 3 * NV : 0);
+    L.Gs = o; o += (ms > 0 ? (ms / N) * tw_gs_off(N) : 0);
     L.total = o;
     return L;
 }
@@ -309,7 +318,7 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
                                             bool first, int tid, int bar)
 {
     constexpr int NT = 32 * W;
-    const int N = NC > 0 ? NC : c.N, n = 2 * N, NV = LF(NV), ns = c.ns;
+    const int N = NC > 0 ? NC : c.N, n = 2 * N, NV = LF(NV), ns = NC > 0 ? 0 : c.ns, ms_ = NC > 0 ? 0 : c.ms;   // compile-time horizons: no state rows
     const double *lin = sm + LF(lin), *sn = sm + LF(sn), *cs = sm + LF(cs), *rr = sm + LF(rr);
     double *wbuf = sm + LF(wb), *Gs = sm + L.Gs;
     const double sqp = sqrt(2.0 * c.q_phi), sqv = sqrt(2.0 * c.q_vx);
@@ -329,10 +338,14 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
     if (NV > n) {   // pad columns of the staging rows (and of the state rows) must read as zero
         const int np = (NV - n) > 0 ? NV - n : 1;
         for (int i = tid; i < LF(nbuf) * TW_KB * 3 * np; i += NT) wbuf[(i / np) * NV + n + i % np] = 0.0;
-        if (first)
-            for (int i = tid; i < c.ms * np; i += NT) Gs[(i / np) * NV + n + i % np] = 0.0;
         tw_sync<W>(bar);
     }
+    if (first)   // zero pads of the packed state rows (len_k - 2 (k + 1) = 0 or 2 entries per row)
+        for (int i = tid; i < ms_; i += NT) {
+            const int k = i / (ns > 0 ? ns : 1), si = i - k * ns;
+            double *row = Gs + ns * tw_gs_off(k) + si * tw_gs_len(k);
+            for (int j = 2 * (k + 1); j < tw_gs_len(k); ++j) row[j] = 0.0;
+        }
 #pragma unroll 1
     for (int k0 = 0; k0 < N; k0 += TW_KB) {
         const int kb = (N - k0 < TW_KB) ? N - k0 : TW_KB;
@@ -365,19 +378,18 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
                     wrow[j] = wc; wrow[NV + j] = wp; wrow[2 * NV + j] = wv;
                     if (first) {
                         qacc[p] = fma(rr[3 * kk], wc, fma(rr[3 * kk + 1], wp, fma(rr[3 * kk + 2], wv, qacc[p])));
-                        for (int si = 0; si < ns; ++si) {
-                            const int sx = c.sidx[si];
-                            const double gv = (sx == 0) ? n0 : (sx == 1) ? n1 : (sx == 2) ? n2 : (sx == 3) ? n3 : (sx == 4) ? n4 : n5;
-                            Gs[(k * ns + si) * NV + j] = gv;
-                        }
+                        if (jb <= k)
+                            for (int si = 0; si < ns; ++si) {
+                                const int sx = c.sidx[si];
+                                const double gv = (sx == 0) ? n0 : (sx == 1) ? n1 : (sx == 2) ? n2 : (sx == 3) ? n3 : (sx == 4) ? n4 : n5;
+                                Gs[ns * tw_gs_off(k) + si * tw_gs_len(k) + j] = gv;
+                            }
                     }
                 }
             } else if (j < n) {   // not born in this block of stages: its W entries are zero
                 for (int s_i = 0; s_i < kb; ++s_i) {
                     double *wrow = wblk + s_i * 3 * NV;
                     wrow[j] = 0.0; wrow[NV + j] = 0.0; wrow[2 * NV + j] = 0.0;
-                    if (first)
-                        for (int si = 0; si < ns; ++si) Gs[((k0 + s_i) * ns + si) * NV + j] = 0.0;
                 }
             }
         }
@@ -467,21 +479,100 @@ __device__ __forceinline__ void tw_build_K(const DevCfg &c, const WLayout &L, co
         }
     }
     const double *Gs = sm + L.Gs;
-    for (int i = 0; i < c.ms; ++i) {
-        const double rs = rho_s[i];
+    const int ns = NC > 0 ? 0 : c.ns, N = NC > 0 ? NC : c.N;
+    if (ns > 0)
+        for (int k = 0; k < N; ++k) {
+            const int len = tw_gs_len(k);
+            for (int si = 0; si < ns; ++si) {
+                const double rs = rho_s[k * ns + si];
+                const double *row = Gs + ns * tw_gs_off(k) + si * len;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            double gr[4], gc[4];
-            tw_ld4(Gs + i * NV + mp.ro[s], gr);
-            tw_ld4(Gs + i * NV + mp.co[s], gc);
+                for (int s = 0; s < S; ++s) {
+                    if (mp.ro[s] < len) {   // the row vanishes beyond column 2 (k + 1) <= len (co <= ro)
+                        double gr[4], gc[4];
+                        tw_ld4(row + mp.ro[s], gr);
+                        tw_ld4(row + mp.co[s], gc);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const double t = gr[r] * rs;
+                        for (int r = 0; r < 4; ++r) {
+                            const double t = gr[r] * rs;
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) a[s][r][cc] = fma(t, gc[cc], a[s][r][cc]);
+                            for (int cc = 0; cc < 4; ++cc) a[s][r][cc] = fma(t, gc[cc], a[s][r][cc]);
+                        }
+                    }
+                }
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------- state-row products (ms > 0)
+// Thread geometry of the two products with the packed state rows, chosen once per step: NG threads (a power of two, lanes of
+// one warp) share a column pair in G_s' v, TPR threads share a row in G_s x.
+struct TwGsGeo { int ng, lg_ng, tpr, lg_tpr; };
+template <int W>
+__device__ __forceinline__ TwGsGeo tw_gs_geo(int N, int ms)
+{
+    constexpr int NT = 32 * W;
+    TwGsGeo g; g.ng = 1; g.lg_ng = 0; g.tpr = 1; g.lg_tpr = 0;
+    while (g.ng * 2 * N <= NT && g.ng < 8) { g.ng *= 2; g.lg_ng += 1; }
+    while (g.tpr * 2 * ms <= NT && g.tpr < 4) { g.tpr *= 2; g.lg_tpr += 1; }
+    return g;
+}
+// gt[v NV + j] = sum_i Gs[i][j] vec_v[i] for v < NVEC and every column j < n, by all threads of the problem: thread (jp, g)
+// sums the stages k = jp + g, jp + g + NG, ... (rows of earlier stages vanish in column pair jp), then the NG partials are
+// folded with shuffles.  The caller synchronises before reading gt.
+template <int W, int NVEC>
+__device__ __forceinline__ void tw_gs_tmul(const WLayout &L, double *sm, const TwGsGeo &geo, int N, int ns, int NV,
+                                           const double *const (&vec)[NVEC], int tid)
+{
+    const double *Gs = sm + L.Gs;
+    double *gt = sm + L.gt;
+    const int jp = tid >> geo.lg_ng, g = tid & (geo.ng - 1);
+    double a0[NVEC], a1[NVEC];
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) { a0[v] = 0.0; a1[v] = 0.0; }
+    if (jp < N) {
+        for (int k = jp + g; k < N; k += geo.ng) {
+            const int len = tw_gs_len(k);
+            const double *row = Gs + ns * tw_gs_off(k) + 2 * jp;
+            for (int si = 0; si < ns; ++si) {
+                const double2 g2 = tw_ld2(row + si * len);
+#pragma unroll
+                for (int v = 0; v < NVEC; ++v) {
+                    const double t = vec[v][k * ns + si];
+                    a0[v] = fma(g2.x, t, a0[v]); a1[v] = fma(g2.y, t, a1[v]);
+                }
             }
         }
     }
+    for (int o = geo.ng >> 1; o > 0; o >>= 1)
+#pragma unroll
+        for (int v = 0; v < NVEC; ++v) { a0[v] += __shfl_xor_sync(0xffffffffu, a0[v], o); a1[v] += __shfl_xor_sync(0xffffffffu, a1[v], o); }
+    if (jp < N && g == 0)
+#pragma unroll
+        for (int v = 0; v < NVEC; ++v) tw_st2(gt + v * NV + 2 * jp, a0[v], a1[v]);
+}
+// (G_s x)_r for the row r = r0 + (tid >> lg_tpr) (0 if r >= ms), summed over the TPR threads of the row; every thread of the
+// problem must call it (shuffles)
+template <int W>
+__device__ __forceinline__ double tw_gs_row_dot(const WLayout &L, const double *sm, const TwGsGeo &geo, int ns, int ms, const double *x,
+                                                int r, int tid)
+{
+    const double *Gs = sm + L.Gs;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (r < ms) {
+        const int k = r / ns, si = r - k * ns, h = tid & (geo.tpr - 1);
+        const double *row = Gs + ns * tw_gs_off(k) + si * tw_gs_len(k);
+        int d = h;
+        for (; d + geo.tpr <= k; d += 2 * geo.tpr) {   // column pairs d and d + TPR (both <= k)
+            const double2 ga = tw_ld2(row + 2 * d), xa = tw_ld2(x + 2 * d);
+            const double2 gb = tw_ld2(row + 2 * (d + geo.tpr)), xb = tw_ld2(x + 2 * (d + geo.tpr));
+            s0 = fma(ga.x, xa.x, s0); s1 = fma(ga.y, xa.y, s1); s2 = fma(gb.x, xb.x, s2); s3 = fma(gb.y, xb.y, s3);
+        }
+        if (d <= k) { const double2 ga = tw_ld2(row + 2 * d), xa = tw_ld2(x + 2 * d); s0 = fma(ga.x, xa.x, s0); s1 = fma(ga.y, xa.y, s1); }
+    }
+    double acc = (s0 + s1) + (s2 + s3);
+    for (int o = geo.tpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
 }
 
 // In-register inversion of the SPD tile by n symmetric sweeps (SWP_k: a_kk <- -1/a_kk, a_ik <- a_ik/a_kk,
@@ -492,8 +583,8 @@ __device__ __forceinline__ void tw_build_K(const DevCfg &c, const WLayout &L, co
 // K is Jacobi-scaled first (K^ = D K D, D = diag(K)^-1/2: the unpivoted sweep is only as accurate as cond(K), and K inherits
 // the variable scaling of H) and un-scaled afterwards.
 template <int W, int S, int NC>
-__device__ __forceinline__ void tw_sweep_invert(const DevCfg &c, const WLayout &L, double *sm, const TwMap<S> &mp,
-                                                double (&a)[S][4][4], int bar)
+__device__ __forceinline__ void tw_sweep_invert_scalar(const DevCfg &c, const WLayout &L, double *sm, const TwMap<S> &mp,
+                                                       double (&a)[S][4][4], int bar)
 {
     const int n = NC > 0 ? 2 * NC : c.n, NV = LF(NV), nb = LF(nb);
     double *vb = sm + LF(piv), *dsc = sm + LF(dsc);
@@ -580,6 +671,195 @@ __device__ __forceinline__ void tw_sweep_invert(const DevCfg &c, const WLayout &
     tw_sync<W>(bar);
 }
 
+// BLOCKED sweep: the four pivots of a 4 x 4 diagonal block at once (one synchronisation per block instead of four, and every
+// thread's work is 128 independent FMAs instead of four dependent rank-1 rounds).  Sweeping the index set P of block K:
+//     A_PP <- -D^-1 (D = A_PP),   A_iP <- A_iP D^-1,   A_ij <- A_ij - A_iP D^-1 A_Pj.
+// The panel V = A_.P (n x 4) is published column-wise (VT[m][i] = A_{i, P_m}; block column K below the diagonal, block row K
+// left of it by symmetry), with D - I in the rows of P itself, and the owner of the diagonal block publishes D^-1 (inverted in
+// its registers).  With that patch every block (I, J) -- panel blocks included -- does the same update
+//     A_IJ <- A_IJ - (V_I D^-1) V_J',
+// and only the diagonal block is repaired afterwards (<- -D^-1).  The panel and the inverse of block K + 1 are published
+// right after a thread's update of step K, into the buffer of the other parity.
+#ifndef TW_SWEEP_PB
+#define TW_SWEEP_PB 1    // pivots per synchronisation of the sweep (1 = scalar sweep, 2 or 4 = blocked; measured: DESIGN.md section 8)
+#endif
+// inverse of the PB x PB SPD block d[o .. o+PB-1][o .. o+PB-1] (PB = 2: closed form; PB = 4: four scalar sweeps in registers)
+template <int PB>
+__device__ __forceinline__ void tw_inv_spd(const double (&a)[4][4], int o_static, double (&di)[PB][PB]);
+template <>
+__device__ __forceinline__ void tw_inv_spd<2>(const double (&a)[4][4], int o, double (&di)[2][2])
+{
+    const double a00 = o ? a[2][2] : a[0][0], a01 = o ? a[3][2] : a[1][0], a11 = o ? a[3][3] : a[1][1];
+    const double r = tw_rcp3(fma(a00, a11, -a01 * a01));   // SPD: det > 0
+    di[0][0] = a11 * r; di[1][1] = a00 * r; di[0][1] = -a01 * r; di[1][0] = di[0][1];
+}
+template <>
+__device__ __forceinline__ void tw_inv_spd<4>(const double (&a)[4][4], int, double (&di)[4][4])
+{
+    double d[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[i][j] = a[i][j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double p = tw_rcp3(d[k][k]);   // Schur complements of an SPD matrix: pivots > 0
+        double w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = d[i][k] * p;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i != k && j != k) d[i][j] = fma(-w[i], d[k][j], d[i][j]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i != k) { d[i][k] = w[i]; d[k][i] = w[i]; }
+        d[k][k] = -p;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) di[i][j] = -d[i][j];
+}
+
+template <int W, int S, int NC>
+__device__ __forceinline__ void tw_sweep_invert(const DevCfg &c, const WLayout &L, double *sm, const TwMap<S> &mp,
+                                                double (&a)[S][4][4], int bar)
+{
+    constexpr int PB = TW_SWEEP_PB;
+    if constexpr (PB == 1 || (S > 1 && PB == 4)) {   // (two tiles per thread leave no registers for the 4-pivot block operands)
+        tw_sweep_invert_scalar<W, S, NC>(c, L, sm, mp, a, bar);
+        return;
+    } else {
+    constexpr int NH = 4 / PB;   // pivot groups per 4 x 4 block
+    const int n = NC > 0 ? 2 * NC : c.n, NV = LF(NV), nb = LF(nb);
+    double *vb = sm + LF(piv), *dsc = sm + LF(dsc);
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+        if (mp.act[s] && mp.ro[s] == mp.co[s])
+            tw_st4(dsc + mp.ro[s], (mp.ro[s] + 0 < n) ? rsqrt(a[s][0][0]) : 0.0, (mp.ro[s] + 1 < n) ? rsqrt(a[s][1][1]) : 0.0,
+                   (mp.ro[s] + 2 < n) ? rsqrt(a[s][2][2]) : 0.0, (mp.ro[s] + 3 < n) ? rsqrt(a[s][3][3]) : 0.0);
+    tw_sync<W>(bar);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        double dr[4], dc[4];
+        tw_ld4(dsc + mp.ro[s], dr);
+        tw_ld4(dsc + mp.co[s], dc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) a[s][r][cc] *= dr[r] * dc[cc];
+        if (mp.ro[s] == mp.co[s])   // pad rows (odd horizons) become identity rows: they pass through the block inverse unchanged
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (mp.ro[s] + r >= n) a[s][r][r] = 1.0;
+    }
+    // panel buffer of one pivot group: PB columns of NV (VT[m][i] = A_{i, P_m}) + the PB x PB inverse; two buffers, alternating
+    const unsigned vb_a = tw_saddr(vb), stride_a = (unsigned)(PB * NV + PB * PB) * 8u, nv8 = (unsigned)NV * 8u, dinv_o = (unsigned)PB * nv8;
+    unsigned ro_a[S], co_a[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { ro_a[s] = vb_a + 8u * (unsigned)mp.ro[s]; co_a[s] = vb_a + 8u * (unsigned)mp.co[s]; }
+    // publish the panel of pivot group h (compile-time) of block K4 into the buffer at boff
+    auto publish = [&](int K4, auto h_, unsigned boff) {
+        constexpr int h = decltype(h_)::value, o = h * PB;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            if (mp.act[s]) {
+                if (mp.ro[s] == K4) {
+                    if (mp.co[s] == K4) {   // diagonal block: D - I in the pivot rows, D^-1 beside the panel
+                        double di[PB][PB];
+                        tw_inv_spd<PB>(a[s], o, di);
+#pragma unroll
+                        for (int m = 0; m < PB; ++m) {
+                            tw_sts4(ro_a[s] + boff + (unsigned)m * nv8, a[s][0][o + m] - (o + m == 0 ? 1.0 : 0.0), a[s][1][o + m] - (o + m == 1 ? 1.0 : 0.0),
+                                    a[s][2][o + m] - (o + m == 2 ? 1.0 : 0.0), a[s][3][o + m] - (o + m == 3 ? 1.0 : 0.0));
+#pragma unroll
+                            for (int q = 0; q < PB; ++q) tw_sts1(vb_a + boff + dinv_o + 8u * (unsigned)(m * PB + q), di[m][q]);
+                        }
+                    } else {                // block row K left of the diagonal: V_{j, m} = a[o + m][j]
+#pragma unroll
+                        for (int m = 0; m < PB; ++m) tw_sts4(co_a[s] + boff + (unsigned)m * nv8, a[s][o + m][0], a[s][o + m][1], a[s][o + m][2], a[s][o + m][3]);
+                    }
+                } else if (mp.co[s] == K4) {   // block column K below the diagonal: V_{i, m} = a[i][o + m]
+#pragma unroll
+                    for (int m = 0; m < PB; ++m) tw_sts4(ro_a[s] + boff + (unsigned)m * nv8, a[s][0][o + m], a[s][1][o + m], a[s][2][o + m], a[s][3][o + m]);
+                }
+            }
+        }
+    };
+    // one pivot group: A_IJ <- A_IJ - (V_I D^-1) V_J' for every block, then the pivot sub-block of the diagonal block <- -D^-1
+    auto update = [&](int K4, auto h_, unsigned boff) {
+        constexpr int h = decltype(h_)::value, o = h * PB;
+        double di[PB][PB];
+#pragma unroll
+        for (int m = 0; m < PB; ++m)
+#pragma unroll
+            for (int q = 0; q < PB; ++q) di[m][q] = tw_lds1(vb_a + boff + dinv_o + 8u * (unsigned)(m * PB + q));
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            double vi[PB][4];
+#pragma unroll
+            for (int m = 0; m < PB; ++m) tw_lds4(ro_a[s] + boff + (unsigned)m * nv8, vi[m]);
+#pragma unroll
+            for (int q = 0; q < PB; ++q) {
+                double vj[4], w[4];
+                tw_lds4(co_a[s] + boff + (unsigned)q * nv8, vj);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    double t = vi[0][r] * di[0][q];
+#pragma unroll
+                    for (int m = 1; m < PB; ++m) t = fma(vi[m][r], di[m][q], t);
+                    w[r] = t;
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) a[s][r][cc] = fma(-w[r], vj[cc], a[s][r][cc]);
+            }
+            if (mp.ro[s] == K4 && mp.co[s] == K4) {
+#pragma unroll
+                for (int m = 0; m < PB; ++m)
+#pragma unroll
+                    for (int q = 0; q < PB; ++q) a[s][o + m][o + q] = -di[m][q];
+            }
+        }
+    };
+    using std::integral_constant;
+    publish(0, integral_constant<int, 0>(), 0u);
+#pragma unroll 1
+    for (int K = 0; K < nb; ++K) {
+        const int K4 = 4 * K;
+        // NH pivot groups per block; the buffer alternates with every group (NH is 1 or 2, so group h of block K uses buffer
+        // (K NH + h) & 1)
+        if constexpr (NH == 2) {
+            tw_sync<W>(bar);
+            update(K4, integral_constant<int, 0>(), 0u);
+            publish(K4, integral_constant<int, 1>(), stride_a);
+            tw_sync<W>(bar);
+            update(K4, integral_constant<int, 1>(), stride_a);
+            if (K + 1 < nb) publish(K4 + 4, integral_constant<int, 0>(), 0u);
+        } else {
+            const unsigned boff = (K & 1) ? stride_a : 0u;
+            tw_sync<W>(bar);
+            update(K4, integral_constant<int, 0>(), boff);
+            if (K + 1 < nb) publish(K4 + 4, integral_constant<int, 0>(), (K & 1) ? 0u : stride_a);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {   // K^-1 = D K^^-1 D
+        double dr[4], dc[4];
+        tw_ld4(dsc + mp.ro[s], dr);
+        tw_ld4(dsc + mp.co[s], dc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) a[s][r][cc] *= dr[r] * dc[cc];
+    }
+    tw_sync<W>(bar);
+    }
+}
+
 // block partials of x~ = K^-1 v (a = -K^-1): P[(seg * nb + other) * 4 + r]; summed per entry by tw_matvec_sum
 template <int W, int S, int NC>
 __device__ __forceinline__ void tw_matvec_partials(const WLayout &L, double *sm, const TwMap<S> &mp, const double (&a)[S][4][4])
@@ -632,7 +912,7 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
 {
     constexpr int NT = 32 * W;
     constexpr int NPASS = (W == 1 && S >= 2) ? 2 : 1;
-    const int N = NC > 0 ? NC : c.N, n = 2 * N, NV = LF(NV), ms = c.ms, ns = c.ns;
+    const int N = NC > 0 ? NC : c.N, n = 2 * N, NV = LF(NV), ms = NC > 0 ? 0 : c.ms, ns = NC > 0 ? 0 : c.ns;   // kernels with a compile-time horizon serve configurations without state-bound rows
     StepResult res;
     res.status = TG_STATUS_NAN; res.iters = 0; res.objective = 0.0; res.free_end = false;
 
@@ -642,6 +922,8 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
     double *z = sm + LF(z), *y = sm + LF(y), *rho = sm + LF(rho), *rinv = sm + LF(rinv), *dyr = sm + LF(dyr);
     double *zs = sm + L.zs, *ys = sm + L.ys, *rhos = sm + L.rhos, *rinvs = sm + L.rinvs;     // state rows (tail of the layout)
     double *ls = sm + L.ls, *us = sm + L.us, *zts = sm + L.zts, *dys = sm + L.dys, *Gs = sm + L.Gs, *red = sm + LF(red);
+    double *tv = sm + L.tv, *gt = sm + L.gt;
+    const TwGsGeo geo = tw_gs_geo<W>(N, ms);
     TG_TICK_DECL;
 
     // ---------------- K1a: reference window + sensor noise of the row (closed loop), nominal rollout (mpc_6stati.py:167-172)
@@ -805,12 +1087,13 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
                 tw_st2(rinv + n + j0, 1.0 / (rho_scale * g0), 1.0 / (rho_scale * g1));
             }
             for (int i = tid; i < ms; i += NT) {
-                const int kk = i / ns + 1, sx = c.sidx[i % ns];
+                const int nsd = ns > 0 ? ns : 1, kk = i / nsd + 1, sx = c.sidx[i % nsd];
                 const double xb = xbar[6 * kk + sx];
                 ls[i] = (c.x_lo[sx] <= -TG_INF) ? -TG_INF : c.x_lo[sx] - xb;
                 us[i] = (c.x_hi[sx] >= TG_INF) ? TG_INF : c.x_hi[sx] - xb;
                 double mx = 0.0;
-                for (int j = 0; j < n; ++j) { const double gij = Gs[i * NV + j]; mx = fmax(mx, gij * gij / dH[j]); }
+                const double *grow = Gs + ns * tw_gs_off(kk - 1) + (i % nsd) * tw_gs_len(kk - 1);
+                for (int j = 0; j < 2 * kk; ++j) { const double gij = grow[j]; mx = fmax(mx, gij * gij / dH[j]); }
                 const double rs = rho_scale * ((mx > 1e-30) ? 1.0 / mx : 1.0);
                 rhos[i] = rs; rinvs[i] = 1.0 / rs;
             }
@@ -843,7 +1126,11 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
                 }
                 for (int i = tid; i < ms; i += NT) { tap.l[2 * n + i] = ls[i]; tap.u[2 * n + i] = us[i]; }
             }
-            if (tap.Gs) for (int i = tid; i < ms * n; i += NT) tap.Gs[i] = Gs[(i / n) * NV + (i % n)];
+            if (tap.Gs)
+                for (int i = tid; i < ms * n; i += NT) {
+                    const int nsd = ns > 0 ? ns : 1, r_ = i / n, j = i % n, k = r_ / nsd;
+                    tap.Gs[i] = (j < 2 * (k + 1)) ? Gs[ns * tw_gs_off(k) + (r_ % nsd) * tw_gs_len(k) + j] : 0.0;
+                }
             if (tap.stop == 2) return res;
             TG_TICK(3);
         }
@@ -863,12 +1150,16 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
                     tw_st2(z + j0, tg_clamp(xj.x, lb0, ub0), tg_clamp(xj.y, lb1, ub1));
                     tw_st2(z + n + j0, tg_clamp(xj.x - xp.x, c.du_lo[0], c.du_hi[0]), tg_clamp(xj.y - xp.y, c.du_lo[1], c.du_hi[1]));
                 }
-                for (int i = tid; i < ms; i += NT) {
-                    double acc = 0.0;
-                    for (int j = 0; j < n; ++j) acc = fma(Gs[i * NV + j], x[j], acc);
-                    zs[i] = tg_clamp(acc, ls[i], us[i]);
+                for (int r0 = 0; r0 < ms; r0 += NT >> geo.lg_tpr) {
+                    const int r_ = r0 + (tid >> geo.lg_tpr);
+                    const double acc = tw_gs_row_dot<W>(L, sm, geo, ns, ms, x, r_, tid);
+                    if (r_ < ms && (tid & (geo.tpr - 1)) == 0) zs[r_] = tg_clamp(acc, ls[r_], us[r_]);
                 }
             }
+            tw_sync<W>(bar);
+        }
+        if (ms > 0) {   // t = rho_s z_s - y_s for the first right-hand side of this factorisation
+            for (int i = tid; i < ms; i += NT) tv[i] = rhos[i] * zs[i] - ys[i];
             tw_sync<W>(bar);
         }
         first = false;
@@ -884,10 +1175,15 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
             if (warm && !free_mode && it == TW_WARM_RESTART_ITER) {
                 // a warm start that has not converged by now is a bad start (the active set changed): restart from zero
                 if (my) { tw_st2(x + j0, 0.0, 0.0); tw_st2(z + j0, 0.0, 0.0); tw_st2(z + n + j0, 0.0, 0.0); tw_st2(y + j0, 0.0, 0.0); tw_st2(y + n + j0, 0.0, 0.0); }
-                for (int i = tid; i < ms; i += NT) { zs[i] = 0.0; ys[i] = 0.0; }
+                for (int i = tid; i < ms; i += NT) { zs[i] = 0.0; ys[i] = 0.0; tv[i] = 0.0; }
                 tw_sync<W>(bar);
             }
             // (a) rhs = sigma x - q + A'(rho z - y)
+            if (ms > 0) {   // state rows: G_s' (rho_s z_s - y_s) by all threads
+                const double *const vec1[1] = {tv};
+                tw_gs_tmul<W, 1>(L, sm, geo, N, ns, NV, vec1, tid);
+                tw_sync<W>(bar);
+            }
             double2 rhs2 = make_double2(0.0, 0.0);
             if (my) {
                 const double2 x2 = tw_ld2(x + j0), q2 = tw_ld2(q + j0);
@@ -899,11 +1195,7 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
                     const double2 zn_ = tw_ld2(z + n + j0 + 2), yn_ = tw_ld2(y + n + j0 + 2), rn_ = tw_ld2(rho + n + j0 + 2);
                     r0 -= rn_.x * zn_.x - yn_.x; r1 -= rn_.y * zn_.y - yn_.y;
                 }
-                for (int i = 0; i < ms; ++i) {
-                    const double t = rhos[i] * zs[i] - ys[i];
-                    const double2 g2 = tw_ld2(Gs + i * NV + j0);
-                    r0 = fma(g2.x, t, r0); r1 = fma(g2.y, t, r1);
-                }
+                if (ms > 0) { const double2 g2 = tw_ld2(gt + j0); r0 += g2.x; r1 += g2.y; }
                 rhs2 = make_double2(r0, r1);
                 tw_st2(v + j0, r0, r1);
             }
@@ -959,16 +1251,17 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
                     }
                 }
             }
-            for (int r_ = tid; r_ < ms; r_ += NT) {
-                double ztl = 0.0;
-                for (int j = 0; j < n; ++j) ztl = fma(Gs[r_ * NV + j], xt[j], ztl);
+            for (int r0 = 0; r0 < ms; r0 += NT >> geo.lg_tpr) {
+                const int r_ = r0 + (tid >> geo.lg_tpr);
+                const double ztl = tw_gs_row_dot<W>(L, sm, geo, ns, ms, xt, r_, tid);
+                if (r_ >= ms || (tid & (geo.tpr - 1)) != 0) continue;
                 const double zr = alpha * ztl + (1.0 - alpha) * zs[r_];
                 const double t_ = zr + ys[r_] * rinvs[r_];
                 const double zn = tg_clamp(t_, ls[r_], us[r_]);
                 const double yn = ys[r_] + rhos[r_] * (zr - zn);
                 clamped = clamped || zn != t_;
                 const double d_ = yn - ys[r_];
-                ys[r_] = yn; zs[r_] = zn;
+                ys[r_] = yn; zs[r_] = zn; tv[r_] = rhos[r_] * zn - yn;
                 rp = fmax(rp, fabs(ztl - zn)); nzt = fmax(nzt, fabs(ztl)); nz = fmax(nz, fabs(zn));
                 if (check) {
                     zts[r_] = ztl; dys[r_] = d_;
@@ -999,6 +1292,13 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
             // (d) residuals at (x~, z, y):  H x~ = rhs - sigma x~ - A'(rho .* z~)
             double rd = 0.0, nh = 0.0, na = 0.0, natdy = 0.0;
             bool bad = false;
+            if (ms > 0) {   // G_s' y_s, G_s' (rho_s z~_s), G_s' dy_s by all threads (zts is scaled in place: it is rewritten at the next check)
+                for (int i = tid; i < ms; i += NT) zts[i] *= rhos[i];
+                tw_sync<W>(bar);
+                const double *const vec3[3] = {ys, zts, dys};
+                tw_gs_tmul<W, 3>(L, sm, geo, N, ns, NV, vec3, tid);
+                tw_sync<W>(bar);
+            }
             if (my) {
                 const double2 yb = tw_ld2(y + j0), yr = tw_ld2(y + n + j0), rb = tw_ld2(rho + j0), rr2 = tw_ld2(rho + n + j0);
                 const double2 xp = (tid > 0) ? tw_ld2(xt + j0 - 2) : make_double2(0.0, 0.0);
@@ -1011,12 +1311,9 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
                     atr0 -= rn_.x * (xn_.x - xt2.x); atr1 -= rn_.y * (xn_.y - xt2.y);
                     atd0 -= dn_.x; atd1 -= dn_.y;
                 }
-                for (int i = 0; i < ms; ++i) {
-                    const double2 g2 = tw_ld2(Gs + i * NV + j0);
-                    const double yy = ys[i], rz = rhos[i] * zts[i], dd = dys[i];
-                    aty0 = fma(g2.x, yy, aty0); aty1 = fma(g2.y, yy, aty1);
-                    atr0 = fma(g2.x, rz, atr0); atr1 = fma(g2.y, rz, atr1);
-                    atd0 = fma(g2.x, dd, atd0); atd1 = fma(g2.y, dd, atd1);
+                if (ms > 0) {
+                    const double2 gy = tw_ld2(gt + j0), gr_ = tw_ld2(gt + NV + j0), gd = tw_ld2(gt + 2 * NV + j0);
+                    aty0 += gy.x; aty1 += gy.y; atr0 += gr_.x; atr1 += gr_.y; atd0 += gd.x; atd1 += gd.y;
                 }
                 const double2 q2 = tw_ld2(q + j0);
                 const double hx0 = rhs2.x - sigma * xt2.x - atr0, hx1 = rhs2.y - sigma * xt2.y - atr1;

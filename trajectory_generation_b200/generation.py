@@ -197,72 +197,123 @@ class ClosedLoopGenerator(BatchedMPC):
         return {"clean": mk((B, T + 1, 6)), "noisy": mk((B, T + 1, 6)), "U": mk((B, T, 2)),
                 "status_counts": np.zeros((B, _lib.TG_NUM_STATUS), np.int32), "iters_total": np.zeros(B, np.int64)}
 
-    def generate(self, x0, u0, scenarios, T, traj_id0=0, out=None, pinned=True):
+    #: generate() streams batches whose result rows exceed this many bytes through two page-locked chunk buffers
+    STREAM_BYTES = 1 << 30
+
+    def generate(self, x0, u0, scenarios, T, traj_id0=0, out=None, pinned=True, chunk=None):
         """x0[B,6], u0[B,2], scenarios (len B), T steps -> dict(clean[B,T+1,6], noisy[B,T+1,6], U[B,T,2],
         status_counts[B,6], iters_total[B]).  Row 0 of clean is x0; noise seed = base + traj_id0 + i.
         The result arrays are page-locked by default (``pinned``), so the kernel writes its rows straight into them
         while it runs (112 B per MPC step: far below what PCIe carries) and nothing is copied afterwards; ``out`` re-uses
-        the buffers of an earlier call (see ``alloc_result``)."""
+        the buffers of an earlier call (see ``alloc_result``).  Page-locking gigabytes takes longer than generating them, so
+        a batch whose rows exceed STREAM_BYTES (or any batch when ``chunk`` is given) is generated in chunks through two
+        cached page-locked chunk buffers (generate_chunks) and gathered into ordinary arrays by host threads while the next
+        chunk computes."""
         x0 = np.ascontiguousarray(np.asarray(x0, float).reshape(-1, 6))
-        B = x0.shape[0]
+        B, T = x0.shape[0], int(T)
         u0 = self._arr(np.asarray(u0, float).reshape(-1, 2), (B, 2))
         if len(scenarios) != B:
             raise ValueError("one scenario per trajectory required")
+        row_bytes = (2 * (T + 1) * 6 + T * 2) * 8
+        if out is None and (chunk is not None or (pinned and B * row_bytes > self.STREAM_BYTES)):
+            return self._generate_streamed(x0, u0, scenarios, T, traj_id0, chunk)
         spec = np.ascontiguousarray(scenarios.spec)
         brk, coef = scenarios.tables()
         if out is None:
-            out = self.alloc_result(B, int(T), pinned)
+            out = self.alloc_result(B, T, pinned)
         elif out["clean"].shape != (B, T + 1, 6) or out["U"].shape != (B, T, 2):
             raise ValueError("`out` was allocated for another batch size / horizon")
         _lib.check(_lib.load().tg_closed_loop_host(
-            self._h, B, int(T), _lib.ptr(x0), _lib.ptr(u0), spec.ctypes.data, _lib.ptr(brk) if len(brk) else None,
+            self._h, B, T, _lib.ptr(x0), _lib.ptr(u0), spec.ctypes.data, _lib.ptr(brk) if len(brk) else None,
             len(brk), _lib.ptr(coef) if len(coef) else None, len(coef), int(traj_id0),
             _lib.ptr(out["clean"]), _lib.ptr(out["noisy"]), _lib.ptr(out["U"]), _lib.ptr(out["status_counts"]),
             _lib.ptr(out["iters_total"])))
         return out
 
-    def generate_to_csv(self, x0, u0, scenarios, T, clean_path, noisy_path, traj_id0=0, chunk=8192, keep=False, n_threads=0):
-        """generate() in chunks of ``chunk`` trajectories with the dataset files written as it goes (the reference holds
-        every DataFrame in RAM and writes once at the end, generation_type2.py:166,216-218,319-322): while the GPU computes
-        chunk k + 1 into one set of pinned buffers, a host thread formats chunk k from the other (tg_write_csv, all cores,
-        appending).  Returns dict(status_counts[B,6], iters_total[B]) (+ the rows if ``keep``)."""
-        import threading
+    def _chunk_buffers(self, nb, T):
+        """two page-locked result sets for chunks of nb trajectories x T steps, cached on the generator"""
+        key = (int(nb), int(T))
+        if getattr(self, "_chunk_key", None) != key:
+            self._chunk_bufs = None                      # release the previous pair first
+            self._chunk_bufs = [self.alloc_result(nb, T), self.alloc_result(nb, T)]
+            self._chunk_key = key
+        return self._chunk_bufs
+
+    def generate_chunks(self, x0, u0, scenarios, T, traj_id0=0, chunk=None):
+        """Iterator over a large batch: yields (lo, hi, res) with res = the result dict of trajectories lo .. hi - 1 as views of
+        one of two page-locked chunk buffers.  The GPU computes chunk k + 1 (a host thread sits in tg_closed_loop_host, which
+        releases the GIL) while the caller consumes chunk k; a yielded view stays valid until the caller asks for the
+        next-but-one chunk.  ``chunk`` defaults to 8192 trajectories (1.1 GB of rows at T = 1200)."""
+        from concurrent.futures import ThreadPoolExecutor
         x0 = np.ascontiguousarray(np.asarray(x0, float).reshape(-1, 6))
         u0 = np.ascontiguousarray(np.asarray(u0, float).reshape(-1, 2))
         B, T = x0.shape[0], int(T)
-        bufs = [self.alloc_result(min(chunk, B), T) for _ in range(2 if B > chunk else 1)]
-        sc_all, it_all, kept = [], [], []
-        writer, err = None, []
+        chunk = int(chunk) if chunk else 8192
+        nb = min(chunk, B)
+        bufs = self._chunk_buffers(nb, T)
+        los = list(range(0, B, chunk))
 
-        def write(res, nb, first_id, append):
-            try:
-                write_csv({k: v[:nb] for k, v in res.items()}, self.cfg.Ts, clean_path, noisy_path, traj_id0=first_id, append=append,
-                          n_threads=n_threads)
-            except Exception as e:     # surfaced by the caller's thread below
-                err.append(e)
+        def run(k):
+            lo = los[k]; hi = min(lo + chunk, B)
+            res = {k_: v[:hi - lo] for k_, v in bufs[k % 2].items()}
+            ClosedLoopGenerator.generate(self, x0[lo:hi], u0[lo:hi], scenarios.slice(lo, hi), T, traj_id0 + lo, out=res)
+            return lo, hi, res
 
-        for k, lo in enumerate(range(0, B, chunk)):
-            hi = min(lo + chunk, B)
-            buf = bufs[k % len(bufs)]
-            res = buf if hi - lo == len(buf["clean"]) else self.alloc_result(hi - lo, T)
-            self.generate(x0[lo:hi], u0[lo:hi], scenarios.slice(lo, hi), T, traj_id0 + lo, out=res)
-            if writer is not None:
-                writer.join()                      # the previous chunk's buffers are free again after this
-            if err:
-                raise err[0]
-            sc_all.append(res["status_counts"].copy()); it_all.append(res["iters_total"].copy())
-            if keep:
-                kept.append({k_: res[k_].copy() for k_ in ("clean", "noisy", "U")})
-            writer = threading.Thread(target=write, args=(res, hi - lo, traj_id0 + lo, lo > 0))
-            writer.start()
-        if writer is not None:
-            writer.join()
-        if err:
-            raise err[0]
-        out = {"status_counts": np.concatenate(sc_all), "iters_total": np.concatenate(it_all)}
+        with ThreadPoolExecutor(1) as ex:
+            fut = ex.submit(run, 0)
+            for k in range(len(los)):
+                item = fut.result()
+                if k + 1 < len(los):
+                    fut = ex.submit(run, k + 1)          # into the buffer the caller released when it asked for this chunk
+                yield item
+
+    def _generate_streamed(self, x0, u0, scenarios, T, traj_id0, chunk, n_copy_threads=4):
+        from concurrent.futures import ThreadPoolExecutor
+        B = x0.shape[0]
+        out = self.alloc_result(B, T, pinned=False)
+        with ThreadPoolExecutor(n_copy_threads) as pool:
+            for lo, hi, res in self.generate_chunks(x0, u0, scenarios, T, traj_id0, chunk):
+                jobs = []
+                step = max(1, (hi - lo + n_copy_threads - 1) // n_copy_threads)
+                for a in range(0, hi - lo, step):        # ndarray copies release the GIL: first touch + copy on several cores
+                    b = min(a + step, hi - lo)
+                    for k_ in ("clean", "noisy", "U"):
+                        jobs.append(pool.submit(np.copyto, out[k_][lo + a:lo + b], res[k_][a:b]))
+                out["status_counts"][lo:hi] = res["status_counts"]; out["iters_total"][lo:hi] = res["iters_total"]
+                for j in jobs:
+                    j.result()
+        return out
+
+    def generate_to_csv(self, x0, u0, scenarios, T, clean_path, noisy_path, traj_id0=0, chunk=8192, keep=False, n_threads=0,
+                        csv_ids=None):
+        """generate() in chunks of ``chunk`` trajectories with the dataset files written as it goes (the reference holds
+        every DataFrame in RAM and writes once at the end, generation_type2.py:166,216-218,319-322): while the GPU computes
+        chunk k + 1 into one set of pinned buffers, the host formats chunk k from the other (tg_write_csv, all cores,
+        appending).  ``csv_ids``: write only the first csv_ids trajectories to the files (BASELINE config 5: CSV for the
+        first 5 000 ids, the rest stays binary).  Returns dict(status_counts[B,6], iters_total[B]) (+ the rows if ``keep``)."""
+        x0 = np.ascontiguousarray(np.asarray(x0, float).reshape(-1, 6))
+        B, T = x0.shape[0], int(T)
+        n_csv = B if csv_ids is None else min(int(csv_ids), B)
+        out = {"status_counts": np.zeros((B, _lib.TG_NUM_STATUS), np.int32), "iters_total": np.zeros(B, np.int64)}
         if keep:
-            for k_ in ("clean", "noisy", "U"):
-                out[k_] = np.concatenate([c[k_] for c in kept])
+            out.update({k_: v for k_, v in self.alloc_result(B, T, pinned=False).items() if k_ in ("clean", "noisy", "U")})
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(1) as writer:                # one writer: chunks are appended in order
+            pending = []
+            for lo, hi, res in self.generate_chunks(x0, u0, scenarios, T, traj_id0, chunk):
+                out["status_counts"][lo:hi] = res["status_counts"]; out["iters_total"][lo:hi] = res["iters_total"]
+                if keep:
+                    for k_ in ("clean", "noisy", "U"):
+                        np.copyto(out[k_][lo:hi], res[k_])
+                if lo < n_csv:
+                    # the rows leave the page-locked chunk buffer before they are formatted, so that the GPU gets the buffer back
+                    # at once and the text is produced beside the following chunks
+                    m = min(hi, n_csv) - lo
+                    rows = {k_: (out[k_][lo:lo + m] if keep else res[k_][:m].copy()) for k_ in ("clean", "noisy", "U")}
+                    pending.append(writer.submit(write_csv, rows, self.cfg.Ts, clean_path, noisy_path, traj_id0=traj_id0 + lo,
+                                                 append=lo > 0, n_threads=n_threads))
+            for f in pending:
+                f.result()
         return out
 
     def make_scenarios(self, B, rules=None, traj_id0=0):
