@@ -82,6 +82,11 @@ def test_config3_mixed_references_generator_plant_csv_and_loader(tmp_path):
         assert tr[0].shape == (int(B * 0.7), 5, T)
 
 
+def _oracle_hard_loop(x0, u0, T, Ts, N):
+    X, U, st, _ = ompc.closed_loop(x0, u0, T, Ts, N, path_kind=R.PATH_SINE, path_prm=(0.5, 0.5, 0.0, 0.0), **HARD)
+    return X, U, st
+
+
 @pytest.mark.parametrize("N", [10, 20, 50])
 def test_config4_horizon_sweep_with_rate_and_state_boxes(N):
     """tight rate limits (generation_type1.py:251) + a box on vy / omega (the 'slip' surrogate), lateral offsets up to
@@ -92,7 +97,7 @@ def test_config4_horizon_sweep_with_rate_and_state_boxes(N):
     x0[:2, 1] = (1.5, -1.2)
     u0 = np.stack([tg.d_steady_state(x0[:, 3]), np.zeros(B)], 1)
     sc = tg.Scenarios(B); sc.set_sine(slice(0, B), 0.5, 0.5, 0.0, 0.0)
-    gen = tg.ClosedLoopGenerator(N=N, Ts=Ts, solver_opts=TIGHT, **HARD)
+    gen = tg.ClosedLoopGenerator(N=N, Ts=Ts, **HARD)            # library-default solver settings
     res = gen.generate(x0, u0, sc, T)
     ok = res["status_counts"][:, :2].sum(1)
     # A trajectory whose yaw rate / lateral speed cannot be kept in the box makes later problems infeasible
@@ -103,21 +108,27 @@ def test_config4_horizon_sweep_with_rate_and_state_boxes(N):
     tot = res["status_counts"].sum(0)
     assert tot[5] == 0 and tot[3] == 0
     assert tot[4] <= (0.01 if N <= 20 else 0.10) * B * T
-    bad = np.where((res["status_counts"][:, 2] > 0) & (res["status_counts"][:, 4] == 0))[0]
-    if len(bad):
-        i = int(bad[0])
-        Xo, Uo, st, _ = ompc.closed_loop(x0[i], u0[i], T, Ts, N, path_kind=R.PATH_SINE, path_prm=(0.5, 0.5, 0.0, 0.0), **HARD)
-        n_ok = sum(s == "optimal" for s in st)
-        assert n_ok == ok[i] and sum(s == "infeasible" for s in st) == T - n_ok
-        assert np.abs(res["U"][i] - Uo).max() < 1e-3 and np.abs(res["clean"][i] - Xo).max() < 1e-3
+    # every trajectory against the oracle's closed loop (N = 10, 20; the N = 50 oracle loops take minutes, two of each kind are
+    # checked there): the same number of optimal / infeasible steps and the same inputs and states, i.e. the same verdict at
+    # every step (an infeasible step holds the last input, so a flipped verdict shows up in U at once)
+    decided = np.where(res["status_counts"][:, 4] == 0)[0]
+    if N == 50:
+        bad = [int(i) for i in decided if res["status_counts"][i, 2] > 0][:2]
+        decided = bad + [int(i) for i in np.where(ok == T)[0][:2]]
+    assert len(decided) >= (B - 1 if N <= 20 else 2)
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(min(16, os.cpu_count() or 1)) as pool:
+        loops = pool.starmap(_oracle_hard_loop, [(x0[i], u0[i], T, Ts, N) for i in decided])
+    n_inf = 0
+    for i, (Xo, Uo, st) in zip(decided, loops):
+        n_ok = sum(s_ == "optimal" for s_ in st)
+        assert n_ok == ok[i] and sum(s_ == "infeasible" for s_ in st) == T - n_ok, (i, st, res["status_counts"][i])
+        assert np.abs(res["U"][i] - Uo).max() < 1e-3 and np.abs(res["clean"][i] - Xo).max() < 1e-3, i
+        n_inf += T - n_ok
+    assert n_inf > 0                                            # the stress scenario does contain infeasible steps
     dU = np.diff(np.concatenate([u0[:, None, :], res["U"]], 1), axis=1)
     assert (np.abs(dU[:, :, 0]) <= 0.1 + 1e-4).all() and (np.abs(dU[:, :, 1]) <= 0.04 + 1e-4).all()      # applied inputs respect the rate box
     assert (np.abs(np.abs(dU[:, :, 1]) - 0.04) < 1e-4).mean() > 0.05                                      # ... and it is active
-    good = [int(i) for i in np.where(ok == T)[0][:2]]
-    for i in good:
-        Xo, Uo, st, _ = ompc.closed_loop(x0[i], u0[i], T, Ts, N, path_kind=R.PATH_SINE, path_prm=(0.5, 0.5, 0.0, 0.0), **HARD)
-        assert all(s == "optimal" for s in st)
-        assert np.abs(res["U"][i] - Uo).max() < 1e-3 and np.abs(res["clean"][i] - Xo).max() < 1e-3
     print(f"N={N}: mean ADMM iterations/step {res['iters_total'].mean() / T:.1f}, max {res['iters_total'].max() / T:.1f}")
 
 

@@ -66,18 +66,24 @@ struct LoopArgs {
 #define TW_REGS_S1 128
 #endif
 #define TW_REGS(S) ((S) == 1 ? TW_REGS_S1 : 128)
+// shapes that have a single-problem-per-CTA instance (see tw_mpc_step_kernel): the one- and two-warp kernels, where four CTAs
+// per SM would leave most of the register file and shared memory unused
+#define TW_HAS_P1(W, NC) ((W) <= 2 && (NC) == 0)
 
-template <int W, int S, int NC>
+// P1 = true: the single-problem-per-CTA instance.  Its only barrier id is the constant 1, so the kernel is built with 2
+// hardware barriers instead of 16 (a barrier id held in a register makes ptxas reserve all 16, and an SM has 64: four
+// resident CTAs at most, whatever the registers and the shared memory would allow).
+template <int W, int S, int NC, bool P1 = false>
 __global__ void __launch_bounds__(TW_CTA_THREADS) __maxnreg__(TW_REGS(S))
 tw_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ WLayout L, const __grid_constant__ StepArgs a)
 {
     extern __shared__ __align__(16) double sm_all[];
     constexpr int NT = 32 * W;
-    const int P = a.ppc;
-    int prob = threadIdx.x / NT, tid = threadIdx.x % NT;
+    const int P = P1 ? 1 : a.ppc;
+    int prob = P1 ? 0 : threadIdx.x / NT, tid = P1 ? threadIdx.x : threadIdx.x % NT;
     unsigned sm_off = (unsigned)prob * (unsigned)((L.total + 1) & ~1) * 8u;
-    asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));   // kept in registers instead of being re-derived at every use
-    const int bar = 1 + prob;
+    if constexpr (!P1) asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));   // kept in registers instead of being re-derived at every use
+    const int bar = P1 ? 1 : 1 + prob;
     double *sm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm_all) + sm_off);
     const int N = NC > 0 ? NC : c.N, n = 2 * N, ms = NC > 0 ? 0 : c.ms;
     if (prob >= P) return;
@@ -164,17 +170,17 @@ tw_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ WLa
     }
 }
 
-template <int W, int S, int NC>
+template <int W, int S, int NC, bool P1 = false>
 __global__ void __launch_bounds__(TW_CTA_THREADS) __maxnreg__(TW_REGS(S))
 tw_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ WLayout L, const __grid_constant__ LoopArgs a)
 {
     extern __shared__ __align__(16) double sm_all[];
     constexpr int NT = 32 * W;
-    const int P = a.ppc;
-    int prob = threadIdx.x / NT, tid = threadIdx.x % NT;
+    const int P = P1 ? 1 : a.ppc;
+    int prob = P1 ? 0 : threadIdx.x / NT, tid = P1 ? threadIdx.x : threadIdx.x % NT;
     unsigned sm_off = (unsigned)prob * (unsigned)((L.total + 1) & ~1) * 8u;
-    asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));
-    const int bar = 1 + prob;
+    if constexpr (!P1) asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));
+    const int bar = P1 ? 1 : 1 + prob;
     double *sm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm_all) + sm_off);
     const int N = NC > 0 ? NC : c.N, n = 2 * N, ms = NC > 0 ? 0 : c.ms, ns = NC > 0 ? 0 : c.ns, T = a.T;
     if (prob >= P) return;
@@ -191,7 +197,7 @@ tw_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
         const long long bfirst = blockIdx.x + (long long)G * round * P;
         const long long left = (a.B - 1 - bfirst) / G + 1;                   // slots with a trajectory, >= 1
         const int active = left < P ? (int)left : P;
-        const bool lockstep = active > 1;
+        const bool lockstep = !P1 && active > 1;
         if (prob >= active) break;                                           // later rounds have no work for this slot either
         const int b = (int)(bfirst + (long long)G * prob);
         tw_sync<W>(bar);
@@ -259,7 +265,8 @@ tw_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
             }
             warm = ok && c.warm_start;
             warm_free = warm && r.free_end;
-            if (lockstep) tg_sync(15, NT * active); else tw_sync<W>(bar);
+            if constexpr (P1) tw_sync<W>(bar);
+            else if (lockstep) tg_sync(15, NT * active); else tw_sync<W>(bar);
         }
         tw_sync<W>(bar);
         if (tid < TG_NUM_STATUS && a.status_counts) a.status_counts[(size_t)b * TG_NUM_STATUS + tid] = cnt[tid];
@@ -440,11 +447,17 @@ static bool pick_tw_shape(int N, int &W, int &S)
 }
 // kernel instances: (W, S) for a run-time horizon, plus the horizons of the BASELINE configurations compiled in (NC = N:
 // shared-memory offsets become immediates, horizon loops get constant trip counts)
+// what the compile-time-horizon instances leave out: state-bound rows, the generator tyre models, finite-difference
+// Jacobians as the primary mode, a controller without the tyre tables
+static bool tw_generic_only(const DevCfg &d)
+{
+    return d.ms > 0 || d.model != TG_MODEL_MPC || d.jacobian != TG_JAC_ANALYTIC || !d.tyre_tab || !d.atan_tab;
+}
 template <typename F>
-static int dispatch_tw(int W, int S, int N, bool has_state_rows, F &&f)
+static int dispatch_tw(int W, int S, int N, bool generic_only, F &&f)
 {
     using std::integral_constant;
-    if (W == 2 && S == 1 && N == 20 && !has_state_rows && !getenv("TRAJGEN_DYNAMIC_N")) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 20>());
+    if (W == 2 && S == 1 && N == 20 && !generic_only && !getenv("TRAJGEN_DYNAMIC_N")) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 20>());
     if (W == 1 && S == 1) return f(integral_constant<int, 1>(), integral_constant<int, 1>(), integral_constant<int, 0>());
     if (W == 2 && S == 1) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 0>());
 #ifndef TG_DEV_SHAPES_ONLY
@@ -563,7 +576,7 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
         while (h->ppc_max > 1 && (size_t)h->ppc_max * stride > h->smem_optin) h->ppc_max -= 1;
         if (const char *e = getenv("TRAJGEN_PPC")) { const int v = atoi(e); if (v >= 1 && v <= h->ppc_max) h->ppc_env = v; }
         int occ = 0;
-        int rc = dispatch_tw(h->W, h->S, d.N, d.ms > 0, [&](auto W_, auto S_, auto NC_) -> int {
+        int rc = dispatch_tw(h->W, h->S, d.N, tw_generic_only(d), [&](auto W_, auto S_, auto NC_) -> int {
             constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
             // the attribute is per kernel function and process-wide: always raise it to the device limit so that handles with
             // different layouts can be used side by side
@@ -571,7 +584,15 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
             CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
             CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tw_closed_loop_kernel<W, S, NC>, 32 * W, stride));
+            if constexpr (TW_HAS_P1(W, NC)) {
+                CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+                CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+                CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tw_closed_loop_kernel<W, S, NC, true>, 32 * W, stride));
+            } else {
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tw_closed_loop_kernel<W, S, NC>, 32 * W, stride));
+            }
             return TG_OK;
         });
         if (rc != TG_OK) return rc;
@@ -662,8 +683,10 @@ static int launch_step(tg_handle *h, StepArgs &a)
 {
     if (a.B <= 0) return TG_OK;   // empty batch: nothing to do
     CK(cudaSetDevice(h->device));
-    return dispatch_tw(h->W, h->S, h->dc.N, h->dc.ms > 0, [&](auto W_, auto S_, auto NC_) -> int {
+    return dispatch_tw(h->W, h->S, h->dc.N, tw_generic_only(h->dc), [&](auto W_, auto S_, auto NC_) -> int {
         constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
+        if constexpr (TW_HAS_P1(W, NC))
+            if (choose_tw_ppc(h, a.B) == 1) return launch_tw(h, tw_mpc_step_kernel<W, S, NC, true>, a, a.B, W);
         return launch_tw(h, tw_mpc_step_kernel<W, S, NC>, a, a.B, W);
     });
 }
@@ -744,8 +767,10 @@ int tg_closed_loop(tg_handle *h, int B, int T, const double *x0, const double *u
     memset(&a, 0, sizeof(a));
     a.B = B; a.T = T; a.x0 = x0; a.u0 = u0; a.spec = spec; a.brk = brk; a.coef = coef; a.traj_id0 = traj_id0;
     a.clean = clean; a.noisy = noisy; a.U = U; a.status_counts = status_counts; a.iters_total = (long long *)iters_total;
-    return dispatch_tw(h->W, h->S, h->dc.N, h->dc.ms > 0, [&](auto W_, auto S_, auto NC_) -> int {
+    return dispatch_tw(h->W, h->S, h->dc.N, tw_generic_only(h->dc), [&](auto W_, auto S_, auto NC_) -> int {
         constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
+        if constexpr (TW_HAS_P1(W, NC))
+            if (choose_tw_ppc(h, B) == 1) return launch_tw(h, tw_closed_loop_kernel<W, S, NC, true>, a, B, W);
         return launch_tw(h, tw_closed_loop_kernel<W, S, NC>, a, B, W);
     });
 }

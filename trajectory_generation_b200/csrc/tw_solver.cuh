@@ -519,12 +519,17 @@ __device__ __forceinline__ TwGsGeo tw_gs_geo(int N, int ms)
 }
 // gt[v NV + j] = sum_i Gs[i][j] vec_v[i] for v < NVEC and every column j < n, by all threads of the problem: thread (jp, g)
 // sums the stages k = jp + g, jp + g + NG, ... (rows of earlier stages vanish in column pair jp), then the NG partials are
-// folded with shuffles.  The caller synchronises before reading gt.
+// folded with shuffles.  The caller synchronises before reading gt.  (32-bit shared addresses and explicit ld.shared: with
+// generic pointers every access of these loops carried 64-bit address arithmetic, ~30 instructions per row.)
+__device__ __forceinline__ double2 tw_lds2(unsigned a) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
 template <int W, int NVEC>
 __device__ __forceinline__ void tw_gs_tmul(const WLayout &L, double *sm, const TwGsGeo &geo, int N, int ns, int NV,
                                            const double *const (&vec)[NVEC], int tid)
 {
-    const double *Gs = sm + L.Gs;
+    const unsigned gs_a = tw_saddr(sm + L.Gs);
+    unsigned vec_a[NVEC];
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) vec_a[v] = tw_saddr(vec[v]);
     double *gt = sm + L.gt;
     const int jp = tid >> geo.lg_ng, g = tid & (geo.ng - 1);
     double a0[NVEC], a1[NVEC];
@@ -532,13 +537,13 @@ __device__ __forceinline__ void tw_gs_tmul(const WLayout &L, double *sm, const T
     for (int v = 0; v < NVEC; ++v) { a0[v] = 0.0; a1[v] = 0.0; }
     if (jp < N) {
         for (int k = jp + g; k < N; k += geo.ng) {
-            const int len = tw_gs_len(k);
-            const double *row = Gs + ns * tw_gs_off(k) + 2 * jp;
-            for (int si = 0; si < ns; ++si) {
-                const double2 g2 = tw_ld2(row + si * len);
+            const unsigned len8 = 8u * (unsigned)tw_gs_len(k);
+            unsigned ra = gs_a + 8u * (unsigned)(ns * tw_gs_off(k) + 2 * jp), va = 8u * (unsigned)(k * ns);
+            for (int si = 0; si < ns; ++si, ra += len8, va += 8u) {
+                const double2 g2 = tw_lds2(ra);
 #pragma unroll
                 for (int v = 0; v < NVEC; ++v) {
-                    const double t = vec[v][k * ns + si];
+                    const double t = tw_lds1(vec_a[v] + va);
                     a0[v] = fma(g2.x, t, a0[v]); a1[v] = fma(g2.y, t, a1[v]);
                 }
             }
@@ -557,18 +562,18 @@ template <int W>
 __device__ __forceinline__ double tw_gs_row_dot(const WLayout &L, const double *sm, const TwGsGeo &geo, int ns, int ms, const double *x,
                                                 int r, int tid)
 {
-    const double *Gs = sm + L.Gs;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (r < ms) {
         const int k = r / ns, si = r - k * ns, h = tid & (geo.tpr - 1);
-        const double *row = Gs + ns * tw_gs_off(k) + si * tw_gs_len(k);
+        const unsigned st = 16u * (unsigned)geo.tpr;                 // bytes between the column pairs of one thread
+        unsigned ga = tw_saddr(sm + L.Gs) + 8u * (unsigned)(ns * tw_gs_off(k) + si * tw_gs_len(k)) + 16u * (unsigned)h;
+        unsigned xa = tw_saddr(x) + 16u * (unsigned)h;
         int d = h;
-        for (; d + geo.tpr <= k; d += 2 * geo.tpr) {   // column pairs d and d + TPR (both <= k)
-            const double2 ga = tw_ld2(row + 2 * d), xa = tw_ld2(x + 2 * d);
-            const double2 gb = tw_ld2(row + 2 * (d + geo.tpr)), xb = tw_ld2(x + 2 * (d + geo.tpr));
-            s0 = fma(ga.x, xa.x, s0); s1 = fma(ga.y, xa.y, s1); s2 = fma(gb.x, xb.x, s2); s3 = fma(gb.y, xb.y, s3);
+        for (; d + geo.tpr <= k; d += 2 * geo.tpr, ga += 2u * st, xa += 2u * st) {   // column pairs d and d + TPR (both <= k)
+            const double2 g_a = tw_lds2(ga), x_a = tw_lds2(xa), g_b = tw_lds2(ga + st), x_b = tw_lds2(xa + st);
+            s0 = fma(g_a.x, x_a.x, s0); s1 = fma(g_a.y, x_a.y, s1); s2 = fma(g_b.x, x_b.x, s2); s3 = fma(g_b.y, x_b.y, s3);
         }
-        if (d <= k) { const double2 ga = tw_ld2(row + 2 * d), xa = tw_ld2(x + 2 * d); s0 = fma(ga.x, xa.x, s0); s1 = fma(ga.y, xa.y, s1); }
+        if (d <= k) { const double2 g_a = tw_lds2(ga), x_a = tw_lds2(xa); s0 = fma(g_a.x, x_a.x, s0); s1 = fma(g_a.y, x_a.y, s1); }
     }
     double acc = (s0 + s1) + (s2 + s3);
     for (int o = geo.tpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -952,7 +957,10 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
 #pragma unroll
         for (int i = 0; i < 6; ++i) xs[i] = sm[LF(x0) + i];
         if (lane < 6) xbar[lane] = sm[LF(x0) + lane];
-        const bool use_tab = c.tyre_tab && c.model != TG_MODEL_GEN1;
+        // kernels with a compile-time horizon serve the standard controller only (MPC tyre model from the tables, analytic
+        // Jacobians: checked by the dispatcher), so the other variants' code is not even compiled into them
+        const bool use_tab = (NC > 0) ? true : (c.tyre_tab && c.model != TG_MODEL_GEN1);
+        const int model = (NC > 0) ? TG_MODEL_MPC : c.model;
         if (use_tab) {
             // (vx, vy, omega) do not depend on the pose, so only they ride the sequential chain (slip angle -> tyre force ->
             // Euler update, from tables); heading and position are recovered afterwards in the reference's summation order.
@@ -960,7 +968,7 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
             const TgRoll rk = tg_roll_setup(c, ud, udel, sd, cd, lane);
 #pragma unroll 1
             for (int k = 0; k < N; ++k) {
-                tg_roll_stage(c, rk, c.model, vx, vy, om, lane, sm + LF(aux) + 6 * k);
+                tg_roll_stage(c, rk, model, vx, vy, om, lane, sm + LF(aux) + 6 * k);
                 if (lane == 0) { xbar[6 * (k + 1) + 3] = vx; xbar[6 * (k + 1) + 4] = vy; xbar[6 * (k + 1) + 5] = om; }
             }
             __syncwarp();
@@ -986,7 +994,7 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
         } else {
 #pragma unroll 1
             for (int k = 0; k < N; ++k) {
-                tg_f_cont_lanes(c.p, c.inv_m, c.inv_Iz, c.model, xs, ud, udel, sd, cd, lane, f, sm + LF(aux) + 6 * k);
+                tg_f_cont_lanes(c.p, c.inv_m, c.inv_Iz, model, xs, ud, udel, sd, cd, lane, f, sm + LF(aux) + 6 * k);
 #pragma unroll
                 for (int i = 0; i < 6; ++i) xs[i] = xs[i] + c.Ts * f[i];
                 if (lane == 0) {
@@ -1008,13 +1016,13 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
 #pragma unroll
             for (int i = 0; i < 6; ++i) xs[i] = xbar[6 * k + i];
             double *gout = tap.g ? tap.g + 6 * k : nullptr;
-            if (c.jacobian == TG_JAC_FD) {
+            if (NC == 0 && c.jacobian == TG_JAC_FD) {
                 tg_linearize_fd(c, xs, ud, udel, lin + TG_LIN * k, gout);
             } else {
                 double sd, cd;
                 TG_SINCOS(udel, sd, cd);
                 bool kink;
-                if (c.tyre_tab && c.model != TG_MODEL_GEN1) kink = tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k, gout, nullptr, sm + LF(aux) + 6 * k);
+                if (NC > 0 || (c.tyre_tab && c.model != TG_MODEL_GEN1)) kink = tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k, gout, nullptr, sm + LF(aux) + 6 * k);
                 else kink = tg_linearize_analytic(c, xs, ud, udel, sd, cd, lin + TG_LIN * k, gout, sm + LF(aux) + 6 * k);
                 if (kink) tg_linearize_fd(c, xs, ud, udel, lin + TG_LIN * k, gout);   // rare: the reference's own arithmetic at a kink
             }
