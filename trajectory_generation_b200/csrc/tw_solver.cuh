@@ -1063,7 +1063,13 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
     for (int si = 0; si < ns; ++si) {
         const int sx = c.sidx[si];
         const double xv = sm[LF(x0) + sx];
-        if (xv < c.x_lo[sx] - c.eps_abs || xv > c.x_hi[sx] + c.eps_abs) x0_infeasible = true;  // k = 0 rows (:217,:220)
+        // k = 0 rows (:217,:220): x0 itself outside its box.  The reference hands these rows to OSQP, which accepts a violation
+        // below its primal tolerance (CVXPY's settings: eps_abs = eps_rel = 1e-5) as "optimal" -- e.g. the plant landing 1e-6
+        // outside a bound that the previous step's plan touched -- so the same tolerance applies here, whatever tighter
+        // tolerance this library's own iteration runs at.
+        const double ea = fmax(c.eps_abs, 1e-5), er = fmax(c.eps_rel, 1e-5);
+        if (xv < c.x_lo[sx] - (ea + er * fmax(fabs(xv), fabs(c.x_lo[sx]))) || xv > c.x_hi[sx] + (ea + er * fmax(fabs(xv), fabs(c.x_hi[sx]))))
+            x0_infeasible = true;
     }
     bool free_mode = (!warm || warm_free) && c.free_mode;
     double rho_scale = free_mode ? TW_FREE_RHO : c.rho;
