@@ -267,8 +267,13 @@ def test_closed_loop_config1_vs_golden(golden_loop):
     assert res["status_counts"][0, 0] == 600
     assert np.abs(res["clean"][0] - g["X40"]).max() < TOL_LOOP
     assert np.abs(res["U"][0] - g["U40"]).max() < TOL_LOOP
-    d = res["U"][0, :, 0]
+    d, do = res["U"][0, :, 0], g["U40"][:, 0]
     assert abs(d.mean() - 0.2161) < 5e-3            # generation_type1.py:250 (soft anchor)
+    # the constant's std (0.1314) is NOT reproduced by the N = 40 loop MPC/main.py ships -- neither by the oracle's (0.0724): the
+    # control statistics are pinned to the oracle run, and the discrepancy is recorded in DESIGN.md section 5
+    assert abs(d.std() - do.std()) < 1e-4 and abs(do.std() - 0.0724) < 2e-3
+    de, deo = res["U"][0, :, 1], g["U40"][:, 1]
+    assert abs(de.mean() - deo.mean()) < 1e-4 and abs(de.std() - deo.std()) < 1e-4 and abs(de.std() - 0.0338) < 3e-3
 
 
 def test_closed_loop_sine_and_generator_plant_vs_golden(golden_loop):

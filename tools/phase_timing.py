@@ -20,7 +20,12 @@ import time; t = time.time(); res = gen.generate(x0, u0, sc, T); dt = time.time(
 L.tg_debug_phases(out, 0)
 v = np.array(out[:16], dtype=float)
 names = ["rollout(+zero,sincos)", "linearise+resid", "K2 condense", "R-terms,bounds,rho", "buildK+sweep", "ADMM tail", "objective/exit", "ADMM init", "ADMM iterations", "ADMM check", "R-terms+dH", "bounds+rho", "H taps/copy", "K2 producer (G, W rows)", "K2 barrier wait", "K2 consumer (rank-3)"]
-ntraj0 = len(range(0, B, min(B, gen.info()["ctas_per_sm"] * gen.info()["num_sms"])))
+# trajectories that slot 0 of CTA 0 runs (N = 20 launch geometry: P problems per CTA, at most 2 CTAs of 4 per SM)
+P = 4
+while P > 1 and (B + P - 1) // P < gen.info()["num_sms"]:
+    P //= 2
+G = min((B + P - 1) // P, 2 * gen.info()["num_sms"] * (4 // P) if P > 1 else 10 ** 9)
+ntraj0 = -(-B // (G * P))
 steps = T * ntraj0
 print(f"B={B} T={T} wall {dt*1e3:.1f} ms  -> {B*T/dt:.3e} steps/s; CTA0 ran {ntraj0} trajectories")
 for nme, c in zip(names, v):

@@ -732,6 +732,8 @@ template <int W, int S, int NC>
 __device__ __forceinline__ void tw_sweep_invert(const DevCfg &c, const WLayout &L, double *sm, const TwMap<S> &mp,
                                                 double (&a)[S][4][4], int bar)
 {
+    // measured (profiles/r02_sweep_variants.txt): the scalar sweep is fastest for every shape -- the blocked
+    // forms save synchronisations but add fp64 work that the problems of an SM have to share the fp64 pipe for
     constexpr int PB = TW_SWEEP_PB;
     if constexpr (PB == 1 || (S > 1 && PB == 4)) {   // (two tiles per thread leave no registers for the 4-pivot block operands)
         tw_sweep_invert_scalar<W, S, NC>(c, L, sm, mp, a, bar);
