@@ -272,7 +272,8 @@ __device__ __forceinline__ void tg_rotate_small(double &sp, double &cp, double d
 }
 
 // f_cont by a lane pair (lane & 1: 0 = front tyre, 1 = rear tyre) with the tyre table and sin/cos(phi) supplied by
-// the caller.  Variants MPC / GEN2 only (GEN1 leaves the rear slip angle unclamped -> callers use tg_f_cont_lanes).
+// the caller.  GEN1 leaves the rear slip angle unclamped (generation_type1.py:46): inside the clamp interval the table still
+// applies, outside it that lane evaluates atan / sin.
 // aux (optional, shared memory) receives {alpha_f raw, alpha_r raw, sin phi, cos phi} for the linearisation.
 __device__ __forceinline__ void tg_f_cont_tab(const DevCfg &c, int variant, const double x[6], double d, double delta,
                                               double sd, double cd, double sp, double cp, int lane, double f[6],
@@ -286,9 +287,11 @@ __device__ __forceinline__ void tg_f_cont_tab(const DevCfg &c, int variant, cons
     const double nl = rear ? (om * p[P_lr] - vy) : (om * p[P_lf] + vy);
     const double at = tg_slip_atan(c.atan_tab, nl, vx_eff);
     const double alpha_raw = rear ? at : (-at + delta);
-    const double alpha = tg_clamp(alpha_raw, -p[P_maxAlpha], p[P_maxAlpha]);
+    const bool free_rear = rear && variant == TG_MODEL_GEN1;
+    const double alpha = free_rear ? alpha_raw : tg_clamp(alpha_raw, -p[P_maxAlpha], p[P_maxAlpha]);
     double g, dg;
-    tg_tyre_tab(c.tyre_tab + rear * (TG_TAB_ROWS * TG_TAB_NC), alpha, p[P_maxAlpha], c.tab_scale, g, dg);
+    if (free_rear && fabs(alpha) > p[P_maxAlpha]) g = tg_sin(p[P_Cr] * tg_atan(p[P_Br] * alpha));
+    else tg_tyre_tab(c.tyre_tab + rear * (TG_TAB_ROWS * TG_TAB_NC), alpha, p[P_maxAlpha], c.tab_scale, g, dg);
     const double F = (rear ? p[P_Dr] : p[P_Df]) * g;
     if (aux && lane < 2) { aux[rear] = alpha_raw; aux[2 + rear] = rear ? cp : sp; }
     const double Fyf = __shfl_sync(0xffffffffu, F, base), Fyr = __shfl_sync(0xffffffffu, F, base + 1);
@@ -380,7 +383,7 @@ __device__ __forceinline__ void tg_plant_step_lanes(const DevCfg &c, double x[6]
 {
     double sd, cd, f[6];
     TG_SINCOS(delta, sd, cd);
-    if (c.tyre_tab && c.plant != TG_PLANT_GEN1) {
+    if (c.tyre_tab) {
         double sp, cp;
         TG_SINCOS(x[2], sp, cp);
         tg_f_cont_tab(c, c.plant, x, d, delta, sd, cd, sp, cp, lane, f);

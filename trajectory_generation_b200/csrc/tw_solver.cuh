@@ -56,7 +56,9 @@ __device__ __forceinline__ void tg_sync(int bar, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads) : "memory");
 }
 
+#ifndef TW_KB
 #define TW_KB 4                  // horizon stages condensed per synchronisation in K2
+#endif
 #define TW_WARM_RESTART_ITER 300
 #define TW_FREE_RHO 1e-6         // rho scale of a solve that starts with no active row (see tw_step_body)
 #define TW_POLISH_MARGIN 1e-3    // a converged standard solve is polished if every row is this far inside its bounds
@@ -346,16 +348,24 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
             double *row = Gs + ns * tw_gs_off(k) + si * tw_gs_len(k);
             for (int j = 2 * (k + 1); j < tw_gs_len(k); ++j) row[j] = 0.0;
         }
-#pragma unroll 1
+    // compile-time horizon that is a multiple of TW_KB: the stage loops below have a constant trip count and are unrolled, so that
+    // the loads of a stage are issued under the arithmetic of the previous one
+    constexpr bool FULLKB = NC > 0 && NC % TW_KB == 0;
+    constexpr int UNR = FULLKB ? TW_KB : 1;
+#ifndef TW_UNROLL_ROUNDS
+#define TW_UNROLL_ROUNDS 0   // unrolling the rounds as well measured 1 % slower (more code, no extra overlap)
+#endif
+    constexpr int UNR0 = (FULLKB && TW_UNROLL_ROUNDS) ? (NC > 0 ? NC / TW_KB : 1) : 1;
+#pragma unroll UNR0
     for (int k0 = 0; k0 < N; k0 += TW_KB) {
-        const int kb = (N - k0 < TW_KB) ? N - k0 : TW_KB;
+        const int kb = FULLKB ? TW_KB : ((N - k0 < TW_KB) ? N - k0 : TW_KB);
         double *wblk = wbuf + ((LF(nbuf) == 2) ? ((k0 / TW_KB) & 1) * TW_KB * 3 * NV : 0);
 #pragma unroll
         for (int p = 0; p < NPASS; ++p) {
             const int j = p * NT + tid;
             if (j < n && k0 + kb > (p * NT + (tid & ~31)) / 2) {   // nothing to do before the first column of this warp is born
                 const int c1 = j & 1, jb = j >> 1;
-#pragma unroll 1
+#pragma unroll UNR
                 for (int s_i = 0; s_i < kb; ++s_i) {
                     const int k = k0 + s_i;
                     const double *r = lin + TG_LIN * k;
@@ -394,7 +404,7 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
             }
         }
         tw_sync<W>(bar);
-#pragma unroll 1
+#pragma unroll UNR
         for (int s_i = 0; s_i < kb; ++s_i) {
             const int lim = 2 * (k0 + s_i) + 2;   // columns born so far
             const double *wrow = wblk + s_i * 3 * NV;
@@ -620,7 +630,11 @@ __device__ __forceinline__ void tw_sweep_invert_scalar(const DevCfg &c, const WL
     unsigned ro_a[S], co_a[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) { ro_a[s] = vb_a + 8u * (unsigned)mp.ro[s]; co_a[s] = vb_a + 8u * (unsigned)mp.co[s]; }
-#pragma unroll 1
+#ifndef TW_SWEEP_UNROLL
+#define TW_SWEEP_UNROLL 1
+#endif
+    constexpr int UNRK = (NC > 0 && TW_SWEEP_UNROLL > 1) ? TW_SWEEP_UNROLL : 1;
+#pragma unroll UNRK
     for (int K = 0; K < nb; ++K) {
         const int K4 = 4 * K;
 #pragma unroll
@@ -968,7 +982,11 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
             // Euler update, from tables); heading and position are recovered afterwards in the reference's summation order.
             double vx = xs[3], vy = xs[4], om = xs[5];
             const TgRoll rk = tg_roll_setup(c, ud, udel, sd, cd, lane);
-#pragma unroll 1
+#ifndef TW_ROLL_UNROLL
+#define TW_ROLL_UNROLL 1
+#endif
+            constexpr int UNRR = (NC > 0) ? TW_ROLL_UNROLL : 1;
+#pragma unroll UNRR
             for (int k = 0; k < N; ++k) {
                 tg_roll_stage(c, rk, model, vx, vy, om, lane, sm + LF(aux) + 6 * k);
                 if (lane == 0) { xbar[6 * (k + 1) + 3] = vx; xbar[6 * (k + 1) + 4] = vy; xbar[6 * (k + 1) + 5] = om; }
