@@ -630,11 +630,7 @@ __device__ __forceinline__ void tw_sweep_invert_scalar(const DevCfg &c, const WL
     unsigned ro_a[S], co_a[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) { ro_a[s] = vb_a + 8u * (unsigned)mp.ro[s]; co_a[s] = vb_a + 8u * (unsigned)mp.co[s]; }
-#ifndef TW_SWEEP_UNROLL
-#define TW_SWEEP_UNROLL 1
-#endif
-    constexpr int UNRK = (NC > 0 && TW_SWEEP_UNROLL > 1) ? TW_SWEEP_UNROLL : 1;
-#pragma unroll UNRK
+#pragma unroll 1
     for (int K = 0; K < nb; ++K) {
         const int K4 = 4 * K;
 #pragma unroll
@@ -982,11 +978,7 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
             // Euler update, from tables); heading and position are recovered afterwards in the reference's summation order.
             double vx = xs[3], vy = xs[4], om = xs[5];
             const TgRoll rk = tg_roll_setup(c, ud, udel, sd, cd, lane);
-#ifndef TW_ROLL_UNROLL
-#define TW_ROLL_UNROLL 1
-#endif
-            constexpr int UNRR = (NC > 0) ? TW_ROLL_UNROLL : 1;
-#pragma unroll UNRR
+#pragma unroll 1
             for (int k = 0; k < N; ++k) {
                 tg_roll_stage(c, rk, model, vx, vy, om, lane, sm + LF(aux) + 6 * k);
                 if (lane == 0) { xbar[6 * (k + 1) + 3] = vx; xbar[6 * (k + 1) + 4] = vy; xbar[6 * (k + 1) + 5] = om; }
