@@ -457,7 +457,14 @@ template <typename F>
 static int dispatch_tw(int W, int S, int N, bool generic_only, F &&f)
 {
     using std::integral_constant;
-    if (W == 2 && S == 1 && N == 20 && !generic_only && !getenv("TRAJGEN_DYNAMIC_N")) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 20>());
+    if (!generic_only && !getenv("TRAJGEN_DYNAMIC_N")) {   // mpc_step's default horizon (20), MPC/main.py's (40), BASELINE config 4's (10, 50)
+        if (W == 2 && S == 1 && N == 20) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 20>());
+#ifndef TG_DEV_SHAPES_ONLY
+        if (W == 1 && S == 1 && N == 10) return f(integral_constant<int, 1>(), integral_constant<int, 1>(), integral_constant<int, 10>());
+        if (W == 8 && S == 1 && N == 40) return f(integral_constant<int, 8>(), integral_constant<int, 1>(), integral_constant<int, 40>());
+        if (W == 8 && S == 2 && N == 50) return f(integral_constant<int, 8>(), integral_constant<int, 2>(), integral_constant<int, 50>());
+#endif
+    }
     if (W == 1 && S == 1) return f(integral_constant<int, 1>(), integral_constant<int, 1>(), integral_constant<int, 0>());
     if (W == 2 && S == 1) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 0>());
 #ifndef TG_DEV_SHAPES_ONLY
