@@ -68,12 +68,12 @@ struct LoopArgs {
 #define TW_REGS(S) ((S) == 1 ? TW_REGS_S1 : 128)
 // shapes that have a single-problem-per-CTA instance (see tw_mpc_step_kernel): the one- and two-warp kernels, where four CTAs
 // per SM would leave most of the register file and shared memory unused
-#define TW_HAS_P1(W, NC) ((W) <= 2 && (NC) == 0)
+#define TW_HAS_P1(W, NC, HS) ((W) <= 2 && ((NC) == 0 || (HS)))
 
 // P1 = true: the single-problem-per-CTA instance.  Its only barrier id is the constant 1, so the kernel is built with 2
 // hardware barriers instead of 16 (a barrier id held in a register makes ptxas reserve all 16, and an SM has 64: four
 // resident CTAs at most, whatever the registers and the shared memory would allow).
-template <int W, int S, int NC, bool P1 = false>
+template <int W, int S, int NC, bool P1 = false, bool HS = (NC == 0)>
 __global__ void __launch_bounds__(TW_CTA_THREADS) __maxnreg__(TW_REGS(S))
 tw_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ WLayout L, const __grid_constant__ StepArgs a)
 {
@@ -85,7 +85,7 @@ tw_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ WLa
     if constexpr (!P1) asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));   // kept in registers instead of being re-derived at every use
     const int bar = P1 ? 1 : 1 + prob;
     double *sm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm_all) + sm_off);
-    const int N = NC > 0 ? NC : c.N, n = 2 * N, ms = NC > 0 ? 0 : c.ms;
+    const int N = NC > 0 ? NC : c.N, n = 2 * N, ms = HS ? c.ms : 0;
     if (prob >= P) return;
     const TwMap<S> mp = tw_make_map<W, S>(LF(nb), tid);
     for (int b0 = blockIdx.x * P; b0 < a.B; b0 += gridDim.x * P) {
@@ -123,7 +123,7 @@ tw_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ WLa
         tap.u = a.u ? a.u + (size_t)b * (2 * n + ms) : nullptr;
         tap.Gs = a.Gs ? a.Gs + (size_t)b * c.ms * n : nullptr;
         tap.stop = a.stop;
-        const StepResult r = tw_step_body<W, S, NC>(c, L, sm, mp, warm, warm_free, tap, nullptr, tid, bar);
+        const StepResult r = tw_step_body<W, S, NC, HS>(c, L, sm, mp, warm, warm_free, tap, nullptr, tid, bar);
         if (a.stop) continue;
         const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);  // :261
         const double ud = sm[LF(uprev)], udel = sm[LF(uprev) + 1];
@@ -170,7 +170,7 @@ tw_mpc_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ WLa
     }
 }
 
-template <int W, int S, int NC, bool P1 = false>
+template <int W, int S, int NC, bool P1 = false, bool HS = (NC == 0)>
 __global__ void __launch_bounds__(TW_CTA_THREADS) __maxnreg__(TW_REGS(S))
 tw_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ WLayout L, const __grid_constant__ LoopArgs a)
 {
@@ -182,7 +182,7 @@ tw_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
     if constexpr (!P1) asm volatile("" : "+r"(tid), "+r"(prob), "+r"(sm_off));
     const int bar = P1 ? 1 : 1 + prob;
     double *sm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm_all) + sm_off);
-    const int N = NC > 0 ? NC : c.N, n = 2 * N, ms = NC > 0 ? 0 : c.ms, ns = NC > 0 ? 0 : c.ns, T = a.T;
+    const int N = NC > 0 ? NC : c.N, n = 2 * N, ms = HS ? c.ms : 0, ns = HS ? c.ns : 0, T = a.T;
     if (prob >= P) return;
     const TwMap<S> mp = tw_make_map<W, S>(LF(nb), tid);
     const StepTaps tap = {};
@@ -226,7 +226,7 @@ tw_closed_loop_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
                 }
                 break;
             }
-            const StepResult r = tw_step_body<W, S, NC>(c, L, sm, mp, warm, warm_free, tap, &fx, tid, bar);
+            const StepResult r = tw_step_body<W, S, NC, HS>(c, L, sm, mp, warm, warm_free, tap, &fx, tid, bar);
             const bool ok = (r.status == TG_STATUS_OPTIMAL || r.status == TG_STATUS_OPTIMAL_INACCURATE);
             if (tid == 0) { cnt[r.status] += 1; *itsum += r.iters; }
             // shifted warm start for the next step, in the next step's dU coordinates
@@ -445,35 +445,49 @@ static bool pick_tw_shape(int N, int &W, int &S)
     else return false;
     return true;
 }
-// kernel instances: (W, S) for a run-time horizon, plus the horizons of the BASELINE configurations compiled in (NC = N:
-// shared-memory offsets become immediates, horizon loops get constant trip counts)
-// what the compile-time-horizon instances leave out: state-bound rows, the generator tyre models, finite-difference
-// Jacobians as the primary mode, a controller without the tyre tables
-static bool tw_generic_only(const DevCfg &d)
+// kernel instances: (W, S) for a run-time horizon, plus the horizons of the reference / the BASELINE configurations compiled in
+// (NC = N: shared-memory offsets become immediates, horizon loops get constant trip counts: 25-50 % faster).  The compile-time
+// instances serve the standard controller only -- MPC tyre model from the tables, analytic Jacobians (tw_standard_controller) --
+// and come without (HS = false) or with (HS = true) the code of the state-bound rows.
+static bool tw_standard_controller(const DevCfg &d)
 {
-    return d.ms > 0 || d.model != TG_MODEL_MPC || d.jacobian != TG_JAC_ANALYTIC || !d.tyre_tab || !d.atan_tab;
+    return d.model == TG_MODEL_MPC && d.jacobian == TG_JAC_ANALYTIC && d.tyre_tab && d.atan_tab;
 }
 template <typename F>
-static int dispatch_tw(int W, int S, int N, bool generic_only, F &&f)
+static int dispatch_tw(int W, int S, const DevCfg &d, F &&f)
 {
     using std::integral_constant;
-    if (!generic_only && !getenv("TRAJGEN_DYNAMIC_N")) {   // mpc_step's default horizon (20), MPC/main.py's (40), BASELINE config 4's (10, 50)
-        if (W == 2 && S == 1 && N == 20) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 20>());
+    typedef integral_constant<bool, false> no_rows;
+    typedef integral_constant<bool, true> rows;
+    const int N = d.N;
+    if (tw_standard_controller(d) && !getenv("TRAJGEN_DYNAMIC_N")) {   // mpc_step's default horizon (20), MPC/main.py's (40), BASELINE config 4's (10, 50)
+        if (d.ms == 0) {
+            if (W == 2 && S == 1 && N == 20) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 20>(), no_rows());
 #ifndef TG_DEV_SHAPES_ONLY
-        if (W == 1 && S == 1 && N == 10) return f(integral_constant<int, 1>(), integral_constant<int, 1>(), integral_constant<int, 10>());
-        if (W == 8 && S == 1 && N == 40) return f(integral_constant<int, 8>(), integral_constant<int, 1>(), integral_constant<int, 40>());
-        if (W == 8 && S == 2 && N == 50) return f(integral_constant<int, 8>(), integral_constant<int, 2>(), integral_constant<int, 50>());
+            if (W == 1 && S == 1 && N == 10) return f(integral_constant<int, 1>(), integral_constant<int, 1>(), integral_constant<int, 10>(), no_rows());
+            if (W == 8 && S == 1 && N == 40) return f(integral_constant<int, 8>(), integral_constant<int, 1>(), integral_constant<int, 40>(), no_rows());
+            if (W == 8 && S == 2 && N == 50) return f(integral_constant<int, 8>(), integral_constant<int, 2>(), integral_constant<int, 50>(), no_rows());
 #endif
-    }
-    if (W == 1 && S == 1) return f(integral_constant<int, 1>(), integral_constant<int, 1>(), integral_constant<int, 0>());
-    if (W == 2 && S == 1) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 0>());
+        } else {
+            if (W == 2 && S == 1 && N == 20) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 20>(), rows());
 #ifndef TG_DEV_SHAPES_ONLY
-    if (W == 4 && S == 1) return f(integral_constant<int, 4>(), integral_constant<int, 1>(), integral_constant<int, 0>());
-    if (W == 8 && S == 1) return f(integral_constant<int, 8>(), integral_constant<int, 1>(), integral_constant<int, 0>());
-    if (W == 8 && S == 2) return f(integral_constant<int, 8>(), integral_constant<int, 2>(), integral_constant<int, 0>());
+            if (W == 1 && S == 1 && N == 10) return f(integral_constant<int, 1>(), integral_constant<int, 1>(), integral_constant<int, 10>(), rows());
+            if (W == 8 && S == 2 && N == 50) return f(integral_constant<int, 8>(), integral_constant<int, 2>(), integral_constant<int, 50>(), rows());
+#endif
+        }
+    }
+    if (W == 1 && S == 1) return f(integral_constant<int, 1>(), integral_constant<int, 1>(), integral_constant<int, 0>(), rows());
+    if (W == 2 && S == 1) return f(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 0>(), rows());
+#ifndef TG_DEV_SHAPES_ONLY
+    if (W == 4 && S == 1) return f(integral_constant<int, 4>(), integral_constant<int, 1>(), integral_constant<int, 0>(), rows());
+    if (W == 8 && S == 1) return f(integral_constant<int, 8>(), integral_constant<int, 1>(), integral_constant<int, 0>(), rows());
+    if (W == 8 && S == 2) return f(integral_constant<int, 8>(), integral_constant<int, 2>(), integral_constant<int, 0>(), rows());
 #endif
     return fail(TG_ERR_UNSUPPORTED, "no kernel shape for this horizon");
 }
+// instances that exist only in their single-problem-per-CTA form: compile-time horizon + state-bound rows on one or two warps
+// (problems with state-bound rows always run one per CTA, choose_tw_ppc)
+#define TW_P1_ONLY(W, NC, HS) ((HS) && (NC) > 0 && (W) <= 2)
 static size_t tw_stride(const tg_handle *h) { return (((size_t)h->WL.total + 1) & ~(size_t)1) * sizeof(double); }
 
 extern "C" {
@@ -583,22 +597,25 @@ int tg_create(const tg_config *cfg, int device, tg_handle **out)
         while (h->ppc_max > 1 && (size_t)h->ppc_max * stride > h->smem_optin) h->ppc_max -= 1;
         if (const char *e = getenv("TRAJGEN_PPC")) { const int v = atoi(e); if (v >= 1 && v <= h->ppc_max) h->ppc_env = v; }
         int occ = 0;
-        int rc = dispatch_tw(h->W, h->S, d.N, tw_generic_only(d), [&](auto W_, auto S_, auto NC_) -> int {
+        int rc = dispatch_tw(h->W, h->S, d, [&](auto W_, auto S_, auto NC_, auto HS_) -> int {
             constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
+            constexpr bool HS = decltype(HS_)::value;
             // the attribute is per kernel function and process-wide: always raise it to the device limit so that handles with
             // different layouts can be used side by side
-            CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-            CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-            CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            if constexpr (TW_HAS_P1(W, NC)) {
-                CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-                CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-                CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tw_closed_loop_kernel<W, S, NC, true>, 32 * W, stride));
+            if constexpr (!TW_P1_ONLY(W, NC, HS)) {
+                CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC, false, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+                CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC, false, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+                CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC, false, HS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC, false, HS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            }
+            if constexpr (TW_HAS_P1(W, NC, HS)) {
+                CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC, true, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+                CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC, true, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+                CK(cudaFuncSetAttribute(tw_mpc_step_kernel<W, S, NC, true, HS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                CK(cudaFuncSetAttribute(tw_closed_loop_kernel<W, S, NC, true, HS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tw_closed_loop_kernel<W, S, NC, true, HS>, 32 * W, stride));
             } else {
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tw_closed_loop_kernel<W, S, NC>, 32 * W, stride));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tw_closed_loop_kernel<W, S, NC, false, HS>, 32 * W, stride));
             }
             return TG_OK;
         });
@@ -668,9 +685,9 @@ static int choose_tw_ppc(const tg_handle *h, int B)
 
 extern "C++" {
 template <typename Kern, typename Args>
-static int launch_tw(tg_handle *h, Kern kern, Args &a, int B, int W)
+static int launch_tw(tg_handle *h, Kern kern, Args &a, int B, int W, int ppc_fixed = 0)
 {
-    const int ppc = choose_tw_ppc(h, B);
+    const int ppc = ppc_fixed > 0 ? ppc_fixed : choose_tw_ppc(h, B);   // ppc_fixed = 1: a single-problem-per-CTA instance
     a.ppc = ppc;
     const size_t smem = (size_t)ppc * tw_stride(h);
     int per_sm = 0;
@@ -690,11 +707,16 @@ static int launch_step(tg_handle *h, StepArgs &a)
 {
     if (a.B <= 0) return TG_OK;   // empty batch: nothing to do
     CK(cudaSetDevice(h->device));
-    return dispatch_tw(h->W, h->S, h->dc.N, tw_generic_only(h->dc), [&](auto W_, auto S_, auto NC_) -> int {
+    return dispatch_tw(h->W, h->S, h->dc, [&](auto W_, auto S_, auto NC_, auto HS_) -> int {
         constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
-        if constexpr (TW_HAS_P1(W, NC))
-            if (choose_tw_ppc(h, a.B) == 1) return launch_tw(h, tw_mpc_step_kernel<W, S, NC, true>, a, a.B, W);
-        return launch_tw(h, tw_mpc_step_kernel<W, S, NC>, a, a.B, W);
+        constexpr bool HS = decltype(HS_)::value;
+        if constexpr (TW_P1_ONLY(W, NC, HS)) {
+            return launch_tw(h, tw_mpc_step_kernel<W, S, NC, true, HS>, a, a.B, W, 1);
+        } else {
+            if constexpr (TW_HAS_P1(W, NC, HS))
+                if (choose_tw_ppc(h, a.B) == 1) return launch_tw(h, tw_mpc_step_kernel<W, S, NC, true, HS>, a, a.B, W, 1);
+            return launch_tw(h, tw_mpc_step_kernel<W, S, NC, false, HS>, a, a.B, W);
+        }
     });
 }
 
@@ -774,11 +796,16 @@ int tg_closed_loop(tg_handle *h, int B, int T, const double *x0, const double *u
     memset(&a, 0, sizeof(a));
     a.B = B; a.T = T; a.x0 = x0; a.u0 = u0; a.spec = spec; a.brk = brk; a.coef = coef; a.traj_id0 = traj_id0;
     a.clean = clean; a.noisy = noisy; a.U = U; a.status_counts = status_counts; a.iters_total = (long long *)iters_total;
-    return dispatch_tw(h->W, h->S, h->dc.N, tw_generic_only(h->dc), [&](auto W_, auto S_, auto NC_) -> int {
+    return dispatch_tw(h->W, h->S, h->dc, [&](auto W_, auto S_, auto NC_, auto HS_) -> int {
         constexpr int W = decltype(W_)::value, S = decltype(S_)::value, NC = decltype(NC_)::value;
-        if constexpr (TW_HAS_P1(W, NC))
-            if (choose_tw_ppc(h, B) == 1) return launch_tw(h, tw_closed_loop_kernel<W, S, NC, true>, a, B, W);
-        return launch_tw(h, tw_closed_loop_kernel<W, S, NC>, a, B, W);
+        constexpr bool HS = decltype(HS_)::value;
+        if constexpr (TW_P1_ONLY(W, NC, HS)) {
+            return launch_tw(h, tw_closed_loop_kernel<W, S, NC, true, HS>, a, B, W, 1);
+        } else {
+            if constexpr (TW_HAS_P1(W, NC, HS))
+                if (choose_tw_ppc(h, B) == 1) return launch_tw(h, tw_closed_loop_kernel<W, S, NC, true, HS>, a, B, W, 1);
+            return launch_tw(h, tw_closed_loop_kernel<W, S, NC, false, HS>, a, B, W);
+        }
     });
 }
 

@@ -315,12 +315,12 @@ __device__ __forceinline__ void tw_ref_window_warp(const DevCfg &c, const WLayou
 // ---------------------------------------------------------------------------------------------------------------- K2
 // H = sum_k W_k' W_k on the tile (W rows carry sqrt(2 q)); optionally q and the state-bound rows.  Lane j owns column j of G;
 // with one warp and n > 32 a lane owns the columns j and j + 32, the second of which is born at stage 16.
-template <int W, int S, int NPASS, int NC>
+template <int W, int S, int NPASS, int NC, bool HS>
 __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, double *sm, const TwMap<S> &mp, double (&a)[S][4][4],
                                             bool first, int tid, int bar)
 {
     constexpr int NT = 32 * W;
-    const int N = NC > 0 ? NC : c.N, n = 2 * N, NV = LF(NV), ns = NC > 0 ? 0 : c.ns, ms_ = NC > 0 ? 0 : c.ms;   // compile-time horizons: no state rows
+    const int N = NC > 0 ? NC : c.N, n = 2 * N, NV = LF(NV), ns = HS ? c.ns : 0, ms_ = HS ? c.ms : 0;   // HS: the instance carries the code of the state-bound rows
     const double *lin = sm + LF(lin), *sn = sm + LF(sn), *cs = sm + LF(cs), *rr = sm + LF(rr);
     double *wbuf = sm + LF(wb), *Gs = sm + L.Gs;
     const double sqp = sqrt(2.0 * c.q_phi), sqv = sqrt(2.0 * c.q_vx);
@@ -467,7 +467,7 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
 }
 
 // K = H + sigma I + A' diag(rho) A on the tile (rho vectors in shared memory)
-template <int W, int S, int NC>
+template <int W, int S, int NC, bool HS>
 __device__ __forceinline__ void tw_build_K(const DevCfg &c, const WLayout &L, const double *sm, const TwMap<S> &mp, double (&a)[S][4][4])
 {
     const int n = NC > 0 ? 2 * NC : c.n, NV = LF(NV);
@@ -489,7 +489,7 @@ __device__ __forceinline__ void tw_build_K(const DevCfg &c, const WLayout &L, co
         }
     }
     const double *Gs = sm + L.Gs;
-    const int ns = NC > 0 ? 0 : c.ns, N = NC > 0 ? NC : c.N;
+    const int ns = HS ? c.ns : 0, N = NC > 0 ? NC : c.N;
     if (ns > 0)
         for (int k = 0; k < N; ++k) {
             const int len = tw_gs_len(k);
@@ -923,13 +923,13 @@ __device__ __forceinline__ double2 tw_matvec_sum(const WLayout &L, const double 
 // x <- x - K^-1 (H x + q) with K = H + O(1e-6), so two iterations land on the unconstrained optimum to ~1e-12 -- the EXACT
 // optimum of the QP whenever it satisfies every row, which the standard residual test then certifies (r_prim = 0).  As soon
 // as a row clamps, the solve falls back to the standard settings (rho, alpha) and refactors.
-template <int W, int S, int NC>
+template <int W, int S, int NC, bool HS>
 __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm, const TwMap<S> &mp, bool warm, bool warm_free,
                                    const StepTaps &tap, const FusedCtx *fx, int tid, int bar)
 {
     constexpr int NT = 32 * W;
     constexpr int NPASS = (W == 1 && S >= 2) ? 2 : 1;
-    const int N = NC > 0 ? NC : c.N, n = 2 * N, NV = LF(NV), ms = NC > 0 ? 0 : c.ms, ns = NC > 0 ? 0 : c.ns;   // kernels with a compile-time horizon serve configurations without state-bound rows
+    const int N = NC > 0 ? NC : c.N, n = 2 * N, NV = LF(NV), ms = HS ? c.ms : 0, ns = HS ? c.ns : 0;   // HS: the instance carries the code of the state-bound rows
     StepResult res;
     res.status = TG_STATUS_NAN; res.iters = 0; res.objective = 0.0; res.free_end = false;
 
@@ -1096,7 +1096,7 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
 
 #pragma unroll 1
     while (!done) {
-        tw_condense<W, S, NPASS, NC>(c, L, sm, mp, a, first, tid, bar);
+        tw_condense<W, S, NPASS, NC, HS>(c, L, sm, mp, a, first, tid, bar);
         if (first) {
 #pragma unroll
             for (int s = 0; s < S; ++s)
@@ -1160,7 +1160,7 @@ __device__ StepResult tw_step_body(const DevCfg &c, const WLayout &L, double *sm
             if (tap.stop == 2) return res;
             TG_TICK(3);
         }
-        tw_build_K<W, S, NC>(c, L, sm, mp, a);
+        tw_build_K<W, S, NC, HS>(c, L, sm, mp, a);
         tw_sweep_invert<W, S, NC>(c, L, sm, mp, a, bar);
         TG_TICK(4);
 
