@@ -230,6 +230,12 @@ class ClosedLoopGenerator(BatchedMPC):
             _lib.ptr(out["iters_total"])))
         return out
 
+    def close(self):
+        """destroys the handle and releases the cached page-locked chunk buffers"""
+        self._chunk_bufs = None
+        self._chunk_key = None
+        super().close()
+
     def _chunk_buffers(self, nb, T):
         """two page-locked result sets for chunks of nb trajectories x T steps, cached on the generator"""
         key = (int(nb), int(T))
