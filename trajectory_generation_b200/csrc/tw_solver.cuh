@@ -57,8 +57,8 @@ __device__ __forceinline__ void tg_sync(int bar, int nthreads)
 }
 
 #ifndef TW_KB
-#define TW_KB 4                  // horizon stages condensed per synchronisation in K2
-#endif
+#define TW_KB 4                  // horizon stages condensed per synchronisation in K2 (twice as many on the eight-warp, one-tile shape,
+#endif                           // N = 31 .. 44, whose synchronisations are the costliest: config 1 53.4 -> 51.8 us per step)
 #define TW_WARM_RESTART_ITER 300
 #define TW_FREE_RHO 1e-6         // rho scale of a solve that starts with no active row (see tw_step_body)
 #define TW_POLISH_MARGIN 1e-3    // a converged standard solve is polished if every row is this far inside its bounds
@@ -98,7 +98,7 @@ __host__ __device__ constexpr WLayout tw_make_layout(int N, int ms, int W)
     L.z = o; o += 2 * NV; L.y = o; o += 2 * NV; L.rho = o; o += 2 * NV + 2; L.rinv = o; o += 2 * NV + 2;   // box rows, then rate rows at + n
     L.dyr = o; o += NV + 2;
     L.piv = o; o += 2 * (4 * NV + 16);   // two panel buffers of the blocked sweep (4 columns of NV + the 4 x 4 inverse)
-    int wbn = L.nbuf * TW_KB * 3 * NV;
+    int wbn = L.nbuf * ((W >= 8 && N <= 44) ? 2 * TW_KB : TW_KB) * 3 * NV;
     if (wbn < nb * nb * 4) wbn = nb * nb * 4;
     const int k1n = tw_even(6 * N) + 4 * tw_even(N + 2);
     if (wbn < k1n) wbn = k1n;
@@ -319,6 +319,7 @@ template <int W, int S, int NPASS, int NC, bool HS>
 __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, double *sm, const TwMap<S> &mp, double (&a)[S][4][4],
                                             bool first, int tid, int bar)
 {
+    constexpr int KB = (W >= 8 && S == 1) ? 2 * TW_KB : TW_KB;   // stages per synchronisation (the layout reserves the staging rows: tw_make_layout)
     constexpr int NT = 32 * W;
     const int N = NC > 0 ? NC : c.N, n = 2 * N, NV = LF(NV), ns = HS ? c.ns : 0, ms_ = HS ? c.ms : 0;   // HS: the instance carries the code of the state-bound rows
     const double *lin = sm + LF(lin), *sn = sm + LF(sn), *cs = sm + LF(cs), *rr = sm + LF(rr);
@@ -339,7 +340,7 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
             for (int cc = 0; cc < 4; ++cc) a[s][r][cc] = 0.0;
     if (NV > n) {   // pad columns of the staging rows (and of the state rows) must read as zero
         const int np = (NV - n) > 0 ? NV - n : 1;
-        for (int i = tid; i < LF(nbuf) * TW_KB * 3 * np; i += NT) wbuf[(i / np) * NV + n + i % np] = 0.0;
+        for (int i = tid; i < LF(nbuf) * KB * 3 * np; i += NT) wbuf[(i / np) * NV + n + i % np] = 0.0;
         tw_sync<W>(bar);
     }
     if (first)   // zero pads of the packed state rows (len_k - 2 (k + 1) = 0 or 2 entries per row)
@@ -348,18 +349,18 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
             double *row = Gs + ns * tw_gs_off(k) + si * tw_gs_len(k);
             for (int j = 2 * (k + 1); j < tw_gs_len(k); ++j) row[j] = 0.0;
         }
-    // compile-time horizon that is a multiple of TW_KB: the stage loops below have a constant trip count and are unrolled, so that
+    // compile-time horizon that is a multiple of KB: the stage loops below have a constant trip count and are unrolled, so that
     // the loads of a stage are issued under the arithmetic of the previous one
-    constexpr bool FULLKB = NC > 0 && NC % TW_KB == 0;
-    constexpr int UNR = FULLKB ? TW_KB : 1;
+    constexpr bool FULLKB = NC > 0 && NC % KB == 0;
+    constexpr int UNR = FULLKB ? KB : 1;
 #ifndef TW_UNROLL_ROUNDS
 #define TW_UNROLL_ROUNDS 0   // unrolling the rounds as well measured 1 % slower (more code, no extra overlap)
 #endif
-    constexpr int UNR0 = (FULLKB && TW_UNROLL_ROUNDS) ? (NC > 0 ? NC / TW_KB : 1) : 1;
+    constexpr int UNR0 = (FULLKB && TW_UNROLL_ROUNDS) ? (NC > 0 ? NC / KB : 1) : 1;
 #pragma unroll UNR0
-    for (int k0 = 0; k0 < N; k0 += TW_KB) {
-        const int kb = FULLKB ? TW_KB : ((N - k0 < TW_KB) ? N - k0 : TW_KB);
-        double *wblk = wbuf + ((LF(nbuf) == 2) ? ((k0 / TW_KB) & 1) * TW_KB * 3 * NV : 0);
+    for (int k0 = 0; k0 < N; k0 += KB) {
+        const int kb = FULLKB ? KB : ((N - k0 < KB) ? N - k0 : KB);
+        double *wblk = wbuf + ((LF(nbuf) == 2) ? ((k0 / KB) & 1) * KB * 3 * NV : 0);
 #pragma unroll
         for (int p = 0; p < NPASS; ++p) {
             const int j = p * NT + tid;
