@@ -743,9 +743,11 @@ template <int W, int S, int NC>
 __device__ __forceinline__ void tw_sweep_invert(const DevCfg &c, const WLayout &L, double *sm, const TwMap<S> &mp,
                                                 double (&a)[S][4][4], int bar)
 {
-    // measured (profiles/r02_sweep_variants.txt): the scalar sweep is fastest for every shape -- the blocked
-    // forms save synchronisations but add fp64 work that the problems of an SM have to share the fp64 pipe for
-    constexpr int PB = TW_SWEEP_PB;
+    // measured (profiles/r02_sweep_variants.txt): with one or two warps per problem the scalar sweep is fastest
+    // (the blocked forms add fp64 work that the 7-8 problems of an SM have to share the fp64 pipe for); with four or eight warps
+    // per problem the synchronisation is costlier and the 2-pivot form wins (config 1: 52.0 -> 49.6 us per step; N = 30: +2 %);
+    // the 4-pivot form loses everywhere.  Two tiles per thread (N > 44) keep the scalar form.
+    constexpr int PB = (W >= 4 && S == 1) ? 2 : TW_SWEEP_PB;
     if constexpr (PB == 1 || (S > 1 && PB == 4)) {   // (two tiles per thread leave no registers for the 4-pivot block operands)
         tw_sweep_invert_scalar<W, S, NC>(c, L, sm, mp, a, bar);
         return;
