@@ -84,6 +84,16 @@ __host__ __device__ constexpr int tw_even(int v) { return (v + 1) & ~1; }   // k
 __host__ __device__ constexpr int tw_gs_len(int k) { return 4 * ((k >> 1) + 1); }
 __host__ __device__ constexpr int tw_gs_off(int k) { return 4 * (k >> 1) * ((k >> 1) + 1) + ((k & 1) ? 4 * ((k >> 1) + 1) : 0); }
 
+// Block vectors that every thread reads at its block row AND its block column (the pivot rows of the sweep, the staging rows of
+// the condensing) are stored PADDED: the four entries of block I at 6 I .. 6 I + 3.  The 16-byte pieces that the lanes of a warp
+// read then fall into distinct banks (stride 48 bytes: 8 block rows cover the 32 banks once) instead of colliding pairwise
+// (stride 32 bytes: block rows I and I + 4 share their banks): one wavefront per 128-bit load instead of two.
+// (Not on the two-tiles-per-thread shape, N > 44, whose constrained problems need the shared memory for their second resident
+// CTA, and not on the one-warp shape, N <= 14, where it gains nothing and costs the sixteenth resident CTA.)
+#define TW_PS(W_, S_) (((S_) >= 2 || (W_) == 1) ? 4 : 6)    // doubles per block in a padded vector
+#define TW_PAD(i, PS_) ((PS_) * ((i) >> 2) + ((i) & 3))
+__host__ __device__ constexpr int tw_ps_layout(int N, int W) { return ((W >= 8 && N > 44) || W == 1) ? 4 : 6; }   // = TW_PS(W, S) of the shape
+
 __host__ __device__ constexpr WLayout tw_make_layout(int N, int ms, int W)
 {
     WLayout L = {};
@@ -97,8 +107,8 @@ __host__ __device__ constexpr WLayout tw_make_layout(int N, int ms, int W)
     L.q = o; o += NV; L.x = o; o += NV; L.xt = o; o += NV; L.v = o; o += NV;
     L.z = o; o += 2 * NV; L.y = o; o += 2 * NV; L.rho = o; o += 2 * NV + 2; L.rinv = o; o += 2 * NV + 2;   // box rows, then rate rows at + n
     L.dyr = o; o += NV + 2;
-    L.piv = o; o += 2 * (4 * NV + 16);   // two panel buffers of the blocked sweep (4 columns of NV + the 4 x 4 inverse)
-    int wbn = L.nbuf * ((W >= 8 && N <= 44) ? 2 * TW_KB : TW_KB) * 3 * NV;
+    L.piv = o; o += 2 * (4 * tw_ps_layout(N, W) * nb + 16);   // two panel buffers of the sweep (up to 4 padded columns + the 4 x 4 inverse)
+    int wbn = L.nbuf * ((W >= 8 && N <= 44) ? 2 * TW_KB : TW_KB) * 3 * tw_ps_layout(N, W) * nb;   // padded staging rows (TW_PAD)
     if (wbn < nb * nb * 4) wbn = nb * nb * 4;
     const int k1n = tw_even(6 * N) + 4 * tw_even(N + 2);
     if (wbn < k1n) wbn = k1n;
@@ -320,6 +330,8 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
                                             bool first, int tid, int bar)
 {
     constexpr int KB = (W >= 8 && S == 1) ? 2 * TW_KB : TW_KB;   // stages per synchronisation (the layout reserves the staging rows: tw_make_layout)
+    constexpr int PS = TW_PS(W, S);
+    const int NVP = PS * LF(nb);                                  // padded length of a staging row
     constexpr int NT = 32 * W;
     const int N = NC > 0 ? NC : c.N, n = 2 * N, NV = LF(NV), ns = HS ? c.ns : 0, ms_ = HS ? c.ms : 0;   // HS: the instance carries the code of the state-bound rows
     const double *lin = sm + LF(lin), *sn = sm + LF(sn), *cs = sm + LF(cs), *rr = sm + LF(rr);
@@ -340,7 +352,7 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
             for (int cc = 0; cc < 4; ++cc) a[s][r][cc] = 0.0;
     if (NV > n) {   // pad columns of the staging rows (and of the state rows) must read as zero
         const int np = (NV - n) > 0 ? NV - n : 1;
-        for (int i = tid; i < LF(nbuf) * KB * 3 * np; i += NT) wbuf[(i / np) * NV + n + i % np] = 0.0;
+        for (int i = tid; i < LF(nbuf) * KB * 3 * np; i += NT) wbuf[(i / np) * NVP + TW_PAD(n + i % np, PS)] = 0.0;
         tw_sync<W>(bar);
     }
     if (first)   // zero pads of the packed state rows (len_k - 2 (k + 1) = 0 or 2 entries per row)
@@ -360,12 +372,12 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
 #pragma unroll UNR0
     for (int k0 = 0; k0 < N; k0 += KB) {
         const int kb = FULLKB ? KB : ((N - k0 < KB) ? N - k0 : KB);
-        double *wblk = wbuf + ((LF(nbuf) == 2) ? ((k0 / KB) & 1) * KB * 3 * NV : 0);
+        double *wblk = wbuf + ((LF(nbuf) == 2) ? ((k0 / KB) & 1) * KB * 3 * NVP : 0);
 #pragma unroll
         for (int p = 0; p < NPASS; ++p) {
             const int j = p * NT + tid;
             if (j < n && k0 + kb > (p * NT + (tid & ~31)) / 2) {   // nothing to do before the first column of this warp is born
-                const int c1 = j & 1, jb = j >> 1;
+                const int c1 = j & 1, jb = j >> 1, pj = TW_PAD(j, PS);
 #pragma unroll UNR
                 for (int s_i = 0; s_i < kb; ++s_i) {
                     const int k = k0 + s_i;
@@ -385,8 +397,8 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
                     G[p][0] = n0; G[p][1] = n1; G[p][2] = n2; G[p][3] = n3; G[p][4] = n4; G[p][5] = n5;
                     const int kk = k + 1;
                     const double wc = sn[kk] * n0 - cs[kk] * n1, wp = sqp * n2, wv = sqv * n3;   // sn, cs carry sqrt(2 q_c)
-                    double *wrow = wblk + s_i * 3 * NV;
-                    wrow[j] = wc; wrow[NV + j] = wp; wrow[2 * NV + j] = wv;
+                    double *wrow = wblk + s_i * 3 * NVP;
+                    wrow[pj] = wc; wrow[NVP + pj] = wp; wrow[2 * NVP + pj] = wv;
                     if (first) {
                         qacc[p] = fma(rr[3 * kk], wc, fma(rr[3 * kk + 1], wp, fma(rr[3 * kk + 2], wv, qacc[p])));
                         if (jb <= k)
@@ -399,8 +411,8 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
                 }
             } else if (j < n) {   // not born in this block of stages: its W entries are zero
                 for (int s_i = 0; s_i < kb; ++s_i) {
-                    double *wrow = wblk + s_i * 3 * NV;
-                    wrow[j] = 0.0; wrow[NV + j] = 0.0; wrow[2 * NV + j] = 0.0;
+                    double *wrow = wblk + s_i * 3 * NVP;
+                    wrow[TW_PAD(j, PS)] = 0.0; wrow[NVP + TW_PAD(j, PS)] = 0.0; wrow[2 * NVP + TW_PAD(j, PS)] = 0.0;
                 }
             }
         }
@@ -408,15 +420,15 @@ __device__ __forceinline__ void tw_condense(const DevCfg &c, const WLayout &L, d
 #pragma unroll UNR
         for (int s_i = 0; s_i < kb; ++s_i) {
             const int lim = 2 * (k0 + s_i) + 2;   // columns born so far
-            const double *wrow = wblk + s_i * 3 * NV;
+            const double *wrow = wblk + s_i * 3 * NVP;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 if (mp.act[s] && mp.ro[s] < lim) {   // rank-3 update of the block: 3 x (4 + 4) operands, 48 FMAs (co <= ro)
 #pragma unroll
                     for (int rI = 0; rI < 3; ++rI) {
                         double rw[4], cw[4];
-                        tw_ld4(wrow + rI * NV + mp.ro[s], rw);
-                        tw_ld4(wrow + rI * NV + mp.co[s], cw);
+                        tw_ld4(wrow + rI * NVP + (mp.ro[s] >> 2) * PS, rw);   // TW_PAD of a multiple of 4
+                        tw_ld4(wrow + rI * NVP + (mp.co[s] >> 2) * PS, cw);
 #pragma unroll
                         for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -627,10 +639,12 @@ __device__ __forceinline__ void tw_sweep_invert_scalar(const DevCfg &c, const WL
     for (int s = 0; s < S; ++s)
         if (mp.act[s] && mp.ro[s] == 0 && mp.co[s] == 0) rp_next = tw_rcp3(a[s][0][0]);
     // shared-space addresses of this thread's operands in the two pivot-row buffers (buffer = pivot parity)
-    const unsigned vb_a = tw_saddr(vb), stride_a = (unsigned)(NV + 2) * 8u;
+    constexpr unsigned PS = TW_PS(W, S);
+    const unsigned NVP = PS * (unsigned)nb;   // padded pivot rows (TW_PAD)
+    const unsigned vb_a = tw_saddr(vb), stride_a = (NVP + 2u) * 8u;
     unsigned ro_a[S], co_a[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) { ro_a[s] = vb_a + 8u * (unsigned)mp.ro[s]; co_a[s] = vb_a + 8u * (unsigned)mp.co[s]; }
+    for (int s = 0; s < S; ++s) { ro_a[s] = vb_a + 2u * PS * (unsigned)mp.ro[s]; co_a[s] = vb_a + 2u * PS * (unsigned)mp.co[s]; }
 #pragma unroll 1
     for (int K = 0; K < nb; ++K) {
         const int K4 = 4 * K;
@@ -644,14 +658,14 @@ __device__ __forceinline__ void tw_sweep_invert_scalar(const DevCfg &c, const WL
                     if (mp.act[s]) {
                         if (mp.ro[s] == K4) {          // block row K: row kr of the block is a_{k, co..co+3}
                             tw_sts4(co_a[s] + boff, a[s][kr][0], a[s][kr][1], a[s][kr][2], a[s][kr][3]);
-                            if (mp.co[s] == K4) { tw_sts1(vb_a + boff + 8u * (unsigned)k, a[s][kr][kr] - 1.0); tw_sts1(vb_a + boff + 8u * (unsigned)NV, rp_next); }
+                            if (mp.co[s] == K4) { tw_sts1(vb_a + boff + 8u * PS * (unsigned)K + 8u * (unsigned)kr, a[s][kr][kr] - 1.0); tw_sts1(vb_a + boff + 8u * NVP, rp_next); }
                         } else if (mp.co[s] == K4) {   // block column K below the diagonal: column kr is a_{ro..ro+3, k}
                             tw_sts4(ro_a[s] + boff, a[s][0][kr], a[s][1][kr], a[s][2][kr], a[s][3][kr]);
                         }
                     }
                 }
                 tw_sync<W>(bar);
-                const double p = tw_lds1(vb_a + boff + 8u * (unsigned)NV);
+                const double p = tw_lds1(vb_a + boff + 8u * NVP);
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     double vr[4], vc[4];
@@ -776,10 +790,12 @@ __device__ __forceinline__ void tw_sweep_invert(const DevCfg &c, const WLayout &
                 if (mp.ro[s] + r >= n) a[s][r][r] = 1.0;
     }
     // panel buffer of one pivot group: PB columns of NV (VT[m][i] = A_{i, P_m}) + the PB x PB inverse; two buffers, alternating
-    const unsigned vb_a = tw_saddr(vb), stride_a = (unsigned)(PB * NV + PB * PB) * 8u, nv8 = (unsigned)NV * 8u, dinv_o = (unsigned)PB * nv8;
+    constexpr unsigned PS = TW_PS(W, S);
+    const unsigned NVP = PS * (unsigned)nb;   // padded panel columns (TW_PAD)
+    const unsigned vb_a = tw_saddr(vb), stride_a = ((unsigned)PB * NVP + (unsigned)(PB * PB)) * 8u, nv8 = NVP * 8u, dinv_o = (unsigned)PB * nv8;
     unsigned ro_a[S], co_a[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) { ro_a[s] = vb_a + 8u * (unsigned)mp.ro[s]; co_a[s] = vb_a + 8u * (unsigned)mp.co[s]; }
+    for (int s = 0; s < S; ++s) { ro_a[s] = vb_a + 2u * PS * (unsigned)mp.ro[s]; co_a[s] = vb_a + 2u * PS * (unsigned)mp.co[s]; }
     // publish the panel of pivot group h (compile-time) of block K4 into the buffer at boff
     auto publish = [&](int K4, auto h_, unsigned boff) {
         constexpr int h = decltype(h_)::value, o = h * PB;
