@@ -279,3 +279,28 @@ def test_streamed_generation_equals_one_launch(tmp_path):
     gen.generate_to_csv(x0, u0, sc, T, a3, b3, traj_id0=7, chunk=32, csv_ids=40)
     tg.write_csv({k: v[:40] for k, v in one.items()}, 0.01, a, b, traj_id0=7)
     assert open(a).read() == open(a3).read() and open(b).read() == open(b3).read()
+
+
+def test_state_row_instances_ignore_the_problems_per_cta_knob(monkeypatch):
+    """Problems with state-bound rows run one per CTA on their own kernel instances (compile-time horizon N = 20 and the run-time
+    horizon N = 12 here); TRAJGEN_PPC must not change what they compute, and the horizons with and without a compile-time
+    instance must agree with each other where they can be compared (same problem, N = 20, through TRAJGEN_DYNAMIC_N)."""
+    B, T = 40, 15
+    rng = np.random.default_rng(3)
+    x0 = np.zeros((B, 6)); x0[:, 1] = rng.uniform(-1.0, 1.0, B); x0[:, 3] = rng.uniform(0.8, 1.2, B)
+    u0 = np.stack([tg.d_steady_state(x0[:, 3]), np.zeros(B)], 1)
+    sc = tg.Scenarios(B); sc.set_sine(slice(0, B), 0.5, 0.5, 0.0, 0.0)
+    for N in (20, 12):
+        ref = tg.ClosedLoopGenerator(N=N, Ts=0.02, **HARD).generate(x0, u0, sc, T)
+        monkeypatch.setenv("TRAJGEN_PPC", "4")
+        alt = tg.ClosedLoopGenerator(N=N, Ts=0.02, **HARD).generate(x0, u0, sc, T)
+        monkeypatch.delenv("TRAJGEN_PPC")
+        for k in ("clean", "U", "status_counts", "iters_total"):
+            np.testing.assert_array_equal(ref[k], alt[k], err_msg=f"N={N} {k}")
+    ref = tg.ClosedLoopGenerator(N=20, Ts=0.02, **HARD).generate(x0, u0, sc, T)
+    monkeypatch.setenv("TRAJGEN_DYNAMIC_N", "1")
+    dyn_ = tg.ClosedLoopGenerator(N=20, Ts=0.02, **HARD).generate(x0, u0, sc, T)
+    monkeypatch.delenv("TRAJGEN_DYNAMIC_N")
+    assert np.array_equal(ref["status_counts"], dyn_["status_counts"])
+    np.testing.assert_allclose(ref["clean"], dyn_["clean"], atol=1e-6)      # different instruction order, same algorithm
+    np.testing.assert_allclose(ref["U"], dyn_["U"], atol=1e-6)
